@@ -1,0 +1,163 @@
+/* b200rt.h — the drop-in boundary: a C ABI (plain pointers and sizes, no torch / C++ types) over the B200-native
+ * implementation of the reference's per-pixel path-tracing hot path.
+ *
+ * Every entry point cites the reference interface it replaces (file:line in TomClabault/SYCL-ray-tracing).
+ * The reference has no FFI of its own (it is one C++ process, source/main.cpp:63-128); the binding a maintainer adds
+ * is the C++ `RenderKernel` in sycl-ray-tracing_b200/host/dropin/ (see INTEGRATION.md), or ctypes
+ * (sycl-ray-tracing_b200/binding.py).
+ *
+ * All functions return 0 on success and a non-zero code on failure; b200rt_last_error() describes the last failure
+ * of the calling thread. There is NO CPU fallback: without a CUDA device every compute entry point fails with
+ * B200RT_ERR_CUDA.
+ *
+ * Layout contracts (trivially-copyable reference structs can be passed straight through with vector::data()):
+ *   triangles   : 9 floats  {a.xyz, b.xyz, c.xyz}                         == Triangle        include/triangle.h:67
+ *   materials   : 10 floats {emission rgba, diffuse rgba, metal, rough}   == SimpleMaterial  include/simple_material.h:6-13
+ *   spheres     : 20 bytes  {center xyz, radius, int primitive_index}     == Sphere          include/sphere.h:55-58
+ *   camera      : 17 floats {view_matrix row-major 4x4, fov_dist}         <- Camera          include/camera.h:34-39
+ *   framebuffer : w*h*4 floats RGBA, row-major, row 0 = BOTTOM row        == Image           include/image.h:25-178
+ *   env map     : env_w*env_h*4 floats RGBA, row-major                    == Image (skysphere), CDF: utils.cpp:126-142
+ */
+#ifndef B200RT_H
+#define B200RT_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B200RT_OK 0
+#define B200RT_ERR_ARG 1
+#define B200RT_ERR_CUDA 2
+#define B200RT_ERR_ALLOC 3
+
+typedef struct b200rt_bvh b200rt_bvh;      /* host-side flattened BVH (the re-laid-out FlattenedBVH) */
+typedef struct b200rt_scene b200rt_scene;  /* device-resident scene: triangles, BVH, materials, lights, env map */
+
+/* ---- FlattenedBVH -------------------------------------------------------------------------------------------------
+ * Replaces BVH::BVH + BVH::flatten() (source/bvh.cpp:19-60, include/bvh.h:211-250) and the 128-byte AoS
+ * FlattenedBVH::FlattenedNode (include/flattened_bvh.h:25-39). New layout, two parallel 64-byte-aligned streams with
+ * one record per INNER node, each record describing BOTH children (so one 64 B fetch tests two volumes):
+ *   axis[i]  : 16 floats {L.lo.xyz, L.hi.xyz, R.lo.xyz, R.hi.xyz, int L.ref, int R.ref, int L.count, int R.count}
+ *              = the 3 axis-aligned slabs of the 7-plane volume (PLANE_NORMALS[0..2], source/bvh.cpp:8-16)
+ *   diag[i]  : 16 floats {L.near[3..6], L.far[3..6], R.near[3..6], R.far[3..6]}
+ *              = the 4 diagonal slabs (PLANE_NORMALS[3..6]); only fetched when an axis test passes
+ *   ref >= 0 : index of an inner node; ref <  0 : leaf, ~ref = (first << 4) | count: triangles [first, first + count) of the leaf-ordered stream
+ *   tris[j]  : 12 floats {a.xyz, as_float(original index), e1.xyz = b-a, 0, e2.xyz = c-a, 0}   (3 x float4)
+ * Leaves hold (first, count) ranges, so the >8-triangle leaf overflow of the reference (bvh.h:226 vs
+ * flattened_bvh.h:35) cannot happen. */
+typedef struct b200rt_bvh_options
+{
+    int max_leaf_size;     /* SAH may stop at <= this many triangles per leaf; default 4, max 15 */
+    int sah_bins;          /* default 16 */
+    int use_diag_slabs;    /* 1: emit the 4 diagonal slabs (7-plane volumes); 0: axis slabs only. default 1 */
+    int num_threads;       /* builder threads; 0 = all */
+} b200rt_bvh_options;
+
+typedef struct b200rt_bvh_info
+{
+    int n_triangles, n_inner_nodes, n_leaves, max_leaf_size, max_depth, has_diag_slabs;
+    double build_seconds;
+    double sah_cost;
+} b200rt_bvh_info;
+
+void b200rt_bvh_default_options(b200rt_bvh_options* opts);
+int b200rt_bvh_build(const float* tri_xyz9, int n_tri, const b200rt_bvh_options* opts_or_null, b200rt_bvh** out);
+int b200rt_bvh_get_info(const b200rt_bvh* bvh, b200rt_bvh_info* out);
+/* borrowed pointers into the host arrays described above; valid until b200rt_bvh_destroy  (FlattenedBVH::get_nodes, flattened_bvh.h:43-44) */
+int b200rt_bvh_get_arrays(const b200rt_bvh* bvh, const float** axis16, const float** diag16, const float** tris12);
+/* structural self-check (every triangle in exactly one leaf, every child volume contains its triangles): 0 = sound */
+int b200rt_bvh_check(const b200rt_bvh* bvh, const float* tri_xyz9, int n_tri);
+void b200rt_bvh_destroy(b200rt_bvh* bvh);
+
+/* ---- scene ---------------------------------------------------------------------------------------------------------
+ * Replaces the 13-argument RenderKernel constructor's borrowed buffers (include/render_kernel.h:24-46,
+ * source/main.cpp:95-106): everything is copied to HBM once and stays resident across renders.
+ * tri_material has n_material_indices >= n_tri entries (analytic spheres index past the triangles, main.cpp:19-31).
+ * env_cdf may be NULL: it is then computed exactly as Utils::compute_env_map_cdf does (utils.cpp:126-142).
+ * bvh may be NULL: one is built with default options. device < 0 = the calling thread's current CUDA device. */
+int b200rt_scene_create(const float* tri_xyz9, int n_tri,
+                        const int* tri_material, int n_material_indices,
+                        const float* materials10, int n_materials,
+                        const int* emissive_tri, int n_emissive,
+                        const void* spheres20, int n_spheres,
+                        const float* env_rgba, int env_w, int env_h, const float* env_cdf_or_null,
+                        const b200rt_bvh* bvh_or_null, int device,
+                        b200rt_scene** out);
+void b200rt_scene_destroy(b200rt_scene* scene);
+/* replace the materials in place (C4 roughness/metalness sweeps re-use the resident geometry) */
+int b200rt_scene_set_materials(b200rt_scene* scene, const float* materials10, int n_materials);
+int b200rt_scene_get_bvh_info(const b200rt_scene* scene, b200rt_bvh_info* out);
+size_t b200rt_scene_device_bytes(const b200rt_scene* scene);
+
+/* ---- rendering -------------------------------------------------------------------------------------------------------- */
+#define B200RT_INTEGRATOR_MEGAKERNEL 0   /* one thread = one pixel, persistent warps pulling 8x4 pixel patches */
+#define B200RT_INTEGRATOR_WAVEFRONT 1    /* path-regeneration wavefront: generate/extend/shade/connect kernels */
+
+#define B200RT_FLAG_FB_IS_ZERO 1         /* caller guarantees the framebuffer is Color::Black(): skip its upload */
+#define B200RT_FLAG_SKIP_DEAD_RAYS 2     /* skip rays whose result provably cannot change the image */
+#define B200RT_FLAG_AXIS_SLABS_ONLY 4    /* ablation: ignore the 4 diagonal slabs while traversing */
+
+typedef struct b200rt_render_options
+{
+    int integrator;       /* B200RT_INTEGRATOR_* */
+    int flags;            /* B200RT_FLAG_* */
+    int rank, world;      /* this process renders the 16x16 tiles with tile_id % world == rank (default 0, 1) */
+} b200rt_render_options;
+
+typedef struct b200rt_stats
+{
+    unsigned long long rays;        /* INTERSECT_SCENE-equivalent queries traced (render_kernel.cpp:504) */
+    unsigned long long samples;     /* camera samples = pixels * spp rendered by this call */
+    double kernel_ms;               /* CUDA-event time of the render kernels on the launching stream */
+    double total_ms;                /* including host<->device copies done by this call */
+    int gpu_launches;               /* kernels launched by this call */
+    unsigned long long h2d_bytes, d2h_bytes;
+} b200rt_stats;
+
+void b200rt_default_render_options(b200rt_render_options* opts);
+
+/* Replaces RenderKernel::set_camera + RenderKernel::render (include/render_kernel.h:48,57;
+ * source/render_kernel.cpp:189-211 -> ray_trace_pixel :75-181): framebuffer_rgba_inout[i] += mean radiance, then
+ * tone-mapped in place (exposure 1.5, gamma 2.2, :167-180). Host pointers; blocking. */
+int b200rt_render(b200rt_scene* scene, const float* camera17, int width, int height, int spp, int max_bounces,
+                  float* framebuffer_rgba_inout, const b200rt_render_options* opts_or_null, b200rt_stats* stats_or_null);
+
+/* Parity hook = RenderKernel::get_camera_ray + INTERSECT_SCENE for every pixel (render_kernel.cpp:56-73, :504-511).
+ * sample < 0: un-jittered rays through (float)x,(float)y; sample >= 0: the jittered ray of that sample index of the
+ * pixel's RNG stream ONLY IF sample == 0 (later samples depend on the path lengths before them).
+ * prim_out / t_out: w*h each, row-major, -1 / -1.0f on miss. Host pointers. */
+int b200rt_trace_primary(b200rt_scene* scene, const float* camera17, int width, int height, int sample, int spp_for_seed,
+                         int* prim_out, float* t_out, const b200rt_render_options* opts_or_null, b200rt_stats* stats_or_null);
+
+/* Replaces BVH::intersect / FlattenedBVH::intersect for a batch (source/bvh.cpp:62-65, flattened_bvh.cpp:10-58):
+ * rays6 = {origin xyz, direction xyz}; extra8_or_null receives {point xyz, normal xyz, u, v} per ray. Host pointers.
+ * any_hit != 0 returns 1/0 in prim_out (any triangle or sphere hit with t > 0) instead of the closest index. */
+int b200rt_trace_rays(b200rt_scene* scene, const float* rays6, int n_rays, int any_hit,
+                      int* prim_out, float* t_out, float* extra8_or_null, const b200rt_render_options* opts_or_null);
+
+/* ---- device-pointer variants (the torch.distributed plumbing in bench.py / the multi-GPU host uses these) ------------
+ * All run on `cuda_stream` (a cudaStream_t; NULL = legacy default stream) of the scene's device and do not synchronise
+ * unless stats are requested. Tiles: the frame is cut into 16x16-pixel tiles, tile_id = ty * tiles_x + tx, owned by
+ * rank tile_id % world; each rank fills a compact tile-major float4 buffer of b200rt_tiles_for_rank() * 256 pixels. */
+int b200rt_tiles_for_rank(int width, int height, int rank, int world);
+int b200rt_render_tiles_device(b200rt_scene* scene, const float* camera17, int width, int height, int spp, int max_bounces,
+                               void* dev_tiles_rgba, const b200rt_render_options* opts_or_null, void* cuda_stream,
+                               b200rt_stats* stats_or_null);
+/* gathered: world consecutive per-rank tile buffers of tiles_per_rank_padded*256 float4 each (rank-major, as an
+ * all-gather leaves them) -> row-major bottom-up RGBA image on the device */
+int b200rt_untile_device(b200rt_scene* scene, const void* dev_gathered_tiles, int tiles_per_rank_padded, int world,
+                         int width, int height, void* dev_image_rgba, void* cuda_stream);
+int b200rt_trace_primary_device(b200rt_scene* scene, const float* camera17, int width, int height, int sample, int spp_for_seed,
+                                void* dev_prim, void* dev_t, const b200rt_render_options* opts_or_null, void* cuda_stream,
+                                b200rt_stats* stats_or_null);
+
+const char* b200rt_last_error(void);
+const char* b200rt_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,14 @@
+"""sycl-ray-tracing_b200 — B200-native (sm_100a CUDA) implementation of the per-pixel path-tracing hot path of
+TomClabault/SYCL-ray-tracing behind the reference's RenderKernel / Camera / Image / SimpleMaterial / FlattenedBVH API.
+
+Import as `sycl_ray_tracing_b200` (see sycl_ray_tracing_b200.py at the repo root: the directory name carries a hyphen).
+"""
+from . import binding
+from .api import (BVH, Camera, FlattenedBVH, Identity, Image, RenderKernel, RotationX, RotationY, Scene, SimpleMaterial,
+                  Translation, compute_env_map_cdf, constant_env, materials_to_array)
+from .binding import (B200RTError, FLAG_AXIS_SLABS_ONLY, FLAG_FB_IS_ZERO, FLAG_SKIP_DEAD_RAYS, INTEGRATOR_MEGAKERNEL,
+                      INTEGRATOR_WAVEFRONT, load_library, tiles_for_rank)
+
+__all__ = ["BVH", "Camera", "FlattenedBVH", "Identity", "Image", "RenderKernel", "RotationX", "RotationY", "Scene",
+           "SimpleMaterial", "Translation", "compute_env_map_cdf", "constant_env", "materials_to_array", "B200RTError",
+           "load_library", "tiles_for_rank", "binding"]

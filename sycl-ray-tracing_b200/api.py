@@ -1,0 +1,386 @@
+"""Host-side mirror of the reference's operator interface for the path-tracing hot path.
+
+Same names, argument order and meaning as the reference's C++ classes, so tests read like the reference's own:
+
+    RenderKernel(width, height, render_samples, max_bounces, image_buffer, triangle_buffer, materials_buffer,
+                 emissive_triangle_indices, materials_indices, sphere_buffer, bvh, skysphere, env_map_cdf)
+        .set_camera(camera) / .render()            include/render_kernel.h:24-57, source/main.cpp:95-113
+    Camera(fov, transform) + presets                 include/camera.h:10-40, source/camera.cpp:3-8
+    Image(w, h)                                      include/image.h:25-178
+    SimpleMaterial                                   include/simple_material.h:6-13
+    BVH(triangles).flatten() -> FlattenedBVH         include/bvh.h:263-280, include/flattened_bvh.h:12-48
+    compute_env_map_cdf(image)                       source/utils.cpp:126-142
+
+Everything that computes goes through the C ABI of include/b200rt.h to the CUDA kernels; nothing here has a CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass, field
+
+import numpy as np
+
+from . import binding as B
+
+
+def _f32(x):
+    return np.ascontiguousarray(x, dtype=np.float32)
+
+
+# ---- Camera (camera.h:10-40) -----------------------------------------------------------------------------------------
+def _hexrow(vals):
+    return np.array([float.fromhex(v) for v in vals], dtype=np.float32)
+
+
+# the reference's presets (camera.cpp:4-8), bit-exact as the compiled reference produces them (sinf/cosf/tan on the host)
+_PRESETS = {
+    "CORNELL_BOX_CAMERA": ['0x1p+0', '0x0p+0', '0x0p+0', '0x0p+0', '0x0p+0', '0x1p+0', '0x0p+0', '0x1p+0', '0x0p+0', '0x0p+0',
+                           '-0x1p+0', '0x1.cp+1', '0x0p+0', '0x0p+0', '0x0p+0', '0x1p+0', '0x1.3504f2p+1'],
+    "GANESHA_CAMERA": ['0x1p+0', '0x0p+0', '0x0p+0', '-0x1.4fdf3cp-6', '0x0p+0', '0x1.ee8dd4p-1', '-0x1.0907dcp-2', '0x1.cfddd6p-1',
+                       '0x0p+0', '-0x1.0907dcp-2', '-0x1.ee8dd4p-1', '0x1.95c4ccp-1', '0x0p+0', '0x0p+0', '0x0p+0', '0x1p+0', '0x1.3504f2p+1'],
+    "ITE_ORB_CAMERA": ['0x1p+0', '0x0p+0', '0x0p+0', '0x0p+0', '0x0p+0', '0x1.6a09e6p-1', '-0x1.6a09e6p-1', '0x1.2aae9p+0',
+                       '0x0p+0', '-0x1.6a09e6p-1', '-0x1.6a09e6p-1', '0x1.e8c09p-1', '0x0p+0', '0x0p+0', '0x0p+0', '0x1p+0', '0x1.3504f2p+1'],
+    "PBRT_DRAGON_CAMERA": ['0x1p+0', '0x0p+0', '0x0p+0', '0x0p+0', '0x0p+0', '0x1.6a09e6p-1', '-0x1.6a09e6p-1', '0x1.adebc2p+2',
+                           '0x0p+0', '-0x1.6a09e6p-1', '-0x1.6a09e6p-1', '0x1.04371ep+3', '0x0p+0', '0x0p+0', '0x0p+0', '0x1p+0', '0x1.3504f2p+1'],
+    "MIS_CAMERA": ['0x1p+0', '0x0p+0', '0x0p+0', '0x0p+0', '0x0p+0', '0x1.f838b8p-1', '-0x1.63a1a8p-3', '-0x1.2190e8p+0',
+                   '0x0p+0', '-0x1.63a1a8p-3', '-0x1.f838b8p-1', '0x1.5b90ccp+3', '0x0p+0', '0x0p+0', '0x0p+0', '0x1p+0', '0x1.3504f2p+1'],
+}
+
+
+def Identity():
+    return np.eye(4, dtype=np.float32)
+
+
+def Translation(x, y, z):
+    m = np.eye(4, dtype=np.float32)
+    m[0, 3], m[1, 3], m[2, 3] = x, y, z
+    return m
+
+
+def _rot(angle_deg):
+    a = np.float32(np.float32(np.pi) / np.float32(180.0)) * np.float32(angle_deg)     # radians(), mat.cpp:10-13
+    return np.float32(np.sin(a)), np.float32(np.cos(a))
+
+
+def RotationX(angle_deg):
+    s, c = _rot(angle_deg)
+    return np.array([[1, 0, 0, 0], [0, c, -s, 0], [0, s, c, 0], [0, 0, 0, 1]], dtype=np.float32)
+
+
+def RotationY(angle_deg):
+    s, c = _rot(angle_deg)
+    return np.array([[c, 0, s, 0], [0, 1, 0, 0], [-s, 0, c, 0], [0, 0, 0, 1]], dtype=np.float32)
+
+
+def compose_transform(a, b):
+    """Transform * Transform in float32, term order of mat.cpp:365-373."""
+    a, b = _f32(a), _f32(b)
+    m = np.zeros((4, 4), np.float32)
+    for i in range(4):
+        for j in range(4):
+            acc = np.float32(a[i, 0] * b[0, j])
+            for k in range(1, 4):
+                acc = np.float32(acc + np.float32(a[i, k] * b[k, j]))
+            m[i, j] = acc
+    return m
+
+
+class Camera:
+    """view_matrix = transformation * diag(1,1,-1); fov_dist = 1 / tan(fov/2) (camera.h:27-39)."""
+
+    DEFAULT_COORDINATES_SYSTEM = np.diag([1.0, 1.0, -1.0, 1.0]).astype(np.float32)
+
+    def __init__(self, full_fov: float = 45.0, transformation=None):
+        t = Identity() if transformation is None else _f32(transformation)
+        self.view_matrix = compose_transform(t, Camera.DEFAULT_COORDINATES_SYSTEM)
+        self.fov = float(full_fov)
+        rad = np.float32(np.float64(np.float32(full_fov) / np.float32(180.0)) * np.pi)   # fov / 180.0f * M_PI (double), to float
+        self.fov_dist = np.float32(np.float32(1.0) / np.float32(np.tan(np.float32(rad / np.float32(2.0)))))
+
+    @classmethod
+    def from_array17(cls, a17):
+        cam = cls.__new__(cls)
+        a17 = _f32(a17)
+        cam.view_matrix = a17[:16].reshape(4, 4).copy()
+        cam.fov_dist = np.float32(a17[16])
+        cam.fov = 45.0
+        return cam
+
+    def as_array17(self) -> np.ndarray:
+        return np.concatenate([_f32(self.view_matrix).reshape(16), np.array([self.fov_dist], np.float32)])
+
+
+for _name, _vals in _PRESETS.items():
+    setattr(Camera, _name, Camera.from_array17(_hexrow(_vals)))
+
+
+# ---- Image (image.h:25-178) ----------------------------------------------------------------------------------------------
+class Image:
+    """RGBA float32, row-major, row 0 = bottom. Image(w, h) starts as Color::Black() = (0, 0, 0, 1)."""
+
+    def __init__(self, w: int = 0, h: int = 0, color=(0.0, 0.0, 0.0, 1.0), data=None):
+        if data is not None:
+            d = _f32(data)
+            assert d.ndim == 3 and d.shape[2] == 4
+            self.pixels = d
+        else:
+            self.pixels = np.empty((h, w, 4), np.float32)
+            self.pixels[...] = np.asarray(color, np.float32)
+
+    def width(self):
+        return self.pixels.shape[1]
+
+    def height(self):
+        return self.pixels.shape[0]
+
+    def data(self):
+        return self.pixels
+
+    def __getitem__(self, index):
+        return self.pixels.reshape(-1, 4)[index]
+
+
+@dataclass
+class SimpleMaterial:
+    """simple_material.h:6-13 (defaults included)."""
+    emission: tuple = (0.0, 0.0, 0.0)
+    diffuse: tuple = (1.0, 0.2, 0.7)
+    metalness: float = 0.0
+    roughness: float = 1.0
+
+    def as_array10(self):
+        e, d = tuple(self.emission)[:3], tuple(self.diffuse)[:3]
+        return np.array([e[0], e[1], e[2], 1.0, d[0], d[1], d[2], 1.0, self.metalness, self.roughness], np.float32)
+
+
+def materials_to_array(materials) -> np.ndarray:
+    if isinstance(materials, np.ndarray):
+        return _f32(materials).reshape(-1, 10)
+    return np.stack([m.as_array10() for m in materials]).astype(np.float32)
+
+
+def compute_env_map_cdf(skysphere: "Image | np.ndarray") -> np.ndarray:
+    """Utils::compute_env_map_cdf (utils.cpp:126-142): serial float32 running sum of the per-texel luminance, whose
+    weights are double constants (image.h:84)."""
+    px = skysphere.pixels if isinstance(skysphere, Image) else _f32(skysphere)
+    p = px.reshape(-1, 4).astype(np.float64)
+    lum = (0.3086 * p[:, 0] + 0.6094 * p[:, 1] + 0.0820 * p[:, 2]).astype(np.float32)
+    return np.cumsum(lum, dtype=np.float32)          # add.accumulate in float32 == the reference's serial loop
+
+
+# ---- BVH / FlattenedBVH ---------------------------------------------------------------------------------------------------
+class BVH:
+    """BVH(std::vector<Triangle>*) (bvh.cpp:19-37). Holds the host-side flattened tree built by the C library."""
+
+    def __init__(self, triangles, max_leaf_size: int = 4, use_diag_slabs: bool = True, sah_bins: int = 16, num_threads: int = 0):
+        L = B.load_library()
+        self.triangles = _f32(triangles).reshape(-1, 9)
+        opts = B.BvhOptions(max_leaf_size, sah_bins, 1 if use_diag_slabs else 0, num_threads)
+        h = C.c_void_p()
+        B.check(L.b200rt_bvh_build(B.fptr(self.triangles), len(self.triangles), C.byref(opts), C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                B.load_library().b200rt_bvh_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def info(self) -> dict:
+        out = B.BvhInfo()
+        B.check(B.load_library().b200rt_bvh_get_info(self._h, C.byref(out)))
+        return out.as_dict()
+
+    def check(self) -> None:
+        B.check(B.load_library().b200rt_bvh_check(self._h, B.fptr(self.triangles), len(self.triangles)))
+
+    def flatten(self) -> "FlattenedBVH":
+        return FlattenedBVH(self)
+
+
+class FlattenedBVH:
+    """The re-laid-out FlattenedBVH (flattened_bvh.h:12-48): numpy views of the 64-byte axis / diag records and the
+    leaf-ordered triangle stream. `intersect` runs the CUDA traversal (there is no host traversal)."""
+
+    def __init__(self, bvh: BVH):
+        self.bvh = bvh
+        L = B.load_library()
+        info = bvh.info()
+        FP = C.POINTER(C.c_float)
+        a, d, t = FP(), FP(), FP()
+        B.check(L.b200rt_bvh_get_arrays(bvh._h, C.byref(a), C.byref(d), C.byref(t)))
+        n = info["n_inner_nodes"]
+        self.axis = np.ctypeslib.as_array(a, shape=(n, 16))
+        self.diag = np.ctypeslib.as_array(d, shape=(n, 16))
+        self.tris = np.ctypeslib.as_array(t, shape=(max(info["n_triangles"], 0), 12)) if info["n_triangles"] else np.zeros((0, 12), np.float32)
+
+    def get_nodes(self):
+        return self.axis, self.diag
+
+    def intersect(self, rays6, triangles=None, any_hit: bool = False):
+        """Batch version of FlattenedBVH::intersect(ray, hit_info, triangles): returns (prim, t, extra8)."""
+        tri = self.bvh.triangles if triangles is None else _f32(triangles).reshape(-1, 9)
+        scene = Scene(tri, np.zeros(len(tri), np.int32), materials_to_array([SimpleMaterial()]), np.zeros(0, np.int32),
+                      bvh=self.bvh)
+        return scene.trace_rays(rays6, any_hit=any_hit)
+
+
+# ---- device-resident scene ---------------------------------------------------------------------------------------------------
+_DIM_ENV = None
+
+
+def constant_env(value: float = 1.0e-20, w: int = 4, h: int = 2) -> np.ndarray:
+    """"No environment map" for the reference means a constant, negligibly dim one (an all-zero map makes its CDF
+    sampling divide 0/0 — SURVEY §8c)."""
+    e = np.full((h, w, 4), value, np.float32)
+    e[..., 3] = 0.0
+    return e
+
+
+class Scene:
+    def __init__(self, triangles, materials_indices, materials, emissive_triangle_indices, spheres=None, skysphere=None,
+                 env_map_cdf=None, bvh: BVH | None = None, device: int = -1):
+        L = B.load_library()
+        self.tri = _f32(triangles).reshape(-1, 9)
+        self.mat_idx = np.ascontiguousarray(materials_indices, np.int32)
+        self.mats = materials_to_array(materials)
+        self.emissive = np.ascontiguousarray(emissive_triangle_indices, np.int32)
+        sph = np.zeros(0, np.uint8)
+        n_sph = 0
+        if spheres is not None and len(spheres):
+            rec = np.zeros(len(spheres), dtype=[("c", np.float32, 3), ("r", np.float32), ("prim", np.int32)])
+            for i, s in enumerate(spheres):
+                rec[i] = (tuple(s[0]), s[1], s[2])
+            sph = rec.view(np.uint8)
+            n_sph = len(spheres)
+        env = constant_env() if skysphere is None else (skysphere.pixels if isinstance(skysphere, Image) else _f32(skysphere))
+        assert env.ndim == 3 and env.shape[2] == 4
+        self.env = np.ascontiguousarray(env)
+        cdf = None if env_map_cdf is None else _f32(env_map_cdf)
+        h = C.c_void_p()
+        B.check(L.b200rt_scene_create(
+            B.fptr(self.tri), len(self.tri), B.iptr(self.mat_idx), len(self.mat_idx), B.fptr(self.mats), len(self.mats),
+            B.iptr(self.emissive), len(self.emissive), sph.ctypes.data_as(C.c_void_p) if n_sph else None, n_sph,
+            B.fptr(self.env), self.env.shape[1], self.env.shape[0], B.fptr(cdf), bvh._h if bvh is not None else None,
+            device, C.byref(h)))
+        self._h = h
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                B.load_library().b200rt_scene_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def bvh_info(self) -> dict:
+        out = B.BvhInfo()
+        B.check(B.load_library().b200rt_scene_get_bvh_info(self._h, C.byref(out)))
+        return out.as_dict()
+
+    def device_bytes(self) -> int:
+        return int(B.load_library().b200rt_scene_device_bytes(self._h))
+
+    def set_materials(self, materials) -> None:
+        self.mats = materials_to_array(materials)
+        B.check(B.load_library().b200rt_scene_set_materials(self._h, B.fptr(self.mats), len(self.mats)))
+
+    @staticmethod
+    def _opts(integrator=0, flags=0, rank=0, world=1):
+        return B.RenderOptions(integrator, flags, rank, world)
+
+    def render(self, camera: Camera, w: int, h: int, spp: int, max_bounces: int, framebuffer: np.ndarray | None = None,
+               integrator: int = 0, flags: int = 0, rank: int = 0, world: int = 1):
+        """RenderKernel::render() on host buffers. Returns (framebuffer, stats)."""
+        if framebuffer is None:
+            framebuffer = Image(w, h).pixels
+            flags |= B.FLAG_FB_IS_ZERO if world == 1 else 0
+        assert framebuffer.dtype == np.float32 and framebuffer.shape == (h, w, 4) and framebuffer.flags["C_CONTIGUOUS"]
+        st = B.Stats()
+        o = self._opts(integrator, flags, rank, world)
+        B.check(B.load_library().b200rt_render(self._h, B.fptr(camera.as_array17()), w, h, spp, max_bounces,
+                                               B.fptr(framebuffer), C.byref(o), C.byref(st)))
+        return framebuffer, st.as_dict()
+
+    def trace_primary(self, camera: Camera, w: int, h: int, sample: int = -1, spp_for_seed: int = 1, flags: int = 0,
+                      rank: int = 0, world: int = 1):
+        prim = np.zeros((h, w), np.int32)
+        t = np.zeros((h, w), np.float32)
+        st = B.Stats()
+        o = self._opts(0, flags, rank, world)
+        B.check(B.load_library().b200rt_trace_primary(self._h, B.fptr(camera.as_array17()), w, h, sample, spp_for_seed,
+                                                      B.iptr(prim), B.fptr(t), C.byref(o), C.byref(st)))
+        return prim, t, st.as_dict()
+
+    def trace_rays(self, rays6, any_hit: bool = False, flags: int = 0):
+        rays6 = _f32(rays6).reshape(-1, 6)
+        n = len(rays6)
+        prim = np.zeros(n, np.int32)
+        t = np.zeros(n, np.float32)
+        extra = np.zeros((n, 8), np.float32)
+        o = self._opts(0, flags)
+        B.check(B.load_library().b200rt_trace_rays(self._h, B.fptr(rays6), n, 1 if any_hit else 0, B.iptr(prim), B.fptr(t),
+                                                   B.fptr(extra), C.byref(o)))
+        return prim, t, extra
+
+    # device-pointer variants (pointers are plain ints, e.g. torch.Tensor.data_ptr())
+    def render_tiles_device(self, camera: Camera, w, h, spp, max_bounces, dev_tiles_ptr: int, stream_ptr: int = 0,
+                            integrator: int = 0, flags: int = 0, rank: int = 0, world: int = 1, want_stats: bool = False):
+        st = B.Stats()
+        o = self._opts(integrator, flags, rank, world)
+        B.check(B.load_library().b200rt_render_tiles_device(self._h, B.fptr(camera.as_array17()), w, h, spp, max_bounces,
+                                                            C.c_void_p(dev_tiles_ptr), C.byref(o), C.c_void_p(stream_ptr),
+                                                            C.byref(st) if want_stats else None))
+        return st.as_dict() if want_stats else None
+
+    def untile_device(self, dev_gathered_ptr: int, tiles_per_rank_padded: int, world: int, w: int, h: int, dev_image_ptr: int,
+                      stream_ptr: int = 0):
+        B.check(B.load_library().b200rt_untile_device(self._h, C.c_void_p(dev_gathered_ptr), tiles_per_rank_padded, world, w, h,
+                                                      C.c_void_p(dev_image_ptr), C.c_void_p(stream_ptr)))
+
+    def trace_primary_device(self, camera: Camera, w, h, dev_prim_ptr: int, dev_t_ptr: int, sample: int = -1,
+                             spp_for_seed: int = 1, stream_ptr: int = 0, flags: int = 0, rank: int = 0, world: int = 1,
+                             want_stats: bool = False):
+        st = B.Stats()
+        o = self._opts(0, flags, rank, world)
+        B.check(B.load_library().b200rt_trace_primary_device(self._h, B.fptr(camera.as_array17()), w, h, sample, spp_for_seed,
+                                                             C.c_void_p(dev_prim_ptr), C.c_void_p(dev_t_ptr), C.byref(o),
+                                                             C.c_void_p(stream_ptr), C.byref(st) if want_stats else None))
+        return st.as_dict() if want_stats else None
+
+
+# ---- RenderKernel (render_kernel.h:21-96) ----------------------------------------------------------------------------------------
+class RenderKernel:
+    """Same 13-argument constructor, set_camera() and render() as the reference's RenderKernel. Buffers are borrowed
+    (the reference stores references, render_kernel.h:81-93); the device scene is created on the first render()."""
+
+    def __init__(self, width, height, render_samples, max_bounces, image_buffer: Image, triangle_buffer, materials_buffer,
+                 emissive_triangle_indices, materials_indices, analytic_spheres=None, bvh: BVH | None = None,
+                 skysphere: Image | None = None, env_map_cdf=None, integrator: int = B.INTEGRATOR_MEGAKERNEL, flags: int = 0):
+        self.m_width, self.m_height = int(width), int(height)
+        self.m_render_samples, self.m_max_bounces = int(render_samples), int(max_bounces)
+        self.m_frame_buffer = image_buffer
+        self._args = (triangle_buffer, materials_indices, materials_buffer, emissive_triangle_indices, analytic_spheres, skysphere,
+                      env_map_cdf, bvh)
+        self.m_camera = Camera()
+        self.integrator, self.flags = integrator, flags
+        self._scene = None
+        self.last_stats = None
+
+    def set_camera(self, camera: Camera):
+        self.m_camera = camera
+
+    def scene(self) -> Scene:
+        if self._scene is None:
+            tri, mi, mats, em, sph, sky, cdf, bvh = self._args
+            self._scene = Scene(tri, mi, mats, em, spheres=sph, skysphere=sky, env_map_cdf=cdf, bvh=bvh)
+        return self._scene
+
+    def render(self):
+        # the reference iterates the framebuffer's own size (render_kernel.cpp:199-201)
+        fb = self.m_frame_buffer.pixels
+        assert fb.shape == (self.m_height, self.m_width, 4), "framebuffer size must match width x height"
+        _, self.last_stats = self.scene().render(self.m_camera, self.m_width, self.m_height, self.m_render_samples,
+                                                 self.m_max_bounces, framebuffer=fb, integrator=self.integrator, flags=self.flags)

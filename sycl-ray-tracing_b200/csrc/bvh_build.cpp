@@ -1,0 +1,416 @@
+// Binned-SAH BVH2 builder emitting the 64-byte two-stream FlattenedBVH layout (see bvh_build.h, include/b200rt.h).
+#include "bvh_build.h"
+
+#include <algorithm>
+#include <atomic>
+#include <chrono>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include <omp.h>
+
+namespace b200rt {
+namespace {
+
+constexpr float kInf = std::numeric_limits<float>::infinity();
+
+struct Box
+{
+    float lo[3] = { kInf, kInf, kInf };
+    float hi[3] = { -kInf, -kInf, -kInf };
+    void grow(const float* p) { for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], p[a]); hi[a] = std::max(hi[a], p[a]); } }
+    void grow(const Box& b) { for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], b.lo[a]); hi[a] = std::max(hi[a], b.hi[a]); } }
+    float half_area() const
+    {
+        float dx = hi[0] - lo[0], dy = hi[1] - lo[1], dz = hi[2] - lo[2];
+        if (!(dx >= 0.0f) || !(dy >= 0.0f) || !(dz >= 0.0f)) return 0.0f;
+        return dx * dy + dy * dz + dz * dx;
+    }
+};
+
+struct Prim { Box box; float c[3]; };
+
+struct BuildNode
+{
+    Box box;
+    int left = -1, right = -1;   // children (build-node indices) or -1
+    int first = 0, count = 0;    // range in the permuted index array (leaves)
+};
+
+struct Builder
+{
+    const std::vector<Prim>& prims;
+    std::vector<int>& order;
+    std::vector<BuildNode> nodes;
+    std::atomic<int> n_nodes{ 0 };
+    int max_leaf, bins;
+
+    Builder(const std::vector<Prim>& p, std::vector<int>& o, int max_leaf_, int bins_)
+        : prims(p), order(o), nodes(2 * p.size() + 2), max_leaf(max_leaf_), bins(bins_) {}
+
+    int alloc() { return n_nodes.fetch_add(1); }
+
+    void make_leaf(int me, int first, int count) { nodes[me].first = first; nodes[me].count = count; nodes[me].left = nodes[me].right = -1; }
+
+    void build(int me, int first, int count, int depth)
+    {
+        Box box, cbox;
+        for (int i = first; i < first + count; i++)
+        {
+            const Prim& p = prims[order[i]];
+            box.grow(p.box);
+            cbox.grow(p.c);
+        }
+        nodes[me].box = box;
+        if (count <= 1) { make_leaf(me, first, count); return; }
+
+        int split = -1;   // number of primitives going left
+        const bool force_median = depth >= 28;   // keeps total depth < kMaxTraversalDepth for any input
+        if (!force_median)
+        {
+            // binned SAH over all three axes
+            float best_cost = kInf; int best_axis = -1, best_bin = -1;
+            const int B = bins;
+            for (int axis = 0; axis < 3; axis++)
+            {
+                float cmin = cbox.lo[axis], cmax = cbox.hi[axis];
+                if (!(cmax > cmin)) continue;
+                float scale = B / (cmax - cmin);
+                Box bbox[32]; int bcount[32];
+                for (int b = 0; b < B; b++) bcount[b] = 0;
+                for (int i = first; i < first + count; i++)
+                {
+                    const Prim& p = prims[order[i]];
+                    int b = std::min(B - 1, std::max(0, (int)((p.c[axis] - cmin) * scale)));
+                    bbox[b].grow(p.box); bcount[b]++;
+                }
+                float right_area[32]; int right_cnt[32];
+                Box acc; int cnt = 0;
+                for (int b = B - 1; b > 0; b--) { acc.grow(bbox[b]); cnt += bcount[b]; right_area[b] = acc.half_area(); right_cnt[b] = cnt; }
+                Box lacc; int lcnt = 0;
+                for (int b = 0; b < B - 1; b++)
+                {
+                    lacc.grow(bbox[b]); lcnt += bcount[b];
+                    if (lcnt == 0 || right_cnt[b + 1] == 0) continue;
+                    float cost = lacc.half_area() * lcnt + right_area[b + 1] * right_cnt[b + 1];
+                    if (cost < best_cost) { best_cost = cost; best_axis = axis; best_bin = b; }
+                }
+            }
+            float parent_area = box.half_area();
+            float leaf_cost = (float)count;
+            float split_cost = parent_area > 0.0f ? 1.0f + best_cost / parent_area : kInf;
+            if (best_axis >= 0 && (count > max_leaf || split_cost < leaf_cost))
+            {
+                float cmin = cbox.lo[best_axis], cmax = cbox.hi[best_axis];
+                float scale = bins / (cmax - cmin);
+                int* b = order.data() + first;
+                int* mid = std::partition(b, b + count, [&](int id) {
+                    int bin = std::min(bins - 1, std::max(0, (int)((prims[id].c[best_axis] - cmin) * scale)));
+                    return bin <= best_bin;
+                });
+                split = (int)(mid - b);
+            }
+            else if (count <= max_leaf) { make_leaf(me, first, count); return; }
+        }
+        if (split <= 0 || split >= count)
+        {
+            // object median along the widest centroid axis (degenerate SAH, or the depth guard)
+            int axis = 0;
+            for (int a = 1; a < 3; a++) if (cbox.hi[a] - cbox.lo[a] > cbox.hi[axis] - cbox.lo[axis]) axis = a;
+            if (count <= max_leaf && !(cbox.hi[axis] > cbox.lo[axis])) { make_leaf(me, first, count); return; }
+            split = count / 2;
+            int* b = order.data() + first;
+            std::nth_element(b, b + split, b + count, [&](int x, int y) { return prims[x].c[axis] < prims[y].c[axis]; });
+        }
+        int l = alloc(), r = alloc();
+        nodes[me].left = l; nodes[me].right = r;
+        if (count > 20000)
+        {
+#pragma omp task default(shared) firstprivate(l, first, split, depth)
+            build(l, first, split, depth + 1);
+#pragma omp task default(shared) firstprivate(r, first, split, count, depth)
+            build(r, first + split, count - split, depth + 1);
+#pragma omp taskwait
+        }
+        else
+        {
+            build(l, first, split, depth + 1);
+            build(r, first + split, count - split, depth + 1);
+        }
+    }
+};
+
+// leaf reference: ~((first << 4) | count), count in 0..15 — one int carries the whole triangle range
+inline int leaf_ref(int first, int count) { return ~((first << 4) | count); }
+
+struct Slabs
+{
+    float lo[3], hi[3], dnear[4], dfar[4];
+    void reset()
+    {
+        for (int a = 0; a < 3; a++) { lo[a] = kInf; hi[a] = -kInf; }
+        for (int k = 0; k < 4; k++) { dnear[k] = kInf; dfar[k] = -kInf; }
+    }
+    void grow_point(const float* p)
+    {
+        for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], p[a]); hi[a] = std::max(hi[a], p[a]); }
+        for (int k = 0; k < 4; k++)
+        {
+            // exact in double (three floats sum without error in 53 bits for any sane exponent spread), rounded outward below
+            double d = 0.0;
+            switch (k)
+            {
+            case 0: d = (double)p[0] + (double)p[1] + (double)p[2]; break;
+            case 1: d = -(double)p[0] + (double)p[1] + (double)p[2]; break;
+            case 2: d = -(double)p[0] - (double)p[1] + (double)p[2]; break;
+            default: d = (double)p[0] - (double)p[1] + (double)p[2]; break;
+            }
+            float f = (float)d;
+            float fl = ((double)f > d) ? std::nextafter(f, -kInf) : f;
+            float fh = ((double)f < d) ? std::nextafter(f, kInf) : f;
+            dnear[k] = std::min(dnear[k], fl);
+            dfar[k] = std::max(dfar[k], fh);
+        }
+    }
+    void grow(const Slabs& s)
+    {
+        for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], s.lo[a]); hi[a] = std::max(hi[a], s.hi[a]); }
+        for (int k = 0; k < 4; k++) { dnear[k] = std::min(dnear[k], s.dnear[k]); dfar[k] = std::max(dfar[k], s.dfar[k]); }
+    }
+};
+
+struct Flattener
+{
+    const Builder& b;
+    const float* tri9;
+    FlatBVH& out;
+    float abs_pad;
+    int max_depth = 0, n_leaves = 0, max_leaf = 0;
+    double sah = 0.0;
+
+    // emits the triangles of a leaf, returns its first slot
+    int emit_leaf(const BuildNode& n, Slabs& s)
+    {
+        int first = (int)out.tris.size();
+        s.reset();
+        for (int i = 0; i < n.count; i++)
+        {
+            int id = b.order[n.first + i];
+            const float* p = tri9 + 9 * (size_t)id;
+            LeafTriangle t;
+            for (int a = 0; a < 3; a++)
+            {
+                t.a[a] = p[a];
+                t.e1[a] = p[3 + a] - p[a];
+                t.e2[a] = p[6 + a] - p[a];
+            }
+            t.prim = id; t.pad1 = 0.0f; t.pad2 = 0.0f;
+            out.tris.push_back(t);
+            s.grow_point(p); s.grow_point(p + 3); s.grow_point(p + 6);
+        }
+        n_leaves++;
+        max_leaf = std::max(max_leaf, n.count);
+        return first;
+    }
+
+    void store_child(AxisNode& an, DiagNode& dn, bool left, const Slabs& s, int ref, int count)
+    {
+        float* lo = left ? an.l_lo : an.r_lo;
+        float* hi = left ? an.l_hi : an.r_hi;
+        float* dnear = left ? dn.l_near : dn.r_near;
+        float* dfar = left ? dn.l_far : dn.r_far;
+        for (int a = 0; a < 3; a++)
+        {
+            // pad: the (float) slab test must never reject a volume whose triangle the exact test accepts
+            float pad = 1e-5f * std::max(std::fabs(s.lo[a]), std::fabs(s.hi[a])) + abs_pad;
+            lo[a] = s.lo[a] - pad; hi[a] = s.hi[a] + pad;
+        }
+        for (int k = 0; k < 4; k++)
+        {
+            float pad = 1e-5f * std::max(std::fabs(s.dnear[k]), std::fabs(s.dfar[k])) + 2.0f * abs_pad;
+            dnear[k] = s.dnear[k] - pad; dfar[k] = s.dfar[k] + pad;
+        }
+        if (left) { an.l_ref = ref; an.l_count = count; } else { an.r_ref = ref; an.r_count = count; }
+    }
+
+    // returns the child reference for build node `bn` and fills its slabs
+    int flatten(int bn, int depth, Slabs& s, int& count_out)
+    {
+        const BuildNode& n = b.nodes[bn];
+        max_depth = std::max(max_depth, depth);
+        if (n.left < 0)
+        {
+            int first = emit_leaf(n, s);
+            count_out = n.count;
+            return leaf_ref(first, n.count);
+        }
+        int me = (int)out.axis.size();
+        out.axis.emplace_back();
+        out.diag.emplace_back();
+        Slabs ls, rs; int lc = 0, rc = 0;
+        int lref = flatten(n.left, depth + 1, ls, lc);
+        int rref = flatten(n.right, depth + 1, rs, rc);
+        store_child(out.axis[me], out.diag[me], true, ls, lref, lc);
+        store_child(out.axis[me], out.diag[me], false, rs, rref, rc);
+        s = ls; s.grow(rs);
+        count_out = 0;
+        return me;
+    }
+};
+
+} // namespace
+
+void build_flat_bvh(const float* tri9, int n_tri, const b200rt_bvh_options& opts, FlatBVH& out)
+{
+    auto t0 = std::chrono::high_resolution_clock::now();
+    out.axis.clear(); out.diag.clear(); out.tris.clear();
+    const int max_leaf = std::min(15, std::max(1, opts.max_leaf_size > 0 ? opts.max_leaf_size : 4));
+    const int bins = std::min(32, std::max(4, opts.sah_bins > 0 ? opts.sah_bins : 16));
+
+    std::vector<Prim> prims((size_t)n_tri);
+    std::vector<int> order((size_t)n_tri);
+    float scene_abs = 0.0f;
+#pragma omp parallel for reduction(max : scene_abs) schedule(static)
+    for (int i = 0; i < n_tri; i++)
+    {
+        const float* p = tri9 + 9 * (size_t)i;
+        Prim& pr = prims[i];
+        pr.box.grow(p); pr.box.grow(p + 3); pr.box.grow(p + 6);
+        for (int a = 0; a < 3; a++)
+        {
+            pr.c[a] = 0.5f * (pr.box.lo[a] + pr.box.hi[a]);
+            scene_abs = std::max(scene_abs, std::max(std::fabs(pr.box.lo[a]), std::fabs(pr.box.hi[a])));
+        }
+        order[i] = i;
+    }
+    if (!std::isfinite(scene_abs)) scene_abs = 1.0f;
+
+    Builder builder(prims, order, max_leaf, bins);
+    int root = builder.alloc();
+    const int threads = opts.num_threads > 0 ? opts.num_threads : omp_get_max_threads();
+    if (n_tri > 0)
+    {
+#pragma omp parallel num_threads(threads)
+#pragma omp single
+        builder.build(root, 0, n_tri, 0);
+    }
+    else builder.make_leaf(root, 0, 0);
+
+    Flattener fl{ builder, tri9, out, 2e-6f * scene_abs + 1e-30f };
+    out.axis.reserve((size_t)std::max(1, n_tri / 2));
+    out.tris.reserve((size_t)n_tri);
+    Slabs s; int cnt = 0;
+    const BuildNode& rn = builder.nodes[root];
+    if (rn.left < 0)
+    {
+        // a single leaf (or an empty scene): wrap it in one inner record whose right child is an empty, unhittable leaf
+        out.axis.emplace_back(); out.diag.emplace_back();
+        Slabs ls; int first = fl.emit_leaf(rn, ls);
+        if (rn.count == 0) ls.reset();
+        fl.store_child(out.axis[0], out.diag[0], true, ls, leaf_ref(first, rn.count), rn.count);
+        Slabs empty; empty.reset();
+        AxisNode& an = out.axis[0]; DiagNode& dn = out.diag[0];
+        for (int a = 0; a < 3; a++) { an.r_lo[a] = kInf; an.r_hi[a] = -kInf; if (rn.count == 0) { an.l_lo[a] = kInf; an.l_hi[a] = -kInf; } }
+        for (int k = 0; k < 4; k++) { dn.r_near[k] = kInf; dn.r_far[k] = -kInf; if (rn.count == 0) { dn.l_near[k] = kInf; dn.l_far[k] = -kInf; } }
+        an.r_ref = leaf_ref((int)out.tris.size(), 0); an.r_count = 0;
+        fl.max_depth = 1;
+    }
+    else fl.flatten(root, 0, s, cnt);
+
+    // SAH cost of the final tree (diagnostic): sum over inner nodes of child areas / root area
+    double root_area = std::max(1e-30f, builder.nodes[root].box.half_area());
+    double sah = 0.0;
+    for (int i = 0; i < builder.n_nodes.load(); i++)
+    {
+        const BuildNode& n = builder.nodes[i];
+        double a = n.box.half_area() / root_area;
+        sah += (n.left < 0) ? a * n.count : a;
+    }
+
+    auto t1 = std::chrono::high_resolution_clock::now();
+    out.info.n_triangles = n_tri;
+    out.info.n_inner_nodes = (int)out.axis.size();
+    out.info.n_leaves = fl.n_leaves;
+    out.info.max_leaf_size = fl.max_leaf;
+    out.info.max_depth = fl.max_depth + 1;
+    out.info.has_diag_slabs = opts.use_diag_slabs ? 1 : 0;
+    out.info.build_seconds = std::chrono::duration<double>(t1 - t0).count();
+    out.info.sah_cost = sah;
+}
+
+int check_flat_bvh(const FlatBVH& bvh, const float* tri9, int n_tri)
+{
+    if ((int)bvh.tris.size() != n_tri) return 1;
+    std::vector<int> seen((size_t)std::max(1, n_tri), 0);
+    // every triangle exactly once, stored edges consistent
+    for (const LeafTriangle& t : bvh.tris)
+    {
+        if (t.prim < 0 || t.prim >= n_tri) return 2;
+        if (seen[t.prim]++) return 3;
+        const float* p = tri9 + 9 * (size_t)t.prim;
+        for (int a = 0; a < 3; a++)
+            if (t.a[a] != p[a] || t.e1[a] != p[3 + a] - p[a] || t.e2[a] != p[6 + a] - p[a]) return 4;
+    }
+    // every child volume contains the vertices of every triangle below it (iterative walk carrying the volume chain
+    // is O(n depth); instead check leaves against their own volume and inner volumes against their children's)
+    struct Item { int node; int depth; };
+    std::vector<Item> stack{ { 0, 1 } };
+    int covered = 0;
+    while (!stack.empty())
+    {
+        Item it = stack.back(); stack.pop_back();
+        if (it.depth > kMaxTraversalDepth) return 5;
+        if (it.node < 0 || it.node >= (int)bvh.axis.size()) return 6;
+        const AxisNode& an = bvh.axis[it.node];
+        const DiagNode& dn = bvh.diag[it.node];
+        for (int side = 0; side < 2; side++)
+        {
+            const float* lo = side ? an.r_lo : an.l_lo; const float* hi = side ? an.r_hi : an.l_hi;
+            const float* dnear = side ? dn.r_near : dn.l_near; const float* dfar = side ? dn.r_far : dn.l_far;
+            int ref = side ? an.r_ref : an.l_ref; int count = side ? an.r_count : an.l_count;
+            if (ref >= 0)
+            {
+                if (count != 0) return 7;
+                // child's children must be inside this volume
+                if (ref >= (int)bvh.axis.size()) return 6;
+                const AxisNode& cn = bvh.axis[ref];
+                const DiagNode& cd = bvh.diag[ref];
+                for (int cs = 0; cs < 2; cs++)
+                {
+                    const float* clo = cs ? cn.r_lo : cn.l_lo; const float* chi = cs ? cn.r_hi : cn.l_hi;
+                    const float* cnear = cs ? cd.r_near : cd.l_near; const float* cfar = cs ? cd.r_far : cd.l_far;
+                    if (!(clo[0] <= chi[0])) continue;   // empty child
+                    for (int a = 0; a < 3; a++) if (clo[a] < lo[a] - 1e-3f * std::fabs(lo[a]) - 1e-6f || chi[a] > hi[a] + 1e-3f * std::fabs(hi[a]) + 1e-6f) return 8;
+                    (void)cnear; (void)cfar;
+                }
+                stack.push_back({ ref, it.depth + 1 });
+            }
+            else
+            {
+                int first = (~ref) >> 4;
+                if (((~ref) & 15) != count) return 13;
+                if (first < 0 || first + count > n_tri) return 9;
+                covered += count;
+                for (int i = first; i < first + count; i++)
+                {
+                    const float* p = tri9 + 9 * (size_t)bvh.tris[i].prim;
+                    for (int v = 0; v < 3; v++)
+                    {
+                        const float* q = p + 3 * v;
+                        for (int a = 0; a < 3; a++) if (q[a] < lo[a] || q[a] > hi[a]) return 10;
+                        for (int k = 0; k < 4; k++)
+                        {
+                            float d = diag_dist(k, q[0], q[1], q[2]);
+                            if (d < dnear[k] || d > dfar[k]) return 11;
+                        }
+                    }
+                }
+            }
+        }
+    }
+    if (covered != n_tri) return 12;
+    return 0;
+}
+
+} // namespace b200rt

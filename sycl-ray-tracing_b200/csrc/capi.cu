@@ -1,0 +1,528 @@
+// extern "C" shim of include/b200rt.h: argument checking, device residency, launches. No compute happens on the host.
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "../../include/b200rt.h"
+#include "bvh_build.h"
+#include "device_types.h"
+#include "kernels.h"
+
+using namespace b200rt;
+
+struct b200rt_bvh { FlatBVH flat; };
+
+struct b200rt_scene
+{
+    int device = 0;
+    SceneDev dev{};
+    b200rt_bvh_info info{};
+    size_t bytes = 0;
+    std::vector<void*> allocs;
+    MaterialDev* d_mats = nullptr; int mats_cap = 0;
+    // per-scene scratch, grown on demand and kept across calls
+    unsigned int* d_work = nullptr;
+    unsigned long long* d_rays = nullptr;
+    float4* d_tiles = nullptr; size_t tiles_cap = 0;
+    float4* d_image = nullptr; size_t image_cap = 0;
+    int* d_prim = nullptr; float* d_t = nullptr; size_t prim_cap = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+namespace {
+
+thread_local std::string g_error = "";
+
+int fail(int code, const char* fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    g_error = buf;
+    return code;
+}
+
+#define CU(expr)                                                                                             \
+    do {                                                                                                     \
+        cudaError_t e__ = (expr);                                                                            \
+        if (e__ != cudaSuccess) return fail(B200RT_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); \
+    } while (0)
+
+template <typename T>
+int upload(b200rt_scene* s, const T* host, size_t n, const T** dev_out)
+{
+    T* d = nullptr;
+    size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    CU(cudaMalloc(&d, bytes));
+    s->allocs.push_back(d);
+    s->bytes += bytes;
+    if (n) CU(cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice));
+    *dev_out = d;
+    return B200RT_OK;
+}
+
+int make_params(const b200rt_scene* s, const float* camera17, int w, int h, int spp, int bounces,
+                const b200rt_render_options* o, RenderParams& P)
+{
+    if (!s || !camera17) return fail(B200RT_ERR_ARG, "scene and camera must not be NULL");
+    if (w <= 0 || h <= 0) return fail(B200RT_ERR_ARG, "bad frame size %dx%d", w, h);
+    if (spp < 0 || bounces < 0) return fail(B200RT_ERR_ARG, "spp and max_bounces must be >= 0");
+    b200rt_render_options d;
+    b200rt_default_render_options(&d);
+    if (o) d = *o;
+    if (d.world <= 0) d.world = 1;
+    if (d.rank < 0 || d.rank >= d.world) return fail(B200RT_ERR_ARG, "rank %d outside world %d", d.rank, d.world);
+    std::memcpy(P.cam.m, camera17, 16 * sizeof(float));
+    P.cam.fov_dist = camera17[16];
+    P.cam.w = w; P.cam.h = h;
+    P.spp = spp; P.max_bounces = bounces;
+    P.rank = d.rank; P.world = d.world;
+    P.tiles_x = (w + kTileDim - 1) / kTileDim;
+    P.tiles_y = (h + kTileDim - 1) / kTileDim;
+    P.n_rank_tiles = b200rt_tiles_for_rank(w, h, d.rank, d.world);
+    P.flags = d.flags;
+    return B200RT_OK;
+}
+
+int ensure_scratch(b200rt_scene* s, size_t tile_px, size_t image_px, size_t prim_px)
+{
+    if (!s->d_work)
+    {
+        CU(cudaMalloc(&s->d_work, sizeof(unsigned int)));
+        CU(cudaMalloc(&s->d_rays, sizeof(unsigned long long)));
+        CU(cudaEventCreate(&s->ev0));
+        CU(cudaEventCreate(&s->ev1));
+    }
+    if (tile_px > s->tiles_cap)
+    {
+        if (s->d_tiles) cudaFree(s->d_tiles);
+        s->d_tiles = nullptr; s->tiles_cap = 0;
+        CU(cudaMalloc(&s->d_tiles, tile_px * sizeof(float4)));
+        s->tiles_cap = tile_px;
+    }
+    if (image_px > s->image_cap)
+    {
+        if (s->d_image) cudaFree(s->d_image);
+        s->d_image = nullptr; s->image_cap = 0;
+        CU(cudaMalloc(&s->d_image, image_px * sizeof(float4)));
+        s->image_cap = image_px;
+    }
+    if (prim_px > s->prim_cap)
+    {
+        if (s->d_prim) cudaFree(s->d_prim);
+        if (s->d_t) cudaFree(s->d_t);
+        s->d_prim = nullptr; s->d_t = nullptr; s->prim_cap = 0;
+        CU(cudaMalloc(&s->d_prim, prim_px * sizeof(int)));
+        CU(cudaMalloc(&s->d_t, prim_px * sizeof(float)));
+        s->prim_cap = prim_px;
+    }
+    return B200RT_OK;
+}
+
+int convert_materials(const float* materials10, int n, std::vector<MaterialDev>& out, int* any_emissive)
+{
+    out.resize((size_t)std::max(n, 1));
+    *any_emissive = 0;
+    for (int i = 0; i < n; i++)
+    {
+        const float* m = materials10 + 10 * (size_t)i;
+        MaterialDev& d = out[i];
+        d.er = m[0]; d.eg = m[1]; d.eb = m[2];
+        d.dr = m[4]; d.dg = m[5]; d.db = m[6];
+        d.metalness = m[8]; d.roughness = m[9];
+        if (m[0] > 0.0f || m[1] > 0.0f || m[2] > 0.0f) *any_emissive = 1;
+    }
+    return B200RT_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+const char* b200rt_last_error(void) { return g_error.c_str(); }
+const char* b200rt_version(void) { return "b200rt 0.1 (sm_100a)"; }
+
+void b200rt_bvh_default_options(b200rt_bvh_options* o)
+{
+    if (!o) return;
+    o->max_leaf_size = 4; o->sah_bins = 16; o->use_diag_slabs = 1; o->num_threads = 0;
+}
+
+void b200rt_default_render_options(b200rt_render_options* o)
+{
+    if (!o) return;
+    o->integrator = B200RT_INTEGRATOR_MEGAKERNEL; o->flags = 0; o->rank = 0; o->world = 1;
+}
+
+int b200rt_bvh_build(const float* tri_xyz9, int n_tri, const b200rt_bvh_options* opts, b200rt_bvh** out)
+{
+    if (!out) return fail(B200RT_ERR_ARG, "out must not be NULL");
+    *out = nullptr;
+    if (n_tri < 0 || (n_tri > 0 && !tri_xyz9)) return fail(B200RT_ERR_ARG, "bad triangle buffer");
+    if (n_tri >= (1 << 27)) return fail(B200RT_ERR_ARG, "at most 2^27-1 triangles (leaf references pack first<<4|count)");
+    b200rt_bvh_options o;
+    b200rt_bvh_default_options(&o);
+    if (opts) o = *opts;
+    b200rt_bvh* b = new (std::nothrow) b200rt_bvh;
+    if (!b) return fail(B200RT_ERR_ALLOC, "out of host memory");
+    try { build_flat_bvh(tri_xyz9, n_tri, o, b->flat); }
+    catch (const std::exception& e) { delete b; return fail(B200RT_ERR_ALLOC, "BVH build failed: %s", e.what()); }
+    if (b->flat.info.max_depth > kMaxTraversalDepth) { delete b; return fail(B200RT_ERR_ARG, "BVH depth %d exceeds the traversal stack", b->flat.info.max_depth); }
+    *out = b;
+    return B200RT_OK;
+}
+
+int b200rt_bvh_get_info(const b200rt_bvh* bvh, b200rt_bvh_info* out)
+{
+    if (!bvh || !out) return fail(B200RT_ERR_ARG, "NULL argument");
+    *out = bvh->flat.info;
+    return B200RT_OK;
+}
+
+int b200rt_bvh_get_arrays(const b200rt_bvh* bvh, const float** axis16, const float** diag16, const float** tris12)
+{
+    if (!bvh) return fail(B200RT_ERR_ARG, "NULL bvh");
+    if (axis16) *axis16 = reinterpret_cast<const float*>(bvh->flat.axis.data());
+    if (diag16) *diag16 = reinterpret_cast<const float*>(bvh->flat.diag.data());
+    if (tris12) *tris12 = reinterpret_cast<const float*>(bvh->flat.tris.data());
+    return B200RT_OK;
+}
+
+int b200rt_bvh_check(const b200rt_bvh* bvh, const float* tri_xyz9, int n_tri)
+{
+    if (!bvh) return fail(B200RT_ERR_ARG, "NULL bvh");
+    int r = check_flat_bvh(bvh->flat, tri_xyz9, n_tri);
+    if (r) return fail(100 + r, "BVH invariant %d violated", r);
+    return B200RT_OK;
+}
+
+void b200rt_bvh_destroy(b200rt_bvh* bvh) { delete bvh; }
+
+int b200rt_scene_create(const float* tri_xyz9, int n_tri, const int* tri_material, int n_material_indices,
+                        const float* materials10, int n_materials, const int* emissive_tri, int n_emissive,
+                        const void* spheres20, int n_spheres,
+                        const float* env_rgba, int env_w, int env_h, const float* env_cdf_or_null,
+                        const b200rt_bvh* bvh_or_null, int device, b200rt_scene** out)
+{
+    if (!out) return fail(B200RT_ERR_ARG, "out must not be NULL");
+    *out = nullptr;
+    if (n_tri < 0 || (n_tri > 0 && !tri_xyz9)) return fail(B200RT_ERR_ARG, "bad triangle buffer");
+    if (n_material_indices < n_tri || (n_material_indices > 0 && !tri_material)) return fail(B200RT_ERR_ARG, "need one material index per triangle");
+    if (n_materials <= 0 || !materials10) return fail(B200RT_ERR_ARG, "need at least one material");
+    if (n_emissive < 0 || (n_emissive > 0 && !emissive_tri)) return fail(B200RT_ERR_ARG, "bad emissive triangle list");
+    if (n_spheres < 0 || (n_spheres > 0 && !spheres20)) return fail(B200RT_ERR_ARG, "bad sphere buffer");
+    if (!env_rgba || env_w <= 0 || env_h <= 0)
+        return fail(B200RT_ERR_ARG, "an environment map is required (the reference samples it unconditionally, render_kernel.cpp:114)");
+    for (int i = 0; i < n_material_indices; i++)
+        if (tri_material[i] < 0 || tri_material[i] >= n_materials) return fail(B200RT_ERR_ARG, "material index %d of primitive %d out of range", tri_material[i], i);
+    for (int i = 0; i < n_emissive; i++)
+        if (emissive_tri[i] < 0 || emissive_tri[i] >= n_tri) return fail(B200RT_ERR_ARG, "emissive triangle index out of range");
+
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0)
+        return fail(B200RT_ERR_CUDA, "no CUDA device: b200rt has no CPU fallback");
+    if (device < 0) CU(cudaGetDevice(&device));
+    if (device >= n_dev) return fail(B200RT_ERR_ARG, "device %d of %d", device, n_dev);
+    CU(cudaSetDevice(device));
+
+    b200rt_bvh* own = nullptr;
+    const b200rt_bvh* bvh = bvh_or_null;
+    if (!bvh)
+    {
+        int r = b200rt_bvh_build(tri_xyz9, n_tri, nullptr, &own);
+        if (r) return r;
+        bvh = own;
+    }
+    if (bvh->flat.info.n_triangles != n_tri) { delete own; return fail(B200RT_ERR_ARG, "BVH was built for %d triangles, scene has %d", bvh->flat.info.n_triangles, n_tri); }
+
+    b200rt_scene* s = new (std::nothrow) b200rt_scene;
+    if (!s) { delete own; return fail(B200RT_ERR_ALLOC, "out of host memory"); }
+    s->device = device;
+    s->info = bvh->flat.info;
+    int rc = B200RT_OK;
+    do
+    {
+        const FlatBVH& f = bvh->flat;
+        if ((rc = upload(s, reinterpret_cast<const float4*>(f.axis.data()), f.axis.size() * 4, &s->dev.axis))) break;
+        if ((rc = upload(s, reinterpret_cast<const float4*>(f.diag.data()), f.diag.size() * 4, &s->dev.diag))) break;
+        if ((rc = upload(s, reinterpret_cast<const float4*>(f.tris.data()), f.tris.size() * 3, &s->dev.tris))) break;
+        std::vector<int> slot_of_prim((size_t)std::max(n_tri, 1), 0);
+        for (size_t i = 0; i < f.tris.size(); i++) slot_of_prim[f.tris[i].prim] = (int)i;
+        if ((rc = upload(s, slot_of_prim.data(), (size_t)n_tri, &s->dev.slot_of_prim))) break;
+        if ((rc = upload(s, tri_material, (size_t)n_material_indices, &s->dev.mat_idx))) break;
+        if ((rc = upload(s, emissive_tri, (size_t)n_emissive, &s->dev.emissive))) break;
+        std::vector<SphereDev> sph((size_t)std::max(n_spheres, 1));
+        for (int i = 0; i < n_spheres; i++) std::memcpy(&sph[i], (const char*)spheres20 + 20 * (size_t)i, 20);
+        if ((rc = upload(s, sph.data(), (size_t)n_spheres, &s->dev.spheres))) break;
+        if ((rc = upload(s, reinterpret_cast<const float4*>(env_rgba), (size_t)env_w * env_h, &s->dev.env))) break;
+        std::vector<float> cdf;
+        const float* cdf_host = env_cdf_or_null;
+        if (!cdf_host)
+        {
+            // Utils::compute_env_map_cdf (utils.cpp:126-142) with Image::luminance_of_pixel's double constants (image.h:84)
+            cdf.resize((size_t)env_w * env_h);
+            float run = 0.0f;
+            for (size_t i = 0; i < cdf.size(); i++)
+            {
+                const float* p = env_rgba + 4 * i;
+                float lum = (float)(0.3086 * p[0] + 0.6094 * p[1] + 0.0820 * p[2]);
+                run = run + lum;
+                cdf[i] = run;
+            }
+            cdf_host = cdf.data();
+        }
+        if ((rc = upload(s, cdf_host, (size_t)env_w * env_h, &s->dev.cdf))) break;
+        s->dev.cdf_total = cdf_host[(size_t)env_w * env_h - 1];
+        s->dev.n_tri = n_tri; s->dev.n_emissive = n_emissive; s->dev.n_spheres = n_spheres;
+        s->dev.env_w = env_w; s->dev.env_h = env_h;
+        s->dev.has_diag = f.info.has_diag_slabs;
+    } while (0);
+    delete own;
+    if (rc) { b200rt_scene_destroy(s); return rc; }
+    rc = b200rt_scene_set_materials(s, materials10, n_materials);
+    if (rc) { b200rt_scene_destroy(s); return rc; }
+    *out = s;
+    return B200RT_OK;
+}
+
+int b200rt_scene_set_materials(b200rt_scene* s, const float* materials10, int n_materials)
+{
+    if (!s || !materials10 || n_materials <= 0) return fail(B200RT_ERR_ARG, "bad materials");
+    CU(cudaSetDevice(s->device));
+    std::vector<MaterialDev> mats;
+    int any = 0;
+    convert_materials(materials10, n_materials, mats, &any);
+    if (n_materials > s->mats_cap)
+    {
+        if (s->d_mats) { cudaFree(s->d_mats); s->d_mats = nullptr; }
+        CU(cudaMalloc(&s->d_mats, sizeof(MaterialDev) * (size_t)n_materials));
+        s->mats_cap = n_materials;
+    }
+    CU(cudaMemcpy(s->d_mats, mats.data(), sizeof(MaterialDev) * (size_t)n_materials, cudaMemcpyHostToDevice));
+    s->dev.mats = s->d_mats;
+    s->dev.n_mats = n_materials;
+    s->dev.any_emissive_material = any;
+    return B200RT_OK;
+}
+
+void b200rt_scene_destroy(b200rt_scene* s)
+{
+    if (!s) return;
+    cudaSetDevice(s->device);
+    for (void* p : s->allocs) cudaFree(p);
+    if (s->d_mats) cudaFree(s->d_mats);
+    if (s->d_work) cudaFree(s->d_work);
+    if (s->d_rays) cudaFree(s->d_rays);
+    if (s->d_tiles) cudaFree(s->d_tiles);
+    if (s->d_image) cudaFree(s->d_image);
+    if (s->d_prim) cudaFree(s->d_prim);
+    if (s->d_t) cudaFree(s->d_t);
+    if (s->ev0) cudaEventDestroy(s->ev0);
+    if (s->ev1) cudaEventDestroy(s->ev1);
+    delete s;
+}
+
+int b200rt_scene_get_bvh_info(const b200rt_scene* s, b200rt_bvh_info* out)
+{
+    if (!s || !out) return fail(B200RT_ERR_ARG, "NULL argument");
+    *out = s->info;
+    return B200RT_OK;
+}
+
+size_t b200rt_scene_device_bytes(const b200rt_scene* s) { return s ? s->bytes : 0; }
+
+int b200rt_tiles_for_rank(int width, int height, int rank, int world)
+{
+    if (width <= 0 || height <= 0 || world <= 0 || rank < 0 || rank >= world) return 0;
+    const int n = ((width + kTileDim - 1) / kTileDim) * ((height + kTileDim - 1) / kTileDim);
+    return (n - rank + world - 1) / world;       // tiles rank, rank + world, ... < n
+}
+
+int b200rt_render_tiles_device(b200rt_scene* s, const float* camera17, int w, int h, int spp, int bounces,
+                               void* dev_tiles, const b200rt_render_options* opts, void* cuda_stream, b200rt_stats* stats)
+{
+    RenderParams P;
+    int rc = make_params(s, camera17, w, h, spp, bounces, opts, P);
+    if (rc) return rc;
+    if (!dev_tiles) return fail(B200RT_ERR_ARG, "dev_tiles must not be NULL");
+    if (opts && opts->integrator != B200RT_INTEGRATOR_MEGAKERNEL && opts->integrator != B200RT_INTEGRATOR_WAVEFRONT)
+        return fail(B200RT_ERR_ARG, "unknown integrator %d", opts->integrator);
+    CU(cudaSetDevice(s->device));
+    if ((rc = ensure_scratch(s, 0, 0, 0))) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (stats) { CU(cudaMemsetAsync(s->d_rays, 0, sizeof(unsigned long long), st)); CU(cudaEventRecord(s->ev0, st)); }
+    CU(launch_megakernel(s->dev, P, nullptr, (float4*)dev_tiles, s->d_work, s->d_rays, st));
+    if (stats)
+    {
+        CU(cudaEventRecord(s->ev1, st));
+        CU(cudaEventSynchronize(s->ev1));
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        std::memset(stats, 0, sizeof(*stats));
+        CU(cudaMemcpy(&stats->rays, s->d_rays, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        stats->kernel_ms = ms; stats->total_ms = ms; stats->gpu_launches = 1;
+        // pixels of this rank that lie inside the frame
+        unsigned long long px = 0;
+        for (int k = 0; k < P.n_rank_tiles; k++)
+        {
+            int tile = P.rank + k * P.world, tx = tile % P.tiles_x, ty = tile / P.tiles_x;
+            px += (unsigned long long)std::min(kTileDim, w - tx * kTileDim) * std::min(kTileDim, h - ty * kTileDim);
+        }
+        stats->samples = px * (unsigned long long)spp;
+    }
+    return B200RT_OK;
+}
+
+int b200rt_untile_device(b200rt_scene* s, const void* dev_gathered, int tiles_per_rank_padded, int world, int w, int h,
+                         void* dev_image, void* cuda_stream)
+{
+    if (!s || !dev_gathered || !dev_image || world <= 0 || w <= 0 || h <= 0) return fail(B200RT_ERR_ARG, "bad untile arguments");
+    if (tiles_per_rank_padded < b200rt_tiles_for_rank(w, h, 0, world)) return fail(B200RT_ERR_ARG, "tiles_per_rank_padded too small");
+    CU(cudaSetDevice(s->device));
+    CU(launch_untile((const float4*)dev_gathered, tiles_per_rank_padded, world, -1, w, h, (float4*)dev_image, (cudaStream_t)cuda_stream));
+    return B200RT_OK;
+}
+
+int b200rt_render(b200rt_scene* s, const float* camera17, int w, int h, int spp, int bounces, float* fb,
+                  const b200rt_render_options* opts, b200rt_stats* stats)
+{
+    RenderParams P;
+    int rc = make_params(s, camera17, w, h, spp, bounces, opts, P);
+    if (rc) return rc;
+    if (!fb) return fail(B200RT_ERR_ARG, "framebuffer must not be NULL");
+    auto t0 = std::chrono::high_resolution_clock::now();
+    CU(cudaSetDevice(s->device));
+    const size_t image_px = (size_t)w * h;
+    if ((rc = ensure_scratch(s, (size_t)std::max(P.n_rank_tiles, 1) * kTilePixels, image_px, 0))) return rc;
+    cudaStream_t st = 0;
+    const bool upload_fb = !(P.flags & B200RT_FLAG_FB_IS_ZERO) || P.world > 1;
+    unsigned long long h2d = 17 * sizeof(float), d2h = 0;
+    if (upload_fb) { CU(cudaMemcpyAsync(s->d_image, fb, image_px * sizeof(float4), cudaMemcpyHostToDevice, st)); h2d += image_px * sizeof(float4); }
+    CU(cudaMemsetAsync(s->d_rays, 0, sizeof(unsigned long long), st));
+    CU(cudaEventRecord(s->ev0, st));
+    const float4* fb_in = (P.flags & B200RT_FLAG_FB_IS_ZERO) ? nullptr : s->d_image;
+    CU(launch_megakernel(s->dev, P, fb_in, s->d_tiles, s->d_work, s->d_rays, st));
+    CU(launch_untile(s->d_tiles, P.n_rank_tiles, P.world, P.world > 1 ? P.rank : -1, w, h, s->d_image, st));
+    CU(cudaEventRecord(s->ev1, st));
+    CU(cudaMemcpyAsync(fb, s->d_image, image_px * sizeof(float4), cudaMemcpyDeviceToHost, st));
+    d2h += image_px * sizeof(float4);
+    CU(cudaStreamSynchronize(st));
+    if (stats)
+    {
+        std::memset(stats, 0, sizeof(*stats));
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        CU(cudaMemcpy(&stats->rays, s->d_rays, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        unsigned long long px = 0;
+        for (int k = 0; k < P.n_rank_tiles; k++)
+        {
+            int tile = P.rank + k * P.world, tx = tile % P.tiles_x, ty = tile / P.tiles_x;
+            px += (unsigned long long)std::min(kTileDim, w - tx * kTileDim) * std::min(kTileDim, h - ty * kTileDim);
+        }
+        stats->samples = px * (unsigned long long)spp;
+        stats->kernel_ms = ms;
+        stats->gpu_launches = 2;
+        stats->h2d_bytes = h2d; stats->d2h_bytes = d2h;
+        stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
+    }
+    return B200RT_OK;
+}
+
+int b200rt_trace_primary_device(b200rt_scene* s, const float* camera17, int w, int h, int sample, int spp_for_seed,
+                                void* dev_prim, void* dev_t, const b200rt_render_options* opts, void* cuda_stream, b200rt_stats* stats)
+{
+    RenderParams P;
+    int rc = make_params(s, camera17, w, h, spp_for_seed, 1, opts, P);
+    if (rc) return rc;
+    if (!dev_prim || !dev_t) return fail(B200RT_ERR_ARG, "output buffers must not be NULL");
+    if (sample > 0) return fail(B200RT_ERR_ARG, "only sample 0 (or < 0 = un-jittered) has a path-independent camera ray");
+    CU(cudaSetDevice(s->device));
+    if ((rc = ensure_scratch(s, 0, 0, 0))) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (stats) CU(cudaEventRecord(s->ev0, st));
+    CU(launch_primary(s->dev, P, sample, (int*)dev_prim, (float*)dev_t, st));
+    if (stats)
+    {
+        CU(cudaEventRecord(s->ev1, st));
+        CU(cudaEventSynchronize(s->ev1));
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        std::memset(stats, 0, sizeof(*stats));
+        stats->kernel_ms = ms; stats->total_ms = ms; stats->gpu_launches = 1;
+        unsigned long long px = 0;
+        for (int k = 0; k < P.n_rank_tiles; k++)
+        {
+            int tile = P.rank + k * P.world, tx = tile % P.tiles_x, ty = tile / P.tiles_x;
+            px += (unsigned long long)std::min(kTileDim, w - tx * kTileDim) * std::min(kTileDim, h - ty * kTileDim);
+        }
+        stats->rays = px; stats->samples = px;
+    }
+    return B200RT_OK;
+}
+
+int b200rt_trace_primary(b200rt_scene* s, const float* camera17, int w, int h, int sample, int spp_for_seed,
+                         int* prim_out, float* t_out, const b200rt_render_options* opts, b200rt_stats* stats)
+{
+    if (!s) return fail(B200RT_ERR_ARG, "NULL scene");
+    if (!prim_out || !t_out) return fail(B200RT_ERR_ARG, "output buffers must not be NULL");
+    if (w <= 0 || h <= 0) return fail(B200RT_ERR_ARG, "bad frame size");
+    auto t0 = std::chrono::high_resolution_clock::now();
+    CU(cudaSetDevice(s->device));
+    const size_t px = (size_t)w * h;
+    int rc = ensure_scratch(s, 0, 0, px);
+    if (rc) return rc;
+    CU(cudaMemset(s->d_prim, 0xff, px * sizeof(int)));                 // -1: pixels of other ranks read as "miss"
+    {
+        std::vector<float> neg(px, -1.0f);
+        CU(cudaMemcpy(s->d_t, neg.data(), px * sizeof(float), cudaMemcpyHostToDevice));
+    }
+    rc = b200rt_trace_primary_device(s, camera17, w, h, sample, spp_for_seed, s->d_prim, s->d_t, opts, nullptr, stats);
+    if (rc) return rc;
+    CU(cudaMemcpy(prim_out, s->d_prim, px * sizeof(int), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(t_out, s->d_t, px * sizeof(float), cudaMemcpyDeviceToHost));
+    if (stats)
+    {
+        stats->d2h_bytes = px * 8; stats->h2d_bytes = 17 * sizeof(float);
+        stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
+    }
+    return B200RT_OK;
+}
+
+int b200rt_trace_rays(b200rt_scene* s, const float* rays6, int n, int any_hit, int* prim_out, float* t_out, float* extra8,
+                      const b200rt_render_options* opts)
+{
+    if (!s) return fail(B200RT_ERR_ARG, "NULL scene");
+    if (n < 0 || (n > 0 && (!rays6 || !prim_out || !t_out))) return fail(B200RT_ERR_ARG, "bad ray buffers");
+    if (n == 0) return B200RT_OK;
+    CU(cudaSetDevice(s->device));
+    float* d_rays6 = nullptr; int* d_prim = nullptr; float* d_t = nullptr; float* d_extra = nullptr;
+    int rc = B200RT_OK;
+    cudaError_t e = cudaSuccess;
+    do
+    {
+        if ((e = cudaMalloc(&d_rays6, sizeof(float) * 6 * (size_t)n)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&d_prim, sizeof(int) * (size_t)n)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&d_t, sizeof(float) * (size_t)n)) != cudaSuccess) break;
+        if (extra8 && (e = cudaMalloc(&d_extra, sizeof(float) * 8 * (size_t)n)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(d_rays6, rays6, sizeof(float) * 6 * (size_t)n, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = launch_trace_rays(s->dev, d_rays6, n, any_hit, opts ? opts->flags : 0, d_prim, d_t, d_extra, 0)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(prim_out, d_prim, sizeof(int) * (size_t)n, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(t_out, d_t, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        if (extra8 && (e = cudaMemcpy(extra8, d_extra, sizeof(float) * 8 * (size_t)n, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+    } while (0);
+    if (e != cudaSuccess) rc = fail(B200RT_ERR_CUDA, "trace_rays: %s", cudaGetErrorString(e));
+    cudaFree(d_rays6); cudaFree(d_prim); cudaFree(d_t); cudaFree(d_extra);
+    return rc;
+}
+
+} // extern "C"

@@ -1,0 +1,61 @@
+// POD structs shared by the host shim and the kernels.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace b200rt {
+
+constexpr int kTileDim = 16;                 // image tiles are 16x16 pixels = 8 warp patches of 8x4
+constexpr int kTilePixels = kTileDim * kTileDim;
+constexpr int kPatchW = 8, kPatchH = 4;      // one warp = one 8x4 pixel patch
+constexpr int kStackSize = 64;
+
+struct MaterialDev   // SimpleMaterial (simple_material.h:6-13) without the junk alphas, two float4
+{
+    float er, eg, eb, metalness;
+    float dr, dg, db, roughness;
+};
+
+struct SphereDev     // == Sphere (sphere.h:55-58)
+{
+    float cx, cy, cz, radius;
+    int prim;
+};
+
+struct SceneDev
+{
+    const float4* axis;        // 4 float4 per inner node (AxisNode)
+    const float4* diag;        // 4 float4 per inner node (DiagNode)
+    const float4* tris;        // 3 float4 per triangle, leaf order (LeafTriangle)
+    const int* slot_of_prim;   // original triangle index -> slot in `tris`
+    const int* mat_idx;        // per primitive (triangles, then spheres)
+    const MaterialDev* mats;
+    const int* emissive;       // original indices of emissive triangles
+    const SphereDev* spheres;
+    const float4* env;         // env_w * env_h RGBA
+    const float* cdf;          // running luminance sum, row-major
+    int n_tri, n_mats, n_emissive, n_spheres;
+    int env_w, env_h;
+    float cdf_total;
+    int has_diag;
+    int any_emissive_material; // some material has emission > 0 (else the BRDF->light MIS ray cannot contribute)
+};
+
+struct CameraDev   // Camera (camera.h:34-39) + frame size, as get_camera_ray uses them (render_kernel.cpp:56-73)
+{
+    float m[16];
+    float fov_dist;
+    int w, h;
+};
+
+struct RenderParams
+{
+    CameraDev cam;
+    int spp, max_bounces;
+    int rank, world;           // interleaved 16x16 tiles: tile_id % world == rank
+    int tiles_x, tiles_y;
+    int n_rank_tiles;          // tiles owned by this rank
+    int flags;
+};
+
+} // namespace b200rt

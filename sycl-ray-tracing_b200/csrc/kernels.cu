@@ -1,0 +1,287 @@
+// sm_100a kernels of the path: primary closest-hit (K1), megakernel integrator (K2), ray batches, untile (K4).
+// Compiled with -fmad=false (see pt_device.cuh).
+#include "kernels.h"
+#include "pt_device.cuh"
+
+namespace b200rt {
+
+// pixel <-> work-unit mapping: a frame is cut into 16x16 tiles owned round-robin by ranks; a tile is 8 warp patches of
+// 8x4 pixels; one warp renders one patch so its 32 rays start as a compact screen-space bundle.
+struct PixelSlot { int x, y; size_t out; bool inside; };
+
+__device__ __forceinline__ PixelSlot unit_pixel(const RenderParams& P, int unit, int lane)
+{
+    const int k = unit >> 3, sub = unit & 7;
+    const int tile_id = P.rank + k * P.world;
+    const int tx = tile_id % P.tiles_x, ty = tile_id / P.tiles_x;
+    PixelSlot s;
+    s.x = tx * kTileDim + (sub & 1) * kPatchW + (lane & 7);
+    s.y = ty * kTileDim + (sub >> 1) * kPatchH + (lane >> 3);
+    s.out = (size_t)k * kTilePixels + sub * 32 + lane;
+    s.inside = s.x < P.cam.w && s.y < P.cam.h;
+    return s;
+}
+
+// ---- K2: megakernel. One thread = one pixel; its samples and bounces run in-thread so the pixel's xorshift stream is
+// consumed in the reference's order (render_kernel.cpp:75-181). The body is a state machine with ONE trace site: path
+// rays and the four side rays of a surface interaction all pass through the same traversal loop, so the lanes of a
+// warp stay converged on traversal whatever stage each of them is in.
+template <bool DIAG>
+__device__ __forceinline__ col render_pixel(const SceneDev& S, const RenderParams& P, int x, int y, unsigned long long& rays)
+{
+    uint32_t rng = pixel_rng(x, y, P.spp);
+    col final_color = CO(0.0f, 0.0f, 0.0f);
+    const bool trace_light_brdf = S.any_emissive_material || !(P.flags & B200RT_FLAG_SKIP_DEAD_RAYS);
+
+    for (int sample = 0; sample < P.spp; sample++)
+    {
+        const float xj = ((float)x + 0.5f) + xs_float(rng) - 1.0f;      // :88-89
+        const float yj = ((float)y + 0.5f) + xs_float(rng) - 1.0f;
+        v3 ro, rd;
+        camera_ray(P.cam, xj, yj, ro, rd);
+        col throughput = CO(1.0f, 1.0f, 1.0f);
+        col sample_color = CO(0.0f, 0.0f, 0.0f);
+        if (P.max_bounces <= 0) continue;
+
+        int bounce = 0;
+        int stage = 4;                    // 4: (ro, rd) is the path ray; 0..3: it is side ray `stage` of the surface `sf`
+        int mode = TRACE_CLOSEST;
+        float tmax = 0.0f;
+        Surface sf;
+        SideRay sr;
+        col c0 = CO(0, 0, 0), c1 = c0, c2 = c0, c3 = c0;
+        sr.kind = SIDE_NONE;
+
+        for (;;)
+        {
+            Hit h;
+            const bool found = trace_ray<DIAG>(S, ro, rd, tmax, mode, h);      // the single trace site
+            rays++;
+            if (stage == 4)
+            {
+                if (!found)
+                {
+                    // MISSED is handled one loop iteration later and only adds the sky when that iteration is bounce 1 (:146-159)
+                    if (bounce == 0 && P.max_bounces >= 2)
+                        sample_color = sample_color + env_from_direction(S, rd) * throughput;
+                    break;
+                }
+                hit_geometry(S, h, ro, rd, sf.p, sf.n);
+                sf.view = -rd;
+                sf.m = S.mats[__ldg(S.mat_idx + h.prim)];                      // :107-108
+                c0 = c1 = c2 = c3 = CO(0.0f, 0.0f, 0.0f);
+                stage = 0;
+            }
+            else
+            {
+                col c = CO(0.0f, 0.0f, 0.0f);
+                if (sr.kind == SIDE_CLOSEST_LIGHT) { if (found) c = side_light_hit(S, sr, h); }
+                else if (!found) c = sr.weight;
+                if (stage == 0) c0 = c; else if (stage == 1) c1 = c; else if (stage == 2) c2 = c; else c3 = c;
+                stage++;
+            }
+
+            bool sample_done = false;
+            for (;;)
+            {
+                if (stage < 4)
+                {
+                    if (stage == 0) side_light_sample(S, sf, rng, sr);
+                    else if (stage == 1) side_light_brdf(S, sf, rng, sr);
+                    else if (stage == 2) side_env_sample(S, sf, rng, sr);
+                    else side_env_brdf(S, sf, rng, sr);
+                    const bool need = sr.kind != SIDE_NONE && !(sr.kind == SIDE_CLOSEST_LIGHT && !trace_light_brdf);
+                    if (need)
+                    {
+                        ro = sr.o; rd = sr.d; tmax = sr.tmax;
+                        mode = sr.kind == SIDE_SHADOW ? TRACE_SHADOW : (sr.kind == SIDE_CLOSEST_LIGHT ? TRACE_CLOSEST : TRACE_ANY);
+                        break;
+                    }
+                    stage++;
+                    continue;
+                }
+                // all four side rays resolved: continuation sample and path bookkeeping (:121-141)
+                float bpdf;
+                v3 ndir = V(0.0f, 0.0f, 0.0f);
+                const col brdf = ct_sample(sf.m, sf.view, sf.n, ndir, bpdf, rng);
+                if (bounce == 0) sample_color = sample_color + CO(sf.m.er, sf.m.eg, sf.m.eb);
+                sample_color = sample_color + ((c0 + c1) + (c3 + c2)) * throughput;       // light = c0+c1 (:712), env = c3+c2 (:630)
+                if (is_black(brdf) || bpdf < 1.0e-8f || isinf(bpdf)) { sample_done = true; break; }
+                throughput = throughput * ((brdf * smax(0.0f, dot(ndir, sf.n))) / bpdf);
+                bounce++;
+                if (bounce >= P.max_bounces) { sample_done = true; break; }
+                ro = sf.p + 1.0e-4f * sf.n; rd = ndir;
+                mode = TRACE_CLOSEST; stage = 4;
+                break;
+            }
+            if (sample_done) break;
+        }
+        final_color = final_color + sample_color;
+    }
+    const float n = (float)P.spp;
+    return CO(final_color.r / n, final_color.g / n, final_color.b / n);         // operator/= divides (color.h:67-74)
+}
+
+template <bool DIAG>
+__global__ void __launch_bounds__(256) k_pathtrace_mega(SceneDev S, RenderParams P, const float4* __restrict__ fb_in_rowmajor,
+                                                        float4* __restrict__ out_tiles, unsigned int* work_counter,
+                                                        unsigned long long* ray_counter)
+{
+    const int lane = threadIdx.x & 31;
+    const int n_units = P.n_rank_tiles * 8;
+    unsigned long long rays = 0;
+    for (;;)
+    {
+        int unit = 0;
+        if (lane == 0) unit = (int)atomicAdd(work_counter, 1u);
+        unit = __shfl_sync(0xffffffffu, unit, 0);
+        if (unit >= n_units) break;
+        const PixelSlot ps = unit_pixel(P, unit, lane);
+        float4 px = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        if (ps.inside)
+        {
+            const col mean = render_pixel<DIAG>(S, P, ps.x, ps.y, rays);
+            const float4 fb = fb_in_rowmajor ? fb_in_rowmajor[(size_t)ps.y * P.cam.w + ps.x] : make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+            px = tonemap(fb, mean);
+        }
+        out_tiles[ps.out] = px;
+    }
+    for (int off = 16; off > 0; off >>= 1) rays += __shfl_down_sync(0xffffffffu, rays, off);
+    if (lane == 0 && rays) atomicAdd(ray_counter, rays);
+}
+
+// ---- K1: primary closest hit (parity hook + C2 traversal microbenchmark) -----------------------------------------------
+template <bool DIAG>
+__global__ void __launch_bounds__(256) k_primary(SceneDev S, RenderParams P, int sample, int* __restrict__ prim_out, float* __restrict__ t_out)
+{
+    const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int lane = threadIdx.x & 31;
+    if (warp >= P.n_rank_tiles * 8) return;
+    const PixelSlot ps = unit_pixel(P, warp, lane);
+    if (!ps.inside) return;
+    float fx = (float)ps.x, fy = (float)ps.y;
+    if (sample >= 0)
+    {
+        uint32_t rng = pixel_rng(ps.x, ps.y, P.spp);
+        fx = ((float)ps.x + 0.5f) + xs_float(rng) - 1.0f;
+        fy = ((float)ps.y + 0.5f) + xs_float(rng) - 1.0f;
+    }
+    v3 o, d;
+    camera_ray(P.cam, fx, fy, o, d);
+    Hit h;
+    const bool found = trace_ray<DIAG>(S, o, d, 0.0f, TRACE_CLOSEST, h);
+    const size_t idx = (size_t)ps.y * P.cam.w + ps.x;
+    prim_out[idx] = found ? h.prim : -1;
+    t_out[idx] = found ? h.t : -1.0f;
+}
+
+// ---- ray batches (BVH::intersect / FlattenedBVH::intersect replacement for tests and tools) ------------------------------
+template <bool DIAG>
+__global__ void __launch_bounds__(256) k_trace_rays(SceneDev S, const float* __restrict__ rays6, int n, int any_hit,
+                                                    int* __restrict__ prim_out, float* __restrict__ t_out, float* __restrict__ extra8)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float* r = rays6 + 6 * (size_t)i;
+    const v3 o = V(r[0], r[1], r[2]), d = V(r[3], r[4], r[5]);
+    Hit h;
+    const bool found = trace_ray<DIAG>(S, o, d, 0.0f, any_hit ? TRACE_ANY : TRACE_CLOSEST, h);
+    if (any_hit) { prim_out[i] = found ? 1 : 0; t_out[i] = found ? h.t : -1.0f; return; }
+    prim_out[i] = found ? h.prim : -1;
+    t_out[i] = found ? h.t : -1.0f;
+    if (extra8)
+    {
+        float* e = extra8 + 8 * (size_t)i;
+        if (found)
+        {
+            v3 p, nn;
+            hit_geometry(S, h, o, d, p, nn);
+            e[0] = p.x; e[1] = p.y; e[2] = p.z; e[3] = nn.x; e[4] = nn.y; e[5] = nn.z; e[6] = h.u; e[7] = h.v;
+        }
+        else { for (int k = 0; k < 8; k++) e[k] = 0.0f; }
+    }
+}
+
+// ---- K4: tile-major (per-rank compact buffers, rank-major) -> row-major bottom-up RGBA --------------------------------------
+__global__ void __launch_bounds__(256) k_untile(const float4* __restrict__ tiles, int tiles_per_rank_padded, int world, int only_rank,
+                                                int w, int h, int tiles_x, float4* __restrict__ image)
+{
+    const int x = blockIdx.x * 16 + (threadIdx.x & 15);
+    const int y = blockIdx.y * 16 + (threadIdx.x >> 4);
+    if (x >= w || y >= h) return;
+    const int tile_id = (y / kTileDim) * tiles_x + (x / kTileDim);
+    const int rank = tile_id % world, k = tile_id / world;
+    if (only_rank >= 0 && rank != only_rank) return;
+    const int lx = x % kTileDim, ly = y % kTileDim;
+    const int sub = (ly / kPatchH) * 2 + (lx / kPatchW);
+    const int lane = (ly % kPatchH) * kPatchW + (lx % kPatchW);
+    const size_t src = ((size_t)(only_rank >= 0 ? 0 : rank) * tiles_per_rank_padded + k) * kTilePixels + sub * 32 + lane;
+    image[(size_t)y * w + x] = tiles[src];
+}
+
+// ---- launchers ----------------------------------------------------------------------------------------------------------------
+static int g_sm_count = 0;
+static int sm_count()
+{
+    if (!g_sm_count)
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (g_sm_count <= 0) g_sm_count = 148;
+    }
+    return g_sm_count;
+}
+
+cudaError_t launch_megakernel(const SceneDev& S, const RenderParams& P, const float4* fb_in_rowmajor, float4* out_tiles,
+                              unsigned int* work_counter, unsigned long long* ray_counter, cudaStream_t stream)
+{
+    cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned int), stream);
+    if (e != cudaSuccess) return e;
+    const bool diag = S.has_diag && !(P.flags & B200RT_FLAG_AXIS_SLABS_ONLY);
+    int per_sm = 0;
+    if (diag) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pathtrace_mega<true>, 256, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pathtrace_mega<false>, 256, 0);
+    if (per_sm <= 0) per_sm = 1;
+    const int n_units = P.n_rank_tiles * 8;
+    int grid = sm_count() * per_sm;                        // persistent: a whole number of resident CTAs per SM
+    const int needed = (n_units + 7) / 8;
+    if (grid > needed) grid = needed;
+    if (grid <= 0) return cudaSuccess;
+    if (diag) k_pathtrace_mega<true><<<grid, 256, 0, stream>>>(S, P, fb_in_rowmajor, out_tiles, work_counter, ray_counter);
+    else k_pathtrace_mega<false><<<grid, 256, 0, stream>>>(S, P, fb_in_rowmajor, out_tiles, work_counter, ray_counter);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_primary(const SceneDev& S, const RenderParams& P, int sample, int* prim_out, float* t_out, cudaStream_t stream)
+{
+    const int n_warps = P.n_rank_tiles * 8;
+    if (n_warps <= 0) return cudaSuccess;
+    const int grid = (n_warps * 32 + 255) / 256;
+    const bool diag = S.has_diag && !(P.flags & B200RT_FLAG_AXIS_SLABS_ONLY);
+    if (diag) k_primary<true><<<grid, 256, 0, stream>>>(S, P, sample, prim_out, t_out);
+    else k_primary<false><<<grid, 256, 0, stream>>>(S, P, sample, prim_out, t_out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_trace_rays(const SceneDev& S, const float* rays6, int n, int any_hit, int flags, int* prim_out, float* t_out,
+                              float* extra8, cudaStream_t stream)
+{
+    if (n <= 0) return cudaSuccess;
+    const int grid = (n + 255) / 256;
+    const bool diag = S.has_diag && !(flags & B200RT_FLAG_AXIS_SLABS_ONLY);
+    if (diag) k_trace_rays<true><<<grid, 256, 0, stream>>>(S, rays6, n, any_hit, prim_out, t_out, extra8);
+    else k_trace_rays<false><<<grid, 256, 0, stream>>>(S, rays6, n, any_hit, prim_out, t_out, extra8);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_untile(const float4* tiles, int tiles_per_rank_padded, int world, int only_rank, int w, int h, float4* image,
+                          cudaStream_t stream)
+{
+    const int tiles_x = (w + kTileDim - 1) / kTileDim, tiles_y = (h + kTileDim - 1) / kTileDim;
+    dim3 grid(tiles_x, tiles_y);
+    k_untile<<<grid, 256, 0, stream>>>(tiles, tiles_per_rank_padded, world, only_rank, w, h, tiles_x, image);
+    return cudaGetLastError();
+}
+
+} // namespace b200rt

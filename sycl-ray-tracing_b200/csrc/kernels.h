@@ -1,0 +1,18 @@
+// Launchers of the sm_100a kernels (kernels.cu). Host code only sees these.
+#pragma once
+#include <cuda_runtime.h>
+
+#include "../../include/b200rt.h"
+#include "device_types.h"
+
+namespace b200rt {
+
+cudaError_t launch_megakernel(const SceneDev& S, const RenderParams& P, const float4* fb_in_rowmajor, float4* out_tiles,
+                              unsigned int* work_counter, unsigned long long* ray_counter, cudaStream_t stream);
+cudaError_t launch_primary(const SceneDev& S, const RenderParams& P, int sample, int* prim_out, float* t_out, cudaStream_t stream);
+cudaError_t launch_trace_rays(const SceneDev& S, const float* rays6, int n, int any_hit, int flags, int* prim_out, float* t_out,
+                              float* extra8, cudaStream_t stream);
+cudaError_t launch_untile(const float4* tiles, int tiles_per_rank_padded, int world, int only_rank, int w, int h, float4* image,
+                          cudaStream_t stream);
+
+} // namespace b200rt

@@ -1,0 +1,597 @@
+// Device-side restatement of the reference's per-pixel path (render_kernel.cpp:56-181, :218-759) for sm_100a.
+//
+// This translation unit is compiled with -fmad=false: every float expression below is evaluated exactly as written
+// (IEEE binary32, round-to-nearest, no contraction), which is what the reference's x86-64 build does and what makes
+// the primary-ray closest hit bit-exact. Where a fused multiply-add is wanted for speed (slab tests, which only need
+// to be conservative) it is requested explicitly with fmaf().
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "device_types.h"
+
+namespace b200rt {
+
+#ifndef B200RT_PI_D
+#define B200RT_PI_D 3.14159265358979323846
+#define B200RT_1_PI_D 0.31830988618379067154
+#endif
+#define B200RT_PI_F 3.14159274101257324219f   /* (float)M_PI */
+
+struct v3 { float x, y, z; };
+struct col { float r, g, b; };
+
+__device__ __forceinline__ v3 V(float x, float y, float z) { v3 r; r.x = x; r.y = y; r.z = z; return r; }
+__device__ __forceinline__ v3 operator+(v3 a, v3 b) { return V(a.x + b.x, a.y + b.y, a.z + b.z); }
+__device__ __forceinline__ v3 operator-(v3 a, v3 b) { return V(a.x - b.x, a.y - b.y, a.z - b.z); }
+__device__ __forceinline__ v3 operator-(v3 a) { return V(-a.x, -a.y, -a.z); }
+__device__ __forceinline__ v3 operator*(float k, v3 a) { return V(k * a.x, k * a.y, k * a.z); }      // vec.h:141-149
+__device__ __forceinline__ float dot(v3 u, v3 v) { return u.x * v.x + u.y * v.y + u.z * v.z; }        // vec.h:186-189
+__device__ __forceinline__ v3 cross(v3 u, v3 v)                                                       // vec.h:178-184
+{
+    return V((u.y * v.z) - (u.z * v.y), (u.z * v.x) - (u.x * v.z), (u.x * v.y) - (u.y * v.x));
+}
+__device__ __forceinline__ float length(v3 v) { return sqrtf(v.x * v.x + v.y * v.y + v.z * v.z); }
+__device__ __forceinline__ v3 normalize(v3 v) { float kk = 1.0f / length(v); return kk * v; }         // vec.h:172-176
+// std::max / std::min with libstdc++'s exact comparison order (NaN behaviour included)
+__device__ __forceinline__ float smax(float a, float b) { return (a < b) ? b : a; }
+__device__ __forceinline__ float smin(float a, float b) { return (b < a) ? b : a; }
+
+__device__ __forceinline__ col CO(float r, float g, float b) { col c; c.r = r; c.g = g; c.b = b; return c; }
+__device__ __forceinline__ col operator+(col a, col b) { return CO(a.r + b.r, a.g + b.g, a.b + b.b); }
+__device__ __forceinline__ col operator*(col a, col b) { return CO(a.r * b.r, a.g * b.g, a.b * b.b); }
+__device__ __forceinline__ col operator*(col c, float k) { return CO(c.r * k, c.g * k, c.b * k); }    // color.h:149-157
+__device__ __forceinline__ col operator/(col c, float k) { float kk = 1.0f / k; return c * kk; }      // color.h:169-173
+__device__ __forceinline__ bool is_black(col c) { return c.r == 0.0f && c.g == 0.0f && c.b == 0.0f; }
+
+// ---- RNG: include/xorshift.h:10-31 ------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t xs_next(uint32_t& s)
+{
+    uint32_t x = s;
+    x ^= x << 13; x ^= x >> 17; x ^= x << 5;
+    s = x;
+    return x;
+}
+__device__ __forceinline__ float xs_float(uint32_t& s)
+{
+    // u32 / (float)UINT_MAX: the divisor rounds to 2^32, so the division is an exact scaling; cap 1 - 1e-6f (xorshift.h:17)
+    return smin(__uint2float_rn(xs_next(s)) * 2.3283064365386962890625e-10f, 1.0f - 1.0e-6f);
+}
+// seed of pixel (x, y): 31 + x*y*spp in wrapping int arithmetic (render_kernel.cpp:77), then 10 warm-up draws (:81-82)
+__device__ __forceinline__ uint32_t pixel_rng(int x, int y, int spp)
+{
+    uint32_t s = 31u + (uint32_t)x * (uint32_t)y * (uint32_t)spp;
+#pragma unroll
+    for (int i = 0; i < 10; i++) xs_next(s);
+    return s;
+}
+
+// ---- camera: render_kernel.cpp:56-73, Transform::operator()(Point) mat.cpp:94-111 --------------------------------------
+__device__ __forceinline__ v3 xform_point(const float* m, v3 p)
+{
+    float xt = m[0] * p.x + m[1] * p.y + m[2] * p.z + m[3];
+    float yt = m[4] * p.x + m[5] * p.y + m[6] * p.z + m[7];
+    float zt = m[8] * p.x + m[9] * p.y + m[10] * p.z + m[11];
+    float wt = m[12] * p.x + m[13] * p.y + m[14] * p.z + m[15];
+    if (wt == 1.f) return V(xt, yt, zt);
+    float w = 1.f / wt;
+    return V(xt * w, yt * w, zt * w);
+}
+__device__ __forceinline__ void camera_ray(const CameraDev& c, float x, float y, v3& o, v3& d)
+{
+    float x_ndc = x / (float)c.w * 2.0f - 1.0f;
+    x_ndc *= (float)c.w / (float)c.h;
+    float y_ndc = y / (float)c.h * 2.0f - 1.0f;
+    o = xform_point(c.m, V(0.0f, 0.0f, 0.0f));
+    v3 pw = xform_point(c.m, V(x_ndc, y_ndc, c.fov_dist));
+    d = normalize(pw - o);
+}
+
+// ---- closest / any hit over the flattened BVH -----------------------------------------------------------------------------
+struct Hit
+{
+    float t;      // -1 = none (hit_info.h:11)
+    int prim;     // original primitive index
+    int slot;     // slot in the leaf-ordered triangle stream (-1 for spheres)
+    float u, v;
+    v3 sphere_n;  // only meaningful when slot < 0 && prim >= 0
+};
+
+enum TraceMode { TRACE_CLOSEST = 0, TRACE_ANY = 1, TRACE_SHADOW = 2 };
+
+struct RaySlabs
+{
+    float ix, iy, iz;        // clamped reciprocals of the direction
+    float rc[4], na[4], nb[4];
+};
+
+__device__ __forceinline__ float safe_rcp(float d)
+{
+    return 1.0f / (fabsf(d) < 1e-30f ? copysignf(1e-30f, d) : d);
+}
+
+__device__ __forceinline__ void setup_slabs(v3 o, v3 d, bool use_diag, RaySlabs& rs)
+{
+    rs.ix = safe_rcp(d.x); rs.iy = safe_rcp(d.y); rs.iz = safe_rcp(d.z);
+    if (use_diag)
+    {
+        // diagonal planes (+-1, +-1, 1) (the reference's PLANE_NORMALS[3..6] without the common sqrt(3)/3, bvh.cpp:8-16)
+        const float d1 = fabsf(d.x) + fabsf(d.y) + fabsf(d.z);
+        const float slack = 2.384185791015625e-07f * (fabsf(o.x) + fabsf(o.y) + fabsf(o.z));   // 2^-22 |o|_1 bounds numer rounding
+        const float den[4] = { (d.x + d.y) + d.z, (-d.x + d.y) + d.z, (-d.x - d.y) + d.z, (d.x - d.y) + d.z };
+        const float num[4] = { (o.x + o.y) + o.z, (-o.x + o.y) + o.z, (-o.x - o.y) + o.z, (o.x - o.y) + o.z };
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+        {
+            // near-parallel planes are switched off: their reciprocal is too inexact to stay conservative
+            bool on = fabsf(den[k]) >= 0.03f * d1;
+            rs.rc[k] = on ? 1.0f / den[k] : 1.0f;
+            rs.na[k] = on ? num[k] + slack : 1e30f;
+            rs.nb[k] = on ? num[k] - slack : -1e30f;
+        }
+    }
+}
+
+// Möller–Trumbore exactly as include/triangle.h:16-60, on the stored a, e1 = b - a, e2 = c - a
+__device__ __forceinline__ bool tri_test(const float4 va, const float4 ve1, const float4 ve2, v3 o, v3 d, float& t_out, float& u_out, float& v_out)
+{
+    const float EPSILON = 0.0000001f;
+    v3 edge1 = V(ve1.x, ve1.y, ve1.z), edge2 = V(ve2.x, ve2.y, ve2.z);
+    v3 h = cross(d, edge2);
+    float a = dot(edge1, h);
+    if (a > -EPSILON && a < EPSILON) return false;
+    float f = 1.0f / a;
+    v3 s = o - V(va.x, va.y, va.z);
+    float u = f * dot(s, h);
+    if (u < 0.0f || u > 1.0f) return false;
+    v3 q = cross(s, edge1);
+    float v = f * dot(d, q);
+    if (v < 0.0f || u + v > 1.0f) return false;
+    float t = f * dot(edge2, q);
+    if (t > EPSILON) { t_out = t; u_out = u; v_out = v; return true; }
+    return false;
+}
+
+// Returns true when a hit was found. MODE:
+//   TRACE_CLOSEST : exact closest hit over all triangles (== brute force, ties -> lowest index)
+//   TRACE_ANY     : any triangle hit with t > EPSILON                       (occlusion test of render_kernel.cpp:592,:615)
+//   TRACE_SHADOW  : any triangle hit with t + 1e-4f < tmax                  (evaluate_shadow_ray, :744-759)
+// MODE is a run-time value so that one copy of the loop serves every ray type of the integrators' single trace site
+// (it is only consulted when a triangle test succeeds).
+template <bool use_diag>
+__device__ __forceinline__ bool traverse_tris(const SceneDev& S, v3 o, v3 d, float tmax, const int MODE, Hit& hit)
+{
+    RaySlabs rs;
+    setup_slabs(o, d, use_diag, rs);
+    float tbest = (MODE == TRACE_SHADOW) ? tmax : __int_as_float(0x7f800000);
+    hit.t = -1.0f; hit.prim = -1; hit.slot = -1;
+
+    int stack_ref[kStackSize];
+    float stack_t[kStackSize];
+    int sp = 0;
+    int cur = 0;
+    for (;;)
+    {
+        if (cur >= 0)
+        {
+            const float4* an = S.axis + 4 * (size_t)cur;
+            const float4 n0 = __ldg(an + 0), n1 = __ldg(an + 1), n2 = __ldg(an + 2), n3 = __ldg(an + 3);
+            // L: lo = (n0.x n0.y n0.z) hi = (n0.w n1.x n1.y); R: lo = (n1.z n1.w n2.x) hi = (n2.y n2.z n2.w)
+            float a0 = (n0.x - o.x) * rs.ix, a1 = (n0.w - o.x) * rs.ix;
+            float b0 = (n0.y - o.y) * rs.iy, b1 = (n1.x - o.y) * rs.iy;
+            float c0 = (n0.z - o.z) * rs.iz, c1 = (n1.y - o.z) * rs.iz;
+            float tnL = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), 0.0f));
+            float tfL = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), tbest));
+            a0 = (n1.z - o.x) * rs.ix; a1 = (n2.y - o.x) * rs.ix;
+            b0 = (n1.w - o.y) * rs.iy; b1 = (n2.z - o.y) * rs.iy;
+            c0 = (n2.x - o.z) * rs.iz; c1 = (n2.w - o.z) * rs.iz;
+            float tnR = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), 0.0f));
+            float tfR = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), tbest));
+            // distance-proportional widening keeps the float slab test conservative (Ize, "Robust BVH ray traversal")
+            bool hitL = tnL <= tfL * 1.000001f;
+            bool hitR = tnR <= tfR * 1.000001f;
+            if (use_diag && (hitL || hitR))
+            {
+                const float4* dn = S.diag + 4 * (size_t)cur;
+                if (hitL)
+                {
+                    const float4 nr = __ldg(dn + 0), fr = __ldg(dn + 1);
+                    float p0 = (nr.x - rs.na[0]) * rs.rc[0], q0 = (fr.x - rs.nb[0]) * rs.rc[0];
+                    float p1 = (nr.y - rs.na[1]) * rs.rc[1], q1 = (fr.y - rs.nb[1]) * rs.rc[1];
+                    float p2 = (nr.z - rs.na[2]) * rs.rc[2], q2 = (fr.z - rs.nb[2]) * rs.rc[2];
+                    float p3 = (nr.w - rs.na[3]) * rs.rc[3], q3 = (fr.w - rs.nb[3]) * rs.rc[3];
+                    float tn = fmaxf(fmaxf(fminf(p0, q0), fminf(p1, q1)), fmaxf(fminf(p2, q2), fminf(p3, q3)));
+                    float tf = fminf(fminf(fmaxf(p0, q0), fmaxf(p1, q1)), fminf(fmaxf(p2, q2), fmaxf(p3, q3)));
+                    tnL = fmaxf(tnL, tn); tfL = fminf(tfL, tf);
+                    hitL = tnL <= tfL * 1.00004f;
+                }
+                if (hitR)
+                {
+                    const float4 nr = __ldg(dn + 2), fr = __ldg(dn + 3);
+                    float p0 = (nr.x - rs.na[0]) * rs.rc[0], q0 = (fr.x - rs.nb[0]) * rs.rc[0];
+                    float p1 = (nr.y - rs.na[1]) * rs.rc[1], q1 = (fr.y - rs.nb[1]) * rs.rc[1];
+                    float p2 = (nr.z - rs.na[2]) * rs.rc[2], q2 = (fr.z - rs.nb[2]) * rs.rc[2];
+                    float p3 = (nr.w - rs.na[3]) * rs.rc[3], q3 = (fr.w - rs.nb[3]) * rs.rc[3];
+                    float tn = fmaxf(fmaxf(fminf(p0, q0), fminf(p1, q1)), fmaxf(fminf(p2, q2), fminf(p3, q3)));
+                    float tf = fminf(fminf(fmaxf(p0, q0), fmaxf(p1, q1)), fminf(fmaxf(p2, q2), fmaxf(p3, q3)));
+                    tnR = fmaxf(tnR, tn); tfR = fminf(tfR, tf);
+                    hitR = tnR <= tfR * 1.00004f;
+                }
+            }
+            const int refL = __float_as_int(n3.x), refR = __float_as_int(n3.y);
+            if (hitL && hitR)
+            {
+                const bool r_first = tnR < tnL;
+                stack_ref[sp] = r_first ? refL : refR;
+                stack_t[sp] = r_first ? tnL : tnR;
+                sp++;
+                cur = r_first ? refR : refL;
+                continue;
+            }
+            if (hitL) { cur = refL; continue; }
+            if (hitR) { cur = refR; continue; }
+        }
+        else
+        {
+            const int packed = ~cur;
+            const int first = packed >> 4, count = packed & 15;
+            const float4* tp = S.tris + 3 * (size_t)first;
+            for (int i = 0; i < count; i++, tp += 3)
+            {
+                const float4 va = __ldg(tp), ve1 = __ldg(tp + 1), ve2 = __ldg(tp + 2);
+                float t, u, v;
+                if (tri_test(va, ve1, ve2, o, d, t, u, v))
+                {
+                    if (MODE == TRACE_ANY) { hit.t = t; return true; }
+                    if (MODE == TRACE_SHADOW) { if (t + 1.0e-4f < tmax) { hit.t = t; return true; } continue; }
+                    const int prim = __float_as_int(va.w);
+                    // strict "<" (bvh.h:158); equal t goes to the lower original index, as brute force would (render_kernel.cpp:464)
+                    if (hit.prim < 0 || t < hit.t || (t == hit.t && prim < hit.prim))
+                    {
+                        hit.t = t; hit.prim = prim; hit.slot = first + i; hit.u = u; hit.v = v;
+                        tbest = t;
+                    }
+                }
+            }
+        }
+        // pop, skipping subtrees that start beyond the current best
+        for (;;)
+        {
+            if (sp == 0) return hit.t > 0.0f;
+            sp--;
+            if (stack_t[sp] <= tbest * 1.00004f) { cur = stack_ref[sp]; break; }
+        }
+    }
+}
+
+// Sphere::intersect, include/sphere.h:11-53
+__device__ __forceinline__ bool sphere_test(const SphereDev& s, v3 o, v3 d, float& t_out)
+{
+    v3 L = o - V(s.cx, s.cy, s.cz);
+    float b = 2.0f * dot(d, L);
+    float c = dot(L, L) - s.radius * s.radius;
+    float delta = b * b - 4.0f * 1.0f * c;
+    if (delta < 0.0f) return false;
+    float t = -1.0f;
+    if (delta == 0.0f) t = -b / 2.0f;
+    else
+    {
+        float sq = sqrtf(delta);
+        float t1 = (-b - sq) / 2.0f;
+        float t2 = (-b + sq) / 2.0f;
+        if (t1 < t2) { t = t1; if (t < 0.0f) t = t2; }
+    }
+    if (t < 0.0f) return false;
+    t_out = t;
+    return true;
+}
+
+// INTERSECT_SCENE (render_kernel.cpp:485-511): BVH triangles, then every analytic sphere; "found" iff closest.t > 0.
+// mode TRACE_ANY / TRACE_SHADOW return the occlusion predicates of :592/:615 and evaluate_shadow_ray (:744-759).
+// With analytic spheres in the scene the exact "closest.t > 0" semantics need the true closest hit (a sphere can
+// report t == 0), so the early-out traversals are only used for triangle-only scenes.
+template <bool use_diag>
+__device__ __forceinline__ bool trace_ray(const SceneDev& S, v3 o, v3 d, float tmax, const int mode, Hit& hit)
+{
+    if (S.n_spheres == 0) return traverse_tris<use_diag>(S, o, d, tmax, mode, hit);
+    traverse_tris<use_diag>(S, o, d, tmax, TRACE_CLOSEST, hit);
+    for (int i = 0; i < S.n_spheres; i++)
+    {
+        float t;
+        const SphereDev s = S.spheres[i];
+        if (sphere_test(s, o, d, t))
+            if (t < hit.t || hit.t == -1.0f)
+            {
+                hit.t = t; hit.prim = s.prim; hit.slot = -1; hit.u = -1.0f; hit.v = -1.0f;
+                v3 p = o + t * d;
+                hit.sphere_n = normalize(p - V(s.cx, s.cy, s.cz));
+            }
+    }
+    bool found = hit.t > 0.0f;
+    if (mode == TRACE_SHADOW) found = found && (hit.t + 1.0e-4f < tmax);
+    return found;
+}
+
+// point and geometric normal of a closest hit (triangle.h:46-49: normalize(cross(e1,e2)), never flipped)
+__device__ __forceinline__ void hit_geometry(const SceneDev& S, const Hit& hit, v3 o, v3 d, v3& p, v3& n)
+{
+    p = o + hit.t * d;
+    if (hit.slot >= 0)
+    {
+        const float4 ve1 = __ldg(S.tris + 3 * (size_t)hit.slot + 1), ve2 = __ldg(S.tris + 3 * (size_t)hit.slot + 2);
+        n = normalize(cross(V(ve1.x, ve1.y, ve1.z), V(ve2.x, ve2.y, ve2.z)));
+    }
+    else n = hit.sphere_n;
+}
+
+// ---- BRDF: render_kernel.cpp:5-22, :218-301, :392-451, :513-518 ---------------------------------------------------------------
+__device__ __forceinline__ v3 rotate_around_normal(v3 n, v3 local)
+{
+    float sign = copysignf(1.0f, n.z);
+    const float a = -1.0f / (sign + n.z);
+    const float b = n.x * n.y * a;
+    v3 b1 = V(1.0f + sign * n.x * n.x * a, sign * b, -sign * n.x);
+    v3 b2 = V(b, sign + n.y * n.y * a, -n.y);
+    return (local.x * b1 + local.y * b2) + local.z * n;
+}
+__device__ __forceinline__ float ggx_d(float alpha, float NoH)
+{
+    NoH = smin(NoH, 0.999999f);
+    float alpha2 = alpha * alpha;
+    float NoH2 = NoH * NoH;
+    float b = (NoH2 * (alpha2 - 1.0f) + 1.0f);
+    return (float)((double)alpha2 * B200RT_1_PI_D / (double)(b * b));      // evaluated in double by the reference (:232)
+}
+__device__ __forceinline__ float g1_schlick(float k, float dp) { return dp / (dp * (1.0f - k) + k); }
+__device__ __forceinline__ float power_heuristic(float a, float b) { float a2 = a * a; return a2 / (a2 + b * b); }
+
+__device__ __forceinline__ float ct_pdf(const MaterialDev& m, v3 view, v3 to_light, v3 n)      // :247-258
+{
+    v3 h = normalize(view + to_light);
+    float alpha = m.roughness * m.roughness;
+    float VoH = smax(0.0f, dot(view, h));
+    float NoH = smax(0.0f, dot(n, h));
+    float D = ggx_d(alpha, NoH);
+    return D * NoH / (4.0f * VoH);
+}
+
+__device__ __forceinline__ col ct_terms(const MaterialDev& m, float NoV, float NoL, float NoH, float VoH, float* pdf_out)   // :272-298 / :424-448
+{
+    const float metalness = m.metalness;
+    const float alpha = m.roughness * m.roughness;
+    const float f04 = 0.04f * (1.0f - metalness);
+    const col F0 = CO(f04 + m.dr * metalness, f04 + m.dg * metalness, f04 + m.db * metalness);
+    const float p5 = powf((1.0f - VoH), 5.0f);
+    const col F = CO(F0.r + (1.0f + -F0.r) * p5, F0.g + (1.0f + -F0.g) * p5, F0.b + (1.0f + -F0.b) * p5);   // fresnel_schlick :218-221
+    const float D = ggx_d(alpha, NoH);
+    const float k = alpha / 2.0f;
+    const float G = g1_schlick(k, NoL) * g1_schlick(k, NoV);                                               // :240-245
+    const float kd0 = 1.0f - metalness;
+    const col kD = CO(kd0 * (1.0f + -F.r), kd0 * (1.0f + -F.g), kd0 * (1.0f + -F.b));
+    const col diffuse_part = (kD * CO(m.dr, m.dg, m.db)) / B200RT_PI_F;
+    const col specular_part = ((F * D) * G) / (4.0f * NoV * NoL);
+    if (pdf_out) *pdf_out = D * NoH / (4.0f * VoH);
+    return diffuse_part + specular_part;
+}
+
+__device__ __forceinline__ col ct_brdf(const MaterialDev& m, v3 to_light, v3 view, v3 n)      // :260-301
+{
+    v3 h = normalize(view + to_light);
+    float NoV = smax(0.0f, dot(n, view));
+    float NoL = smax(0.0f, dot(n, to_light));
+    float NoH = smax(0.0f, dot(n, h));
+    float VoH = smax(0.0f, dot(h, view));
+    if (NoV > 0.0f && NoL > 0.0f && NoH > 0.0f) return ct_terms(m, NoV, NoL, NoH, VoH, nullptr);
+    return CO(0.0f, 0.0f, 0.0f);
+}
+
+// cook_torrance_brdf_importance_sample :392-451 — consumes exactly two draws
+__device__ __forceinline__ col ct_sample(const MaterialDev& m, v3 view, v3 n, v3& out_dir, float& pdf, uint32_t& rng)
+{
+    pdf = 0.0f;
+    const float alpha = m.roughness * m.roughness;
+    const float rand1 = xs_float(rng);
+    const float rand2 = xs_float(rng);
+    const float phi = 2.0f * B200RT_PI_F * rand1;
+    const float theta = acosf((1.0f - rand2) / (rand2 * (alpha * alpha - 1.0f) + 1.0f));   // no sqrt: the reference's own variant (:404)
+    const float sin_theta = sinf(theta);
+    v3 local = V(cosf(phi) * sin_theta, sinf(phi) * sin_theta, cosf(theta));
+    v3 mn = rotate_around_normal(n, local);
+    if (dot(mn, n) < 0.0f) return CO(0.0f, 0.0f, 0.0f);
+    v3 to_light = normalize((2.0f * dot(mn, view)) * mn - view);
+    out_dir = to_light;
+    float NoV = smax(0.0f, dot(n, view));
+    float NoL = smax(0.0f, dot(n, to_light));
+    float NoH = smax(0.0f, dot(n, mn));
+    float VoH = smax(0.0f, dot(mn, view));
+    if (NoV > 0.0f && NoL > 0.0f && NoH > 0.0f) return ct_terms(m, NoV, NoL, NoH, VoH, &pdf);
+    return CO(0.0f, 0.0f, 0.0f);
+}
+
+// ---- environment map: render_kernel.cpp:520-567, image.h:80-85,:165-177 ------------------------------------------------------
+__device__ __forceinline__ col env_texel(const SceneDev& S, int idx) { float4 p = __ldg(S.env + idx); return CO(p.x, p.y, p.z); }
+__device__ __forceinline__ int env_offset(const SceneDev& S, int x, int y)
+{
+    int px = min(max(x, 0), S.env_w - 1), py = min(max(y, 0), S.env_h - 1);
+    return py * S.env_w + px;
+}
+__device__ __forceinline__ col env_from_direction(const SceneDev& S, v3 d)
+{
+    float u = 0.5f + atan2f(d.z, d.x) / (2.0f * B200RT_PI_F);
+    float v = 0.5f + asinf(d.y) / B200RT_PI_F;
+    int x = max(min((int)(u * (float)S.env_w), S.env_w - 1), 0);
+    int y = max(min((int)(v * (float)S.env_h), S.env_h - 1), 0);
+    return env_texel(S, y * S.env_w + x);
+}
+__device__ __forceinline__ void env_cdf_search(const SceneDev& S, float value, int& xo, int& yo)
+{
+    int lower = 0, upper = S.env_h - 1;
+    const int x_index = S.env_w - 1;
+    while (lower < upper)
+    {
+        int y_index = (lower + upper) / 2;
+        if (value < __ldg(S.cdf + y_index * S.env_w + x_index)) upper = y_index; else lower = y_index + 1;
+    }
+    const int y = max(min(lower, S.env_h), 0);
+    lower = 0; upper = S.env_w - 1;
+    while (lower < upper)
+    {
+        int xi = (lower + upper) / 2;
+        if (value < __ldg(S.cdf + y * S.env_w + xi)) upper = xi; else lower = xi + 1;
+    }
+    xo = max(min(lower, S.env_w), 0); yo = y;
+}
+
+// ---- one surface interaction, split into the reference's four "side rays" + the continuation ---------------------------------
+// The RNG draw schedule per hit is fixed: [3 light] 2 | 1 2 | 2, and no draw depends on a trace result, so a
+// hit is processed as: for k in 0..3 { generate side ray k; trace it; keep its contribution }, then the continuation.
+struct Surface
+{
+    v3 p, n, view;       // hit point, geometric normal, -ray.direction
+    MaterialDev m;
+};
+
+enum SideKind { SIDE_NONE = 0, SIDE_SHADOW = 1, SIDE_CLOSEST_LIGHT = 2, SIDE_OCCLUSION = 3 };
+
+struct SideRay
+{
+    v3 o, d;
+    float tmax;        // SIDE_SHADOW: distance to the light sample
+    col weight;        // contribution if unoccluded (SIDE_CLOSEST_LIGHT: brdf * cosine, finished by side_light_hit)
+    float pdf;         // SIDE_CLOSEST_LIGHT: direction pdf
+    int kind;
+};
+
+// k = 0: light sample of sample_light_sources (:636-675, sample_random_point_on_lights :715-742); 3 draws iff emissive triangles exist
+__device__ __forceinline__ void side_light_sample(const SceneDev& S, const Surface& sf, uint32_t& rng, SideRay& r)
+{
+    r.kind = SIDE_NONE;
+    if (S.n_emissive <= 0) return;
+    const int pick = (int)(xs_float(rng) * (float)S.n_emissive);
+    const int em_tri = __ldg(S.emissive + pick);
+    const float rand_1 = xs_float(rng);
+    const float rand_2 = xs_float(rng);
+    const int slot = __ldg(S.slot_of_prim + em_tri);
+    const float4 va = __ldg(S.tris + 3 * (size_t)slot), ve1 = __ldg(S.tris + 3 * (size_t)slot + 1), ve2 = __ldg(S.tris + 3 * (size_t)slot + 2);
+    const float sqrt_r1 = sqrtf(rand_1);
+    const float u = 1.0f - sqrt_r1;
+    const float v = (1.0f - rand_2) * sqrt_r1;
+    const v3 AB = V(ve1.x, ve1.y, ve1.z), AC = V(ve2.x, ve2.y, ve2.z);
+    const v3 lp = (V(va.x, va.y, va.z) + u * AB) + v * AC;
+    const v3 nrm = cross(AB, AC);
+    const float len_n = length(nrm);
+    const v3 light_n = (1.0f / len_n) * nrm;
+    const float area = len_n * 0.5f;
+    float light_pdf = 1.0f / ((float)S.n_emissive * area);
+
+    const v3 so = sf.p + 1.0e-4f * sf.n;
+    const v3 sd = lp - so;
+    const float dist = length(sd);
+    const v3 sdn = normalize(sd);
+    const float dot_light = smax(dot(light_n, -sdn), 0.0f);
+    if (!(dot_light > 0.0f)) return;
+    light_pdf *= dist * dist;
+    light_pdf /= dot_light;
+    const col brdf = ct_brdf(sf.m, sdn, sf.view, sf.n);
+    const float bp = ct_pdf(sf.m, sf.view, sdn, sf.n);
+    if (!(bp != 0.0f)) return;
+    const MaterialDev em = S.mats[__ldg(S.mat_idx + em_tri)];
+    const float w = power_heuristic(light_pdf, bp);
+    const float cosine_term = dot(sf.n, sdn);
+    r.weight = (((CO(em.er, em.eg, em.eb) * cosine_term) * brdf) * w) / light_pdf;     // :671
+    r.o = so; r.d = sdn; r.tmax = dist; r.kind = SIDE_SHADOW;
+}
+
+// k = 1: BRDF sample of sample_light_sources (:677-710); 2 draws. The ray is a CLOSEST-hit query (it must know what it hit).
+__device__ __forceinline__ void side_light_brdf(const SceneDev& S, const Surface& sf, uint32_t& rng, SideRay& r)
+{
+    r.kind = SIDE_NONE;
+    v3 dir = V(0.0f, 0.0f, 0.0f);
+    float pdf;
+    const col brdf = ct_sample(sf.m, sf.view, sf.n, dir, pdf, rng);
+    if (is_black(brdf)) return;
+    r.o = sf.p + 1.0e-5f * sf.n; r.d = dir; r.pdf = pdf;
+    r.weight = brdf * dot(sf.n, dir);      // (brdf * cosine_term) of :706
+    r.kind = SIDE_CLOSEST_LIGHT;
+}
+// finishes k = 1 once the closest hit is known (:688-708)
+__device__ __forceinline__ col side_light_hit(const SceneDev& S, const SideRay& r, const Hit& nh)
+{
+    v3 hp, hn;
+    hit_geometry(S, nh, r.o, r.d, hp, hn);
+    const float cos_angle = smax(dot(hn, -r.d), 0.0f);
+    if (!(cos_angle > 0.0f)) return CO(0.0f, 0.0f, 0.0f);
+    const MaterialDev hm = S.mats[__ldg(S.mat_idx + nh.prim)];
+    if (!(hm.er > 0.0f || hm.eg > 0.0f || hm.eb > 0.0f)) return CO(0.0f, 0.0f, 0.0f);
+    const float d2 = nh.t * nh.t;
+    // Triangle::area (triangle.cpp:8-11); the reference indexes the triangle buffer with the primitive index, so an
+    // emissive analytic sphere would read out of bounds there — spheres contribute no area light here.
+    if (nh.slot < 0) return CO(0.0f, 0.0f, 0.0f);
+    const float4 ve1 = __ldg(S.tris + 3 * (size_t)nh.slot + 1), ve2 = __ldg(S.tris + 3 * (size_t)nh.slot + 2);
+    const float light_area = length(cross(V(ve1.x, ve1.y, ve1.z), V(ve2.x, ve2.y, ve2.z))) / 2.0f;
+    const float light_pdf = d2 / (light_area * cos_angle);        // no 1/N_lights: kept (:702)
+    const float w = power_heuristic(r.pdf, light_pdf);
+    return ((r.weight * CO(hm.er, hm.eg, hm.eb)) * w) / r.pdf;
+}
+
+// k = 2: env-map sample of sample_environment_map (:571-604); 1 draw
+__device__ __forceinline__ void side_env_sample(const SceneDev& S, const Surface& sf, uint32_t& rng, SideRay& r)
+{
+    r.kind = SIDE_NONE;
+    const float total = S.cdf_total;
+    int x, y;
+    env_cdf_search(S, xs_float(rng) * total, x, y);
+    const float u = (float)x / (float)S.env_w;
+    const float v = (float)y / (float)S.env_h;
+    const float phi = (float)((double)(u * 2.0f) * B200RT_PI_D);             // double in the reference (:578-579)
+    const float theta = (float)((double)v * B200RT_PI_D);
+    const float sin_theta = sinf(theta);
+    const float cos_theta = cosf(theta);
+    const v3 dir = V(-sin_theta * cosf(phi), -cos_theta, -sin_theta * sinf(phi));
+    const float cosine_term = dot(sf.n, dir);
+    if (!(cosine_term > 0.0f)) return;
+    const int idx = env_offset(S, x, y);
+    const col radiance = env_texel(S, idx);
+    float env_pdf = (float)(0.3086 * (double)radiance.r + 0.6094 * (double)radiance.g + 0.0820 * (double)radiance.b) / total;   // image.h:80-85
+    env_pdf = (float)((double)((env_pdf * (float)S.env_w) * (float)S.env_h) / ((double)2.0f * B200RT_PI_D * B200RT_PI_D * (double)sin_theta));   // :595
+    const col brdf = ct_brdf(sf.m, dir, sf.view, sf.n);
+    const float brdf_pdf = ct_pdf(sf.m, sf.view, dir, sf.n);
+    const float w = power_heuristic(env_pdf, brdf_pdf);
+    r.weight = (((brdf * cosine_term) * w) * radiance) / env_pdf;          // :602
+    r.o = sf.p + 1.0e-4f * sf.n; r.d = dir; r.kind = SIDE_OCCLUSION;
+}
+
+// k = 3: BRDF sample of sample_environment_map (:606-628); 2 draws
+__device__ __forceinline__ void side_env_brdf(const SceneDev& S, const Surface& sf, uint32_t& rng, SideRay& r)
+{
+    r.kind = SIDE_NONE;
+    v3 dir = V(0.0f, 0.0f, 0.0f);
+    float bpdf;
+    const col brdf = ct_sample(sf.m, sf.view, sf.n, dir, bpdf, rng);
+    const float cosine_term = smax(dot(sf.n, dir), 0.0f);
+    if (!(bpdf != 0.0f && cosine_term > 0.0f)) return;
+    const col sky = env_from_direction(S, dir);
+    const float theta_b = acosf(dir.z);                                     // z, not y: the reference's own convention (:618)
+    const float sin_b = sinf(theta_b);
+    float env_pdf = (0.3086f * sky.r + 0.6094f * sky.g + 0.0820f * sky.b) / S.cdf_total;
+    env_pdf *= (float)(S.env_w * S.env_h);
+    env_pdf = (float)((double)env_pdf / ((double)2.0f * B200RT_PI_D * B200RT_PI_D * (double)sin_b));
+    const float w = power_heuristic(bpdf, env_pdf);
+    r.weight = (((sky * w) * cosine_term) * brdf) / bpdf;                  // :626
+    r.o = sf.p + 1.0e-5f * sf.n; r.d = dir; r.kind = SIDE_OCCLUSION;
+}
+
+// tone map of render_kernel.cpp:171-180 applied to (framebuffer + mean radiance); alpha follows the reference's Color ops
+__device__ __forceinline__ float4 tonemap(float4 fb_in, col mean)
+{
+    const float gamma = 2.2f, exposure = 1.5f;
+    const float r = fb_in.x + mean.r, g = fb_in.y + mean.g, b = fb_in.z + mean.b;
+    float4 o;
+    o.x = powf(1.0f + -expf(-r * exposure), 1.0f / gamma);
+    o.y = powf(1.0f + -expf(-g * exposure), 1.0f / gamma);
+    o.z = powf(1.0f + -expf(-b * exposure), 1.0f / gamma);
+    o.w = 1.0f + -(-fb_in.w * exposure);      // Color::operator* scales alpha, exp()/pow() pass it through (color.h:149-183)
+    return o;
+}
+
+} // namespace b200rt
