@@ -67,9 +67,12 @@ def main():
         kat[f"floats_{seed}"] = fl
     save("xorshift.npz", **kat)
 
+    # prim = the octree's answer (BVH::intersect), prim_brute = RenderKernel::intersect_scene's (lowest index on exact-t ties)
     for key, s in ref_scenes.items():
         prim, t, _ = s.primary(cams[CAMS[key]], 128, 128, mode=0)
-        save(f"primary_{key}.npz", prim=prim.astype(np.int16), t=t, w=128, h=128)
+        pb, tb, _ = s.primary(cams[CAMS[key]], 128, 128, mode=1)
+        assert np.array_equal(t.view(np.uint32), tb.view(np.uint32))
+        save(f"primary_{key}.npz", prim=prim.astype(np.int16), prim_brute=pb.astype(np.int16), t=t, w=128, h=128)
 
     env_const = np.full((2, 4, 4), 1.0e-20, np.float32); env_const[..., 3] = 0.0
     env_test = test_env()
@@ -85,7 +88,10 @@ def main():
     c2 = scenes.c2_scene(nu=100, nv=50)
     s = o.scene_from_arrays(c2["tri9"], c2["mat_idx"], c2["mats10"], c2["emissive"])
     prim, t, _ = s.primary(cams["c2"], 240, 135, mode=0)
-    save("primary_c2small.npz", prim=prim.astype(np.int32), t=t, w=240, h=135, nu=100, nv=50)
+    pb, tb, _ = s.primary(cams["c2"], 240, 135, mode=1)
+    assert np.array_equal(t.view(np.uint32), tb.view(np.uint32))
+    print("c2small: exact-t ties where the octree's traversal order and brute force pick different triangles:", int((prim != pb).sum()))
+    save("primary_c2small.npz", prim=prim.astype(np.int32), prim_brute=pb.astype(np.int32), t=t, w=240, h=135, nu=100, nv=50)
 
     # C3-class (small): metal displaced sphere on a ground quad under the procedural sun+sky
     c3 = scenes.c3_scene(roughness=0.25, nu=100, nv=50, sky_w=64, sky_h=32)

@@ -13,6 +13,15 @@ def bits(a):
     return np.ascontiguousarray(a, np.float32).view(np.uint32)
 
 
+def assert_primary_parity(prim, t, g_prim_octree, g_prim_brute, g_t, max_ties):
+    """Bit-exact t everywhere; the primitive index equals brute force's everywhere (lowest index on an exact-t tie) and
+    the octree's everywhere except on those ties (the octree resolves ties by traversal order)."""
+    assert np.array_equal(bits(t), bits(g_t)), f"{(bits(t) != bits(g_t)).sum()} t-bit mismatches"
+    assert np.array_equal(prim, g_prim_brute.astype(np.int32)), f"{(prim != g_prim_brute).sum()} mismatches vs brute force"
+    ties = prim != g_prim_octree.astype(np.int32)
+    assert ties.sum() <= max_ties, f"{ties.sum()} octree mismatches"
+
+
 def make_scene(rt, golden_scenes, key, env=None, **kw):
     a = scene_arrays(golden_scenes, key)
     return rt.Scene(a["tri9"], a["mat_idx"], a["mats10"], a["emissive"], skysphere=env, **kw)
@@ -57,8 +66,7 @@ def test_primary_bit_exact_bundled(rt, golden_scenes, golden_cameras, key):
     g = load_golden(f"primary_{key}.npz")
     sc = make_scene(rt, golden_scenes, key)
     prim, t, st = sc.trace_primary(cam(rt, golden_cameras, CAM_OF[key]), int(g["w"]), int(g["h"]))
-    assert np.array_equal(prim, g["prim"].astype(np.int32)), f"{(prim != g['prim']).sum()} primitive mismatches"
-    assert np.array_equal(bits(t), bits(g["t"])), f"{(bits(t) != bits(g['t'])).sum()} t-bit mismatches"
+    assert_primary_parity(prim, t, g["prim"], g["prim_brute"], g["t"], max_ties=0)
     # 7-plane and 3-plane traversals must agree exactly
     prim2, t2, _ = sc.trace_primary(cam(rt, golden_cameras, CAM_OF[key]), int(g["w"]), int(g["h"]), flags=rt.FLAG_AXIS_SLABS_ONLY)
     assert np.array_equal(prim, prim2) and np.array_equal(bits(t), bits(t2))
@@ -71,7 +79,7 @@ def test_primary_bit_exact_c2_small(rt, golden_cameras):
     sc = rt.Scene(c2["tri9"], c2["mat_idx"], c2["mats10"], c2["emissive"])
     assert np.array_equal(c2["camera"].as_array17(), golden_cameras["c2"])
     prim, t, _ = sc.trace_primary(c2["camera"], int(g["w"]), int(g["h"]))
-    assert np.array_equal(prim, g["prim"]) and np.array_equal(bits(t), bits(g["t"]))
+    assert_primary_parity(prim, t, g["prim"], g["prim_brute"], g["t"], max_ties=11)      # 11 shared-edge ties on the x=120 column
 
 
 def test_primary_c2_full_vs_oracle(rt):
@@ -85,8 +93,16 @@ def test_primary_c2_full_vs_oracle(rt):
     o = best_oracle()
     os_ = o.scene_from_arrays(c2["tri9"], c2["mat_idx"], c2["mats10"], c2["emissive"])
     rprim, rt_, _ = os_.primary(c2["camera"].as_array17(), 1920, 1080, mode=0)
-    mism = (prim != rprim) | (bits(t) != bits(rt_))
-    assert mism.sum() == 0, f"{mism.sum()} of {mism.size} primary rays differ from the {o.kind} oracle"
+    assert np.array_equal(bits(t), bits(rt_)), f"{(bits(t) != bits(rt_)).sum()} t-bit mismatches vs the {o.kind} oracle"
+    ties = prim != rprim
+    # the compiled reference's octree resolves exact-t ties (rays through shared edges) by traversal order; the port
+    # and the GPU take the lowest index like brute force
+    assert ties.sum() <= (200 if o.kind == "reference" else 0), f"{ties.sum()} primitive mismatches vs the {o.kind} oracle"
+    if o.kind == "reference":
+        from oracle.oracle import PortOracle
+        ps = PortOracle().scene_from_arrays(c2["tri9"], c2["mat_idx"], c2["mats10"], c2["emissive"])
+        pprim, pt, _ = ps.primary(c2["camera"].as_array17(), 1920, 1080, mode=0)
+        assert np.array_equal(prim, pprim) and np.array_equal(bits(t), bits(pt))
 
 
 # ---- radiance ---------------------------------------------------------------------------------------------------------------
