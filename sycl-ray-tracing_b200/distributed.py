@@ -1,0 +1,106 @@
+"""Multi-GPU frame rendering: one process per GPU (torchrun), scene replicated, image cut into interleaved 16x16 tiles
+(tile_id % world == rank), one gather of the per-rank tile buffers to rank 0 per frame (NCCL over NVLink when the
+tensors are CUDA tensors), then the un-tile kernel. The reference has no counterpart (it is one OpenMP process,
+render_kernel.cpp:198); pixels are independent (per-pixel seed 31 + x*y*spp, :77), so there is no exchange step during
+rendering and the N-rank image equals the 1-rank image bit for bit.
+
+torch is plumbing only here: device buffers, streams and torch.distributed. The fill/untile steps are injectable so the
+tile bookkeeping can be exercised on CPU with the gloo backend (tests/test_distributed_cpu.py).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+TILE = 16
+TILE_PX = 256
+
+
+def tiles_for_rank(w: int, h: int, rank: int, world: int) -> int:
+    n = ((w + TILE - 1) // TILE) * ((h + TILE - 1) // TILE)
+    return (n - rank + world - 1) // world
+
+
+def tile_slot_coords(w: int, h: int, rank: int, world: int, tiles_padded: int) -> np.ndarray:
+    """(tiles_padded*256, 2) int32 pixel coordinates (x, y) of every slot of a rank's tile-major buffer; (-1, -1) for
+    slots outside the frame or in padding tiles. Host-side statement of the kernels' unit_pixel() mapping."""
+    tiles_x = (w + TILE - 1) // TILE
+    out = np.full((tiles_padded * TILE_PX, 2), -1, np.int32)
+    n = tiles_for_rank(w, h, rank, world)
+    slot = np.arange(TILE_PX)
+    sub, lane = slot // 32, slot % 32
+    lx = (sub & 1) * 8 + (lane & 7)
+    ly = (sub >> 1) * 4 + (lane >> 3)
+    for k in range(n):
+        tile = rank + k * world
+        tx, ty = tile % tiles_x, tile // tiles_x
+        x, y = tx * TILE + lx, ty * TILE + ly
+        ok = (x < w) & (y < h)
+        out[k * TILE_PX:(k + 1) * TILE_PX, 0] = np.where(ok, x, -1)
+        out[k * TILE_PX:(k + 1) * TILE_PX, 1] = np.where(ok, y, -1)
+    return out
+
+
+def untile_numpy(gathered: np.ndarray, w: int, h: int, world: int) -> np.ndarray:
+    """numpy statement of the k_untile kernel (test helper for the CPU/gloo path)."""
+    tiles_padded = gathered.shape[1] // TILE_PX
+    img = np.zeros((h, w, gathered.shape[2]), gathered.dtype)
+    for r in range(world):
+        xy = tile_slot_coords(w, h, r, world, tiles_padded)
+        ok = xy[:, 0] >= 0
+        img[xy[ok, 1], xy[ok, 0]] = gathered[r][ok]
+    return img
+
+
+class FrameGatherer:
+    """Owns the per-rank tile buffer, the gathered buffer and the final image (rank 0) and runs
+    fill -> gather -> untile for one frame."""
+
+    def __init__(self, w: int, h: int, rank: int, world: int, device, fill_tiles, untile, channels: int = 4):
+        import torch
+        import torch.distributed as dist
+        self.torch, self.dist = torch, dist
+        self.w, self.h, self.rank, self.world = w, h, rank, world
+        self.tiles_padded = tiles_for_rank(w, h, 0, world)
+        self.n_my_tiles = tiles_for_rank(w, h, rank, world)
+        self.fill_tiles, self.untile = fill_tiles, untile
+        self.tiles = torch.zeros((self.tiles_padded * TILE_PX, channels), dtype=torch.float32, device=device)
+        self.gathered = None
+        self.image = None
+        if rank == 0:
+            self.gathered = torch.zeros((world, self.tiles_padded * TILE_PX, channels), dtype=torch.float32, device=device)
+            self.image = torch.zeros((h, w, channels), dtype=torch.float32, device=device)
+
+    def frame(self):
+        """Renders this rank's tiles, gathers to rank 0 and un-tiles there. Returns the image tensor on rank 0, else None."""
+        self.fill_tiles(self.tiles)
+        if self.world > 1:
+            if self.rank == 0:
+                self.dist.gather(self.tiles, gather_list=list(self.gathered.unbind(0)), dst=0)
+            else:
+                self.dist.gather(self.tiles, gather_list=None, dst=0)
+            src = self.gathered
+        else:
+            src = self.tiles.unsqueeze(0)
+        if self.rank == 0:
+            self.untile(src, self.image)
+            return self.image
+        return None
+
+
+def make_cuda_gatherer(scene, camera, w, h, spp, max_bounces, rank, world, device, integrator=0, flags=0):
+    """FrameGatherer whose fill/untile steps are the CUDA kernels, launched on torch's current stream."""
+    import torch
+
+    def fill(tiles):
+        st = torch.cuda.current_stream(device).cuda_stream
+        scene.render_tiles_device(camera, w, h, spp, max_bounces, tiles.data_ptr(), stream_ptr=st, integrator=integrator,
+                                  flags=flags, rank=rank, world=world)
+
+    g = None
+
+    def untile(src, image):
+        st = torch.cuda.current_stream(device).cuda_stream
+        scene.untile_device(src.data_ptr(), g.tiles_padded, world, w, h, image.data_ptr(), stream_ptr=st)
+
+    g = FrameGatherer(w, h, rank, world, device, fill, untile)
+    return g

@@ -1,7 +1,6 @@
 #!/bin/bash
-# first-contact GPU check: build is in-tree already; run the gpu tests verbosely
-set -x
-nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total --format=csv
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q -s 2>&1 | tail -60 > gpurun_out/pytest_gpu.log
-tail -60 gpurun_out/pytest_gpu.log
+nproc; free -g | head -2
+python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -3
+python bench.py --workload c2 --steps 5 --warmup 3 > gpurun_out/bench_c2.json 2> gpurun_out/bench_c2.err; tail -2 gpurun_out/bench_c2.err; cat gpurun_out/bench_c2.json
+python bench.py --workload c3 --spp 4 --steps 3 --warmup 3 --no-cpu-baseline > gpurun_out/bench_c3_4spp.json 2> gpurun_out/bench_c3_4spp.err; tail -2 gpurun_out/bench_c3_4spp.err; cat gpurun_out/bench_c3_4spp.json
