@@ -49,7 +49,7 @@ def parse_args():
     p.add_argument("--spp", type=int, default=0, help="override samples per pixel (0 = the workload's)")
     p.add_argument("--width", type=int, default=0)
     p.add_argument("--height", type=int, default=0)
-    p.add_argument("--integrator", type=int, default=0)
+    p.add_argument("--integrator", type=int, default=1, help="0 = megakernel, 1 = wavefront (default)")
     p.add_argument("--flags", type=int, default=0)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-sample", default="", help="WxHxSPP of the bounded CPU sample (default per workload)")
@@ -266,8 +266,8 @@ def main():
             dist.all_reduce(rays_t)
         rays_per_frame = int(rays_t.item())
         del tiles_probe
-        kernel_name = "k_pathtrace_mega"
-        launches_per_step = 1 + (1 if rank == 0 else 0)
+        kernel_name = "k_pathtrace_mega" if args.integrator == 0 else "wf_trace (+ wf_shade), all launches of the frame"
+        launches_per_step = int(st["gpu_launches"]) + (1 if rank == 0 else 0)
 
     for _ in range(args.warmup):
         step()

@@ -154,6 +154,11 @@ int b200rt_trace_primary_device(b200rt_scene* scene, const float* camera17, int 
                                 void* dev_prim, void* dev_t, const b200rt_render_options* opts_or_null, void* cuda_stream,
                                 b200rt_stats* stats_or_null);
 
+/* device-pointer variant of b200rt_trace_rays (dev_extra8 may be NULL) */
+int b200rt_trace_rays_device(b200rt_scene* scene, const void* dev_rays6, int n_rays, int any_hit, void* dev_prim, void* dev_t,
+                             void* dev_extra8_or_null, const b200rt_render_options* opts_or_null, void* cuda_stream,
+                             b200rt_stats* stats_or_null);
+
 const char* b200rt_last_error(void);
 const char* b200rt_version(void);
 

@@ -340,6 +340,16 @@ class Scene:
         B.check(B.load_library().b200rt_untile_device(self._h, C.c_void_p(dev_gathered_ptr), tiles_per_rank_padded, world, w, h,
                                                       C.c_void_p(dev_image_ptr), C.c_void_p(stream_ptr)))
 
+    def trace_rays_device(self, dev_rays6_ptr: int, n: int, dev_prim_ptr: int, dev_t_ptr: int, dev_extra8_ptr: int = 0,
+                          any_hit: bool = False, stream_ptr: int = 0, flags: int = 0, want_stats: bool = False):
+        st = B.Stats()
+        o = self._opts(0, flags)
+        B.check(B.load_library().b200rt_trace_rays_device(self._h, C.c_void_p(dev_rays6_ptr), n, 1 if any_hit else 0,
+                                                          C.c_void_p(dev_prim_ptr), C.c_void_p(dev_t_ptr),
+                                                          C.c_void_p(dev_extra8_ptr) if dev_extra8_ptr else None, C.byref(o),
+                                                          C.c_void_p(stream_ptr), C.byref(st) if want_stats else None))
+        return st.as_dict() if want_stats else None
+
     def trace_primary_device(self, camera: Camera, w, h, dev_prim_ptr: int, dev_t_ptr: int, sample: int = -1,
                              spp_for_seed: int = 1, stream_ptr: int = 0, flags: int = 0, rank: int = 0, world: int = 1,
                              want_stats: bool = False):

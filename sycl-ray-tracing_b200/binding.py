@@ -56,7 +56,7 @@ EXPORTS = [
     "b200rt_bvh_destroy", "b200rt_scene_create", "b200rt_scene_destroy", "b200rt_scene_set_materials",
     "b200rt_scene_get_bvh_info", "b200rt_scene_device_bytes", "b200rt_default_render_options", "b200rt_render",
     "b200rt_trace_primary", "b200rt_trace_rays", "b200rt_tiles_for_rank", "b200rt_render_tiles_device",
-    "b200rt_untile_device", "b200rt_trace_primary_device", "b200rt_last_error", "b200rt_version",
+    "b200rt_untile_device", "b200rt_trace_primary_device", "b200rt_trace_rays_device", "b200rt_last_error", "b200rt_version",
 ]
 
 _lib = None
@@ -96,6 +96,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     L.b200rt_render_tiles_device.argtypes = [VP, FP, I, I, I, I, VP, C.POINTER(RenderOptions), VP, C.POINTER(Stats)]
     L.b200rt_untile_device.argtypes = [VP, VP, I, I, I, I, VP, VP]
     L.b200rt_trace_primary_device.argtypes = [VP, FP, I, I, I, I, VP, VP, C.POINTER(RenderOptions), VP, C.POINTER(Stats)]
+    L.b200rt_trace_rays_device.argtypes = [VP, VP, I, I, VP, VP, VP, C.POINTER(RenderOptions), VP, C.POINTER(Stats)]
     _lib = L
     return L
 

@@ -28,6 +28,7 @@ struct b200rt_scene
     size_t bytes = 0;
     std::vector<void*> allocs;
     MaterialDev* d_mats = nullptr; int mats_cap = 0;
+    std::vector<char> mat_used;           // material slots some primitive references (slot 0 of parse_obj is emissive but normally unused)
     // per-scene scratch, grown on demand and kept across calls
     unsigned int* d_work = nullptr;
     unsigned long long* d_rays = nullptr;
@@ -35,6 +36,9 @@ struct b200rt_scene
     float4* d_image = nullptr; size_t image_cap = 0;
     int* d_prim = nullptr; float* d_t = nullptr; size_t prim_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    // wavefront integrator state (allocated on first use, grown on demand)
+    WfBuffers wf{}; std::vector<void*> wf_allocs; int wf_cap = 0;
+    unsigned int* h_active = nullptr;     // pinned
 };
 
 namespace {
@@ -129,7 +133,51 @@ int ensure_scratch(b200rt_scene* s, size_t tile_px, size_t image_px, size_t prim
     return B200RT_OK;
 }
 
-int convert_materials(const float* materials10, int n, std::vector<MaterialDev>& out, int* any_emissive)
+template <typename T>
+cudaError_t wf_alloc(b200rt_scene* s, T** p, size_t n)
+{
+    void* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, n * sizeof(T));
+    if (e == cudaSuccess) { s->wf_allocs.push_back(d); *p = (T*)d; }
+    return e;
+}
+
+int ensure_wavefront(b200rt_scene* s, int n_slots)
+{
+    if (!s->h_active) CU(cudaMallocHost(&s->h_active, sizeof(unsigned int)));
+    if (n_slots <= s->wf_cap) { s->wf.n_slots = n_slots; return B200RT_OK; }
+    for (void* p : s->wf_allocs) cudaFree(p);
+    s->wf_allocs.clear(); s->wf_cap = 0;
+    WfBuffers& w = s->wf;
+    const size_t n = (size_t)n_slots;
+    CU(wf_alloc(s, &w.rng, n)); CU(wf_alloc(s, &w.sample, n)); CU(wf_alloc(s, &w.bounce, n)); CU(wf_alloc(s, &w.flags, n));
+    CU(wf_alloc(s, &w.final_c, n)); CU(wf_alloc(s, &w.sample_c, n)); CU(wf_alloc(s, &w.thr, n)); CU(wf_alloc(s, &w.thr_next, n));
+    CU(wf_alloc(s, &w.ray_o, 5 * n)); CU(wf_alloc(s, &w.ray_d, 5 * n)); CU(wf_alloc(s, &w.side_w, 4 * n));
+    CU(wf_alloc(s, &w.res_t, 5 * n)); CU(wf_alloc(s, &w.res_prim, 5 * n)); CU(wf_alloc(s, &w.res_tslot, 5 * n));
+    CU(wf_alloc(s, &w.queue, 5 * n)); CU(wf_alloc(s, &w.counters, 8)); CU(wf_alloc(s, &w.rays_total, 1));
+    w.n_slots = n_slots;
+    s->wf_cap = n_slots;
+    return B200RT_OK;
+}
+
+// runs the selected integrator for this rank's tiles on `st`; *launches receives the number of kernels launched
+int run_integrator(b200rt_scene* s, const RenderParams& P, int integrator, const float4* fb_in, float4* out_tiles, cudaStream_t st, int* launches)
+{
+    if (integrator == B200RT_INTEGRATOR_WAVEFRONT)
+    {
+        int rc = ensure_wavefront(s, P.n_rank_tiles * kTilePixels);
+        if (rc) return rc;
+        CU(run_wavefront(s->dev, P, s->wf, fb_in, out_tiles, s->h_active, st, launches));
+        // the frame's ray count lives in wf.rays_total; mirror it into the shared counter the callers read
+        CU(cudaMemcpyAsync(s->d_rays, s->wf.rays_total, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+        return B200RT_OK;
+    }
+    CU(launch_megakernel(s->dev, P, fb_in, out_tiles, s->d_work, s->d_rays, st));
+    *launches = 1;
+    return B200RT_OK;
+}
+
+int convert_materials(const float* materials10, int n, const std::vector<char>& used, std::vector<MaterialDev>& out, int* any_emissive)
 {
     out.resize((size_t)std::max(n, 1));
     *any_emissive = 0;
@@ -140,7 +188,8 @@ int convert_materials(const float* materials10, int n, std::vector<MaterialDev>&
         d.er = m[0]; d.eg = m[1]; d.eb = m[2];
         d.dr = m[4]; d.dg = m[5]; d.db = m[6];
         d.metalness = m[8]; d.roughness = m[9];
-        if (m[0] > 0.0f || m[1] > 0.0f || m[2] > 0.0f) *any_emissive = 1;
+        const bool referenced = i >= (int)used.size() || used[i];
+        if (referenced && (m[0] > 0.0f || m[1] > 0.0f || m[2] > 0.0f)) *any_emissive = 1;
     }
     return B200RT_OK;
 }
@@ -249,6 +298,8 @@ int b200rt_scene_create(const float* tri_xyz9, int n_tri, const int* tri_materia
     if (!s) { delete own; return fail(B200RT_ERR_ALLOC, "out of host memory"); }
     s->device = device;
     s->info = bvh->flat.info;
+    s->mat_used.assign((size_t)n_materials, 0);
+    for (int i = 0; i < n_material_indices; i++) s->mat_used[tri_material[i]] = 1;
     int rc = B200RT_OK;
     do
     {
@@ -301,7 +352,7 @@ int b200rt_scene_set_materials(b200rt_scene* s, const float* materials10, int n_
     CU(cudaSetDevice(s->device));
     std::vector<MaterialDev> mats;
     int any = 0;
-    convert_materials(materials10, n_materials, mats, &any);
+    convert_materials(materials10, n_materials, s->mat_used, mats, &any);
     if (n_materials > s->mats_cap)
     {
         if (s->d_mats) { cudaFree(s->d_mats); s->d_mats = nullptr; }
@@ -327,6 +378,8 @@ void b200rt_scene_destroy(b200rt_scene* s)
     if (s->d_image) cudaFree(s->d_image);
     if (s->d_prim) cudaFree(s->d_prim);
     if (s->d_t) cudaFree(s->d_t);
+    for (void* p : s->wf_allocs) cudaFree(p);
+    if (s->h_active) cudaFreeHost(s->h_active);
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     delete s;
@@ -360,8 +413,11 @@ int b200rt_render_tiles_device(b200rt_scene* s, const float* camera17, int w, in
     CU(cudaSetDevice(s->device));
     if ((rc = ensure_scratch(s, 0, 0, 0))) return rc;
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    if (stats) { CU(cudaMemsetAsync(s->d_rays, 0, sizeof(unsigned long long), st)); CU(cudaEventRecord(s->ev0, st)); }
-    CU(launch_megakernel(s->dev, P, nullptr, (float4*)dev_tiles, s->d_work, s->d_rays, st));
+    const int integrator = opts ? opts->integrator : B200RT_INTEGRATOR_MEGAKERNEL;
+    CU(cudaMemsetAsync(s->d_rays, 0, sizeof(unsigned long long), st));
+    if (stats) CU(cudaEventRecord(s->ev0, st));
+    int launches = 0;
+    if ((rc = run_integrator(s, P, integrator, nullptr, (float4*)dev_tiles, st, &launches))) return rc;
     if (stats)
     {
         CU(cudaEventRecord(s->ev1, st));
@@ -370,7 +426,7 @@ int b200rt_render_tiles_device(b200rt_scene* s, const float* camera17, int w, in
         CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
         std::memset(stats, 0, sizeof(*stats));
         CU(cudaMemcpy(&stats->rays, s->d_rays, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        stats->kernel_ms = ms; stats->total_ms = ms; stats->gpu_launches = 1;
+        stats->kernel_ms = ms; stats->total_ms = ms; stats->gpu_launches = launches;
         // pixels of this rank that lie inside the frame
         unsigned long long px = 0;
         for (int k = 0; k < P.n_rank_tiles; k++)
@@ -411,7 +467,10 @@ int b200rt_render(b200rt_scene* s, const float* camera17, int w, int h, int spp,
     CU(cudaMemsetAsync(s->d_rays, 0, sizeof(unsigned long long), st));
     CU(cudaEventRecord(s->ev0, st));
     const float4* fb_in = (P.flags & B200RT_FLAG_FB_IS_ZERO) ? nullptr : s->d_image;
-    CU(launch_megakernel(s->dev, P, fb_in, s->d_tiles, s->d_work, s->d_rays, st));
+    const int integrator = opts ? opts->integrator : B200RT_INTEGRATOR_MEGAKERNEL;
+    if (integrator != B200RT_INTEGRATOR_MEGAKERNEL && integrator != B200RT_INTEGRATOR_WAVEFRONT) return fail(B200RT_ERR_ARG, "unknown integrator %d", integrator);
+    int launches = 0;
+    if ((rc = run_integrator(s, P, integrator, fb_in, s->d_tiles, st, &launches))) return rc;
     CU(launch_untile(s->d_tiles, P.n_rank_tiles, P.world, P.world > 1 ? P.rank : -1, w, h, s->d_image, st));
     CU(cudaEventRecord(s->ev1, st));
     CU(cudaMemcpyAsync(fb, s->d_image, image_px * sizeof(float4), cudaMemcpyDeviceToHost, st));
@@ -431,7 +490,7 @@ int b200rt_render(b200rt_scene* s, const float* camera17, int w, int h, int spp,
         }
         stats->samples = px * (unsigned long long)spp;
         stats->kernel_ms = ms;
-        stats->gpu_launches = 2;
+        stats->gpu_launches = launches + 1;
         stats->h2d_bytes = h2d; stats->d2h_bytes = d2h;
         stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
     }
@@ -494,6 +553,29 @@ int b200rt_trace_primary(b200rt_scene* s, const float* camera17, int w, int h, i
     {
         stats->d2h_bytes = px * 8; stats->h2d_bytes = 17 * sizeof(float);
         stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
+    }
+    return B200RT_OK;
+}
+
+int b200rt_trace_rays_device(b200rt_scene* s, const void* dev_rays6, int n, int any_hit, void* dev_prim, void* dev_t, void* dev_extra8,
+                             const b200rt_render_options* opts, void* cuda_stream, b200rt_stats* stats)
+{
+    if (!s) return fail(B200RT_ERR_ARG, "NULL scene");
+    if (n < 0 || (n > 0 && (!dev_rays6 || !dev_prim || !dev_t))) return fail(B200RT_ERR_ARG, "bad ray buffers");
+    CU(cudaSetDevice(s->device));
+    int rc = ensure_scratch(s, 0, 0, 0);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    if (stats) CU(cudaEventRecord(s->ev0, st));
+    CU(launch_trace_rays(s->dev, (const float*)dev_rays6, n, any_hit, opts ? opts->flags : 0, (int*)dev_prim, (float*)dev_t, (float*)dev_extra8, st));
+    if (stats)
+    {
+        CU(cudaEventRecord(s->ev1, st));
+        CU(cudaEventSynchronize(s->ev1));
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        std::memset(stats, 0, sizeof(*stats));
+        stats->kernel_ms = ms; stats->total_ms = ms; stats->gpu_launches = 1; stats->rays = (unsigned long long)n;
     }
     return B200RT_OK;
 }

@@ -58,4 +58,18 @@ struct RenderParams
     int flags;
 };
 
+// wavefront integrator state: one slot per pixel of this rank's tile-major buffer (SoA, HBM resident)
+struct WfBuffers
+{
+    int n_slots;
+    uint32_t* rng; int* sample; int* bounce; int* flags;
+    float4* final_c; float4* sample_c; float4* thr; float4* thr_next;
+    float4* ray_o; float4* ray_d;             // [5 * n_slots]: k * n_slots + slot; k = 0..3 side rays, 4 = path ray; .w = tmax / ray kind
+    float4* side_w;                           // [4 * n_slots]: MIS-weighted contribution if unoccluded (.w = direction pdf for k = 1)
+    float* res_t; int* res_prim; int* res_tslot;   // [5 * n_slots]: closest hit (t, primitive, triangle slot) or occlusion flag in res_prim
+    unsigned int* queue;                      // [5 * n_slots]: (slot << 3) | k
+    unsigned int* counters;                   // [2] = pixels still rendering, [3], [4] = ping-pong queue lengths
+    unsigned long long* rays_total;
+};
+
 } // namespace b200rt

@@ -22,104 +22,39 @@ __device__ __forceinline__ PixelSlot unit_pixel(const RenderParams& P, int unit,
     return s;
 }
 
-// ---- K2: megakernel. One thread = one pixel; its samples and bounces run in-thread so the pixel's xorshift stream is
-// consumed in the reference's order (render_kernel.cpp:75-181). The body is a state machine with ONE trace site: path
-// rays and the four side rays of a surface interaction all pass through the same traversal loop, so the lanes of a
-// warp stay converged on traversal whatever stage each of them is in.
-template <bool DIAG>
-__device__ __forceinline__ col render_pixel(const SceneDev& S, const RenderParams& P, int x, int y, unsigned long long& rays)
+// ---- K2: megakernel. One lane = one pixel at a time; a pixel's samples and bounces run in that lane so the pixel's
+// xorshift stream is consumed in the reference's order (render_kernel.cpp:75-181). Persistent warps: every lane is a
+// small state machine with ONE trace site per loop iteration — camera rays, continuation rays and the four side rays
+// of a surface interaction all go through the same traversal call, a finished sample starts the next one in the same
+// iteration, and a lane that finishes its pixel immediately pulls the next pixel slot from a global counter. Nothing
+// ever waits for the slowest path of a warp except at the very end of the frame.
+struct LaneState
 {
-    uint32_t rng = pixel_rng(x, y, P.spp);
-    col final_color = CO(0.0f, 0.0f, 0.0f);
-    const bool trace_light_brdf = S.any_emissive_material || !(P.flags & B200RT_FLAG_SKIP_DEAD_RAYS);
+    // pixel
+    int x, y; unsigned int slot; uint32_t rng; int sample; col final_color;
+    // path
+    v3 ro, rd; float tmax; int mode; int stage; int bounce;
+    col throughput, sample_color, c0, c1, c2, c3;
+    Surface sf; SideRay sr;
+};
 
-    for (int sample = 0; sample < P.spp; sample++)
-    {
-        const float xj = ((float)x + 0.5f) + xs_float(rng) - 1.0f;      // :88-89
-        const float yj = ((float)y + 0.5f) + xs_float(rng) - 1.0f;
-        v3 ro, rd;
-        camera_ray(P.cam, xj, yj, ro, rd);
-        col throughput = CO(1.0f, 1.0f, 1.0f);
-        col sample_color = CO(0.0f, 0.0f, 0.0f);
-        if (P.max_bounces <= 0) continue;
+__device__ __forceinline__ void start_sample(const RenderParams& P, LaneState& L)
+{
+    const float xj = ((float)L.x + 0.5f) + xs_float(L.rng) - 1.0f;      // :88-89
+    const float yj = ((float)L.y + 0.5f) + xs_float(L.rng) - 1.0f;
+    camera_ray(P.cam, xj, yj, L.ro, L.rd);
+    L.throughput = CO(1.0f, 1.0f, 1.0f);
+    L.sample_color = CO(0.0f, 0.0f, 0.0f);
+    L.bounce = 0; L.stage = 4; L.mode = TRACE_CLOSEST; L.tmax = 0.0f;
+    L.sr.kind = SIDE_NONE;
+}
 
-        int bounce = 0;
-        int stage = 4;                    // 4: (ro, rd) is the path ray; 0..3: it is side ray `stage` of the surface `sf`
-        int mode = TRACE_CLOSEST;
-        float tmax = 0.0f;
-        Surface sf;
-        SideRay sr;
-        col c0 = CO(0, 0, 0), c1 = c0, c2 = c0, c3 = c0;
-        sr.kind = SIDE_NONE;
-
-        for (;;)
-        {
-            Hit h;
-            const bool found = trace_ray<DIAG>(S, ro, rd, tmax, mode, h);      // the single trace site
-            rays++;
-            if (stage == 4)
-            {
-                if (!found)
-                {
-                    // MISSED is handled one loop iteration later and only adds the sky when that iteration is bounce 1 (:146-159)
-                    if (bounce == 0 && P.max_bounces >= 2)
-                        sample_color = sample_color + env_from_direction(S, rd) * throughput;
-                    break;
-                }
-                hit_geometry(S, h, ro, rd, sf.p, sf.n);
-                sf.view = -rd;
-                sf.m = S.mats[__ldg(S.mat_idx + h.prim)];                      // :107-108
-                c0 = c1 = c2 = c3 = CO(0.0f, 0.0f, 0.0f);
-                stage = 0;
-            }
-            else
-            {
-                col c = CO(0.0f, 0.0f, 0.0f);
-                if (sr.kind == SIDE_CLOSEST_LIGHT) { if (found) c = side_light_hit(S, sr, h); }
-                else if (!found) c = sr.weight;
-                if (stage == 0) c0 = c; else if (stage == 1) c1 = c; else if (stage == 2) c2 = c; else c3 = c;
-                stage++;
-            }
-
-            bool sample_done = false;
-            for (;;)
-            {
-                if (stage < 4)
-                {
-                    if (stage == 0) side_light_sample(S, sf, rng, sr);
-                    else if (stage == 1) side_light_brdf(S, sf, rng, sr);
-                    else if (stage == 2) side_env_sample(S, sf, rng, sr);
-                    else side_env_brdf(S, sf, rng, sr);
-                    const bool need = sr.kind != SIDE_NONE && !(sr.kind == SIDE_CLOSEST_LIGHT && !trace_light_brdf);
-                    if (need)
-                    {
-                        ro = sr.o; rd = sr.d; tmax = sr.tmax;
-                        mode = sr.kind == SIDE_SHADOW ? TRACE_SHADOW : (sr.kind == SIDE_CLOSEST_LIGHT ? TRACE_CLOSEST : TRACE_ANY);
-                        break;
-                    }
-                    stage++;
-                    continue;
-                }
-                // all four side rays resolved: continuation sample and path bookkeeping (:121-141)
-                float bpdf;
-                v3 ndir = V(0.0f, 0.0f, 0.0f);
-                const col brdf = ct_sample(sf.m, sf.view, sf.n, ndir, bpdf, rng);
-                if (bounce == 0) sample_color = sample_color + CO(sf.m.er, sf.m.eg, sf.m.eb);
-                sample_color = sample_color + ((c0 + c1) + (c3 + c2)) * throughput;       // light = c0+c1 (:712), env = c3+c2 (:630)
-                if (is_black(brdf) || bpdf < 1.0e-8f || isinf(bpdf)) { sample_done = true; break; }
-                throughput = throughput * ((brdf * smax(0.0f, dot(ndir, sf.n))) / bpdf);
-                bounce++;
-                if (bounce >= P.max_bounces) { sample_done = true; break; }
-                ro = sf.p + 1.0e-4f * sf.n; rd = ndir;
-                mode = TRACE_CLOSEST; stage = 4;
-                break;
-            }
-            if (sample_done) break;
-        }
-        final_color = final_color + sample_color;
-    }
-    const float n = (float)P.spp;
-    return CO(final_color.r / n, final_color.g / n, final_color.b / n);         // operator/= divides (color.h:67-74)
+// slot (tile-major index into this rank's tile buffer) -> pixel; consecutive slots are the lanes of one 8x4 patch
+__device__ __forceinline__ bool slot_pixel(const RenderParams& P, unsigned int slot, int& x, int& y)
+{
+    const PixelSlot ps = unit_pixel(P, (int)(slot >> 5), (int)(slot & 31u));
+    x = ps.x; y = ps.y;
+    return ps.inside;
 }
 
 template <bool DIAG>
@@ -127,26 +62,126 @@ __global__ void __launch_bounds__(256) k_pathtrace_mega(SceneDev S, RenderParams
                                                         float4* __restrict__ out_tiles, unsigned int* work_counter,
                                                         unsigned long long* ray_counter)
 {
+    const unsigned int FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const int n_units = P.n_rank_tiles * 8;
+    const unsigned int n_slots = (unsigned int)P.n_rank_tiles * kTilePixels;
+    const bool trace_light_brdf = S.any_emissive_material || !(P.flags & B200RT_FLAG_SKIP_DEAD_RAYS);
+    const bool no_paths = P.spp <= 0 || P.max_bounces <= 0;
     unsigned long long rays = 0;
+    bool have_pixel = false, exhausted = false;
+    LaneState L;
+
     for (;;)
     {
-        int unit = 0;
-        if (lane == 0) unit = (int)atomicAdd(work_counter, 1u);
-        unit = __shfl_sync(0xffffffffu, unit, 0);
-        if (unit >= n_units) break;
-        const PixelSlot ps = unit_pixel(P, unit, lane);
-        float4 px = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-        if (ps.inside)
+        // (1) idle lanes pull the next pixel slot
+        while (!have_pixel && !exhausted)
         {
-            const col mean = render_pixel<DIAG>(S, P, ps.x, ps.y, rays);
-            const float4 fb = fb_in_rowmajor ? fb_in_rowmajor[(size_t)ps.y * P.cam.w + ps.x] : make_float4(0.0f, 0.0f, 0.0f, 1.0f);
-            px = tonemap(fb, mean);
+            const unsigned int slot = atomicAdd(work_counter, 1u);
+            if (slot >= n_slots) { exhausted = true; break; }
+            int x, y;
+            if (!slot_pixel(P, slot, x, y)) { out_tiles[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); continue; }
+            if (no_paths)
+            {
+                const float4 fb = fb_in_rowmajor ? fb_in_rowmajor[(size_t)y * P.cam.w + x] : make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+                const float n = (float)P.spp;
+                out_tiles[slot] = tonemap(fb, CO(0.0f / n, 0.0f / n, 0.0f / n));
+                continue;
+            }
+            L.x = x; L.y = y; L.slot = slot;
+            L.rng = pixel_rng(x, y, P.spp);
+            L.sample = 0;
+            L.final_color = CO(0.0f, 0.0f, 0.0f);
+            start_sample(P, L);
+            have_pixel = true;
         }
-        out_tiles[ps.out] = px;
+        if (__all_sync(FULL, !have_pixel)) break;
+        if (!have_pixel) continue;
+
+        // (2) the single trace site
+        Hit h;
+        const bool found = trace_ray<DIAG>(S, L.ro, L.rd, L.tmax, L.mode, h);
+        rays++;
+
+        // (3) consume the result
+        bool sample_done = false;
+        if (L.stage == 4)
+        {
+            if (!found)
+            {
+                // MISSED is handled one loop iteration later and only adds the sky when that iteration is bounce 1 (:146-159)
+                if (L.bounce == 0 && P.max_bounces >= 2)
+                    L.sample_color = L.sample_color + env_from_direction(S, L.rd) * L.throughput;
+                sample_done = true;
+            }
+            else
+            {
+                hit_geometry(S, h, L.ro, L.rd, L.sf.p, L.sf.n);
+                L.sf.view = -L.rd;
+                L.sf.m = S.mats[__ldg(S.mat_idx + h.prim)];                      // :107-108
+                L.c0 = L.c1 = L.c2 = L.c3 = CO(0.0f, 0.0f, 0.0f);
+                L.stage = 0;
+            }
+        }
+        else
+        {
+            col c = CO(0.0f, 0.0f, 0.0f);
+            if (L.sr.kind == SIDE_CLOSEST_LIGHT) { if (found) c = side_light_hit(S, L.sr, h); }
+            else if (!found) c = L.sr.weight;
+            if (L.stage == 0) L.c0 = c; else if (L.stage == 1) L.c1 = c; else if (L.stage == 2) L.c2 = c; else L.c3 = c;
+            L.stage++;
+        }
+
+        // (4) advance to the next ray this lane has to trace
+        while (!sample_done)
+        {
+            if (L.stage < 4)
+            {
+                if (L.stage == 0) side_light_sample(S, L.sf, L.rng, L.sr);
+                else if (L.stage == 1) side_light_brdf(S, L.sf, L.rng, L.sr);
+                else if (L.stage == 2) side_env_sample(S, L.sf, L.rng, L.sr);
+                else side_env_brdf(S, L.sf, L.rng, L.sr);
+                const bool need = L.sr.kind != SIDE_NONE && !(L.sr.kind == SIDE_CLOSEST_LIGHT && !trace_light_brdf);
+                if (need)
+                {
+                    L.ro = L.sr.o; L.rd = L.sr.d; L.tmax = L.sr.tmax;
+                    L.mode = L.sr.kind == SIDE_SHADOW ? TRACE_SHADOW : (L.sr.kind == SIDE_CLOSEST_LIGHT ? TRACE_CLOSEST : TRACE_ANY);
+                    break;
+                }
+                L.stage++;
+                continue;
+            }
+            // all four side rays resolved: continuation sample and path bookkeeping (:121-141)
+            float bpdf;
+            v3 ndir = V(0.0f, 0.0f, 0.0f);
+            const col brdf = ct_sample(L.sf.m, L.sf.view, L.sf.n, ndir, bpdf, L.rng);
+            if (L.bounce == 0) L.sample_color = L.sample_color + CO(L.sf.m.er, L.sf.m.eg, L.sf.m.eb);
+            L.sample_color = L.sample_color + ((L.c0 + L.c1) + (L.c3 + L.c2)) * L.throughput;   // light = c0+c1 (:712), env = c3+c2 (:630)
+            if (is_black(brdf) || bpdf < 1.0e-8f || isinf(bpdf)) { sample_done = true; break; }
+            L.throughput = L.throughput * ((brdf * smax(0.0f, dot(ndir, L.sf.n))) / bpdf);
+            L.bounce++;
+            if (L.bounce >= P.max_bounces) { sample_done = true; break; }
+            L.ro = L.sf.p + 1.0e-4f * L.sf.n; L.rd = ndir;
+            L.mode = TRACE_CLOSEST; L.stage = 4;
+            break;
+        }
+
+        // (5) sample / pixel bookkeeping
+        if (sample_done)
+        {
+            L.final_color = L.final_color + L.sample_color;
+            L.sample++;
+            if (L.sample < P.spp) start_sample(P, L);
+            else
+            {
+                const float n = (float)P.spp;
+                const col mean = CO(L.final_color.r / n, L.final_color.g / n, L.final_color.b / n);   // operator/= divides (color.h:67-74)
+                const float4 fb = fb_in_rowmajor ? fb_in_rowmajor[(size_t)L.y * P.cam.w + L.x] : make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+                out_tiles[L.slot] = tonemap(fb, mean);
+                have_pixel = false;
+            }
+        }
     }
-    for (int off = 16; off > 0; off >>= 1) rays += __shfl_down_sync(0xffffffffu, rays, off);
+    for (int off = 16; off > 0; off >>= 1) rays += __shfl_down_sync(FULL, rays, off);
     if (lane == 0 && rays) atomicAdd(ray_counter, rays);
 }
 
@@ -243,9 +278,8 @@ cudaError_t launch_megakernel(const SceneDev& S, const RenderParams& P, const fl
     if (diag) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pathtrace_mega<true>, 256, 0);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pathtrace_mega<false>, 256, 0);
     if (per_sm <= 0) per_sm = 1;
-    const int n_units = P.n_rank_tiles * 8;
     int grid = sm_count() * per_sm;                        // persistent: a whole number of resident CTAs per SM
-    const int needed = (n_units + 7) / 8;
+    const int needed = P.n_rank_tiles;                     // one CTA's worth of lanes per 16x16 tile at most
     if (grid > needed) grid = needed;
     if (grid <= 0) return cudaSuccess;
     if (diag) k_pathtrace_mega<true><<<grid, 256, 0, stream>>>(S, P, fb_in_rowmajor, out_tiles, work_counter, ray_counter);

@@ -1,0 +1,350 @@
+// K3: wavefront integrator with path regeneration (sm_100a). Compiled with -fmad=false (see pt_device.cuh).
+//
+// One slot per pixel of this rank's tile-major buffer. A slot carries the pixel's xorshift state through all of its
+// samples, so the per-pixel RNG stream is consumed in exactly the reference's order (render_kernel.cpp:75-181) and the
+// image is bit-identical to the megakernel's. Every iteration is two launches:
+//
+//   wf_shade : per slot — resolve the side rays of the previous surface interaction (sample_color += (light + env) *
+//              throughput, :128), consume the path ray's closest hit (miss -> sky/finish sample, hit -> material fetch,
+//              the four side rays of sample_light_sources / sample_environment_map with their MIS weights, the
+//              continuation sample, termination tests :130-135), finish samples / pixels, regenerate camera rays, and
+//              append every ray it produced to a compacted queue (grouped by ray kind per warp, so 32 consecutive queue
+//              entries are the same kind of ray from neighbouring pixels).
+//   wf_trace : persistent CTAs walk the queue; one ray per lane; closest-hit, any-hit or shadow traversal by ray kind.
+//
+// No RNG draw depends on a trace result, which is what allows a whole surface interaction — all four side
+// rays and the continuation ray — to be generated in one shade pass and traced in one trace pass.
+#include "kernels.h"
+#include "pt_device.cuh"
+
+namespace b200rt {
+
+enum { WF_ALIVE = 1, WF_PENDING = 2, WF_TERMINATED = 4, WF_DONE = 8 };
+
+__device__ __forceinline__ void wf_enqueue(unsigned int* queue, unsigned int* counter, bool pred, unsigned int entry)
+{
+    const unsigned int mask = __ballot_sync(0xffffffffu, pred);
+    if (!mask) return;
+    const int lane = threadIdx.x & 31;
+    const int leader = __ffs(mask) - 1;
+    unsigned int base = 0;
+    if (lane == leader) base = atomicAdd(counter, (unsigned int)__popc(mask));
+    base = __shfl_sync(0xffffffffu, base, leader);
+    if (pred) queue[base + __popc(mask & ((1u << lane) - 1u))] = entry;
+}
+
+__device__ __forceinline__ void wf_store_ray(const WfBuffers& B, int k, int slot, v3 o, v3 d, float tmax, int kind)
+{
+    const size_t i = (size_t)k * B.n_slots + slot;
+    B.ray_o[i] = make_float4(o.x, o.y, o.z, tmax);
+    B.ray_d[i] = make_float4(d.x, d.y, d.z, __int_as_float(kind));
+}
+
+__device__ __forceinline__ void wf_start_sample(const RenderParams& P, const WfBuffers& B, int slot, int x, int y, uint32_t& rng)
+{
+    const float xj = ((float)x + 0.5f) + xs_float(rng) - 1.0f;      // :88-89
+    const float yj = ((float)y + 0.5f) + xs_float(rng) - 1.0f;
+    v3 o, d;
+    camera_ray(P.cam, xj, yj, o, d);
+    wf_store_ray(B, 4, slot, o, d, 0.0f, SIDE_CLOSEST_LIGHT);
+}
+
+__device__ __forceinline__ bool wf_slot_pixel(const RenderParams& P, int slot, int& x, int& y)
+{
+    const int unit = slot >> 5, lane = slot & 31;
+    const int k = unit >> 3, sub = unit & 7;
+    const int tile_id = P.rank + k * P.world;
+    const int tx = tile_id % P.tiles_x, ty = tile_id / P.tiles_x;
+    x = tx * kTileDim + (sub & 1) * kPatchW + (lane & 7);
+    y = ty * kTileDim + (sub >> 1) * kPatchH + (lane >> 3);
+    return x < P.cam.w && y < P.cam.h;
+}
+
+__global__ void __launch_bounds__(256) wf_init(SceneDev S, RenderParams P, WfBuffers B, const float4* __restrict__ fb_in_rowmajor,
+                                               float4* __restrict__ out_tiles)
+{
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    bool q_path = false;
+    if (slot < B.n_slots)
+    {
+        int x, y;
+        const bool inside = wf_slot_pixel(P, slot, x, y);
+        if (!inside) { out_tiles[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); B.flags[slot] = WF_DONE; }
+        else if (P.spp <= 0 || P.max_bounces <= 0)
+        {
+            const float4 fb = fb_in_rowmajor ? fb_in_rowmajor[(size_t)y * P.cam.w + x] : make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+            const float n = (float)P.spp;
+            out_tiles[slot] = tonemap(fb, CO(0.0f / n, 0.0f / n, 0.0f / n));
+            B.flags[slot] = WF_DONE;
+        }
+        else
+        {
+            uint32_t rng = pixel_rng(x, y, P.spp);
+            wf_start_sample(P, B, slot, x, y, rng);
+            B.rng[slot] = rng;
+            B.sample[slot] = 0;
+            B.bounce[slot] = 0;
+            B.final_c[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            B.sample_c[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+            B.thr[slot] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
+            B.flags[slot] = WF_ALIVE;
+            q_path = true;
+        }
+    }
+    const unsigned int active = __ballot_sync(0xffffffffu, q_path);
+    if ((threadIdx.x & 31) == 0 && active) atomicAdd(&B.counters[2], (unsigned int)__popc(active));
+    wf_enqueue(B.queue, &B.counters[3], q_path, ((unsigned int)slot << 3) | 4u);
+}
+
+// normal of an analytic sphere hit (Sphere::intersect, sphere.h:47-49), recomputed from the stored hit distance
+__device__ __forceinline__ v3 wf_sphere_normal(const SceneDev& S, int prim, v3 p)
+{
+    for (int i = 0; i < S.n_spheres; i++)
+    {
+        const SphereDev s = S.spheres[i];
+        if (s.prim == prim) return normalize(p - V(s.cx, s.cy, s.cz));
+    }
+    return V(0.0f, 0.0f, 0.0f);
+}
+
+__global__ void __launch_bounds__(256) wf_shade(SceneDev S, RenderParams P, WfBuffers B, const float4* __restrict__ fb_in_rowmajor,
+                                                float4* __restrict__ out_tiles, int parity)
+{
+    const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = B.n_slots;
+    unsigned int* q_count = &B.counters[3 + parity];
+    if (slot == 0) B.counters[3 + (parity ^ 1)] = 0;      // the other queue was fully consumed by the previous trace pass
+    bool q_path = false, q0 = false, q1 = false, q2 = false, q3 = false, pixel_done = false;
+    const int flags_in = slot < n ? B.flags[slot] : WF_DONE;
+    if (!(flags_in & WF_DONE))
+    {
+        int x, y;
+        wf_slot_pixel(P, slot, x, y);
+        uint32_t rng = B.rng[slot];
+        int sample = B.sample[slot], bounce = B.bounce[slot];
+        float4 t4 = B.thr[slot], s4 = B.sample_c[slot];
+        col throughput = CO(t4.x, t4.y, t4.z), sample_color = CO(s4.x, s4.y, s4.z);
+        int flags = flags_in;
+        bool finish = false;
+        const bool trace_light_brdf = S.any_emissive_material || !(P.flags & B200RT_FLAG_SKIP_DEAD_RAYS);
+
+        // A. resolve the side rays of the previous surface interaction
+        if (flags & WF_PENDING)
+        {
+            col c[4];
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+            {
+                c[k] = CO(0.0f, 0.0f, 0.0f);
+                const size_t i = (size_t)k * n + slot;
+                const float4 rd4 = B.ray_d[i];
+                const int kind = __float_as_int(rd4.w);
+                if (kind == SIDE_NONE) continue;
+                const float4 w4 = B.side_w[i];
+                if (kind == SIDE_CLOSEST_LIGHT)
+                {
+                    const float t = B.res_t[i];
+                    if (t > 0.0f)
+                    {
+                        const float4 ro4 = B.ray_o[i];
+                        SideRay sr;
+                        sr.o = V(ro4.x, ro4.y, ro4.z); sr.d = V(rd4.x, rd4.y, rd4.z);
+                        sr.weight = CO(w4.x, w4.y, w4.z); sr.pdf = w4.w; sr.kind = kind; sr.tmax = 0.0f;
+                        Hit h;
+                        h.t = t; h.prim = B.res_prim[i]; h.slot = B.res_tslot[i]; h.u = h.v = -1.0f;
+                        if (h.slot < 0) h.sphere_n = wf_sphere_normal(S, h.prim, sr.o + t * sr.d);
+                        c[k] = side_light_hit(S, sr, h);
+                    }
+                }
+                else if (B.res_prim[i] == 0) c[k] = CO(w4.x, w4.y, w4.z);      // unoccluded
+            }
+            sample_color = sample_color + ((c[0] + c[1]) + (c[3] + c[2])) * throughput;     // light = c0+c1 (:712), env = c3+c2 (:630), :128
+            const float4 tn = B.thr_next[slot];
+            throughput = CO(tn.x, tn.y, tn.z);
+            flags &= ~WF_PENDING;
+            if (flags & WF_TERMINATED) finish = true;
+        }
+
+        // B. consume the path ray
+        if (!finish && (flags & WF_ALIVE))
+        {
+            const size_t i = (size_t)4 * n + slot;
+            const float4 ro4 = B.ray_o[i], rd4 = B.ray_d[i];
+            const v3 ro = V(ro4.x, ro4.y, ro4.z), rd = V(rd4.x, rd4.y, rd4.z);
+            const float t = B.res_t[i];
+            if (!(t > 0.0f))
+            {
+                if (bounce == 0 && P.max_bounces >= 2)                           // :146-159
+                    sample_color = sample_color + env_from_direction(S, rd) * throughput;
+                finish = true;
+            }
+            else
+            {
+                Hit h;
+                h.t = t; h.prim = B.res_prim[i]; h.slot = B.res_tslot[i]; h.u = h.v = -1.0f;
+                Surface sf;
+                sf.p = ro + t * rd;
+                if (h.slot >= 0)
+                {
+                    const float4 ve1 = __ldg(S.tris + 3 * (size_t)h.slot + 1), ve2 = __ldg(S.tris + 3 * (size_t)h.slot + 2);
+                    sf.n = normalize(cross(V(ve1.x, ve1.y, ve1.z), V(ve2.x, ve2.y, ve2.z)));
+                }
+                else sf.n = wf_sphere_normal(S, h.prim, sf.p);
+                sf.view = -rd;
+                sf.m = S.mats[__ldg(S.mat_idx + h.prim)];                        // :107-108
+                SideRay sr;
+                sr.o = sr.d = V(0.0f, 0.0f, 0.0f); sr.tmax = 0.0f; sr.pdf = 0.0f; sr.weight = CO(0.0f, 0.0f, 0.0f);
+                side_light_sample(S, sf, rng, sr);
+                wf_store_ray(B, 0, slot, sr.o, sr.d, sr.tmax, sr.kind);
+                if (sr.kind != SIDE_NONE) { B.side_w[(size_t)0 * n + slot] = make_float4(sr.weight.r, sr.weight.g, sr.weight.b, 0.0f); q0 = true; }
+                side_light_brdf(S, sf, rng, sr);
+                if (sr.kind != SIDE_NONE && !trace_light_brdf) sr.kind = SIDE_NONE;
+                wf_store_ray(B, 1, slot, sr.o, sr.d, 0.0f, sr.kind);
+                if (sr.kind != SIDE_NONE) { B.side_w[(size_t)1 * n + slot] = make_float4(sr.weight.r, sr.weight.g, sr.weight.b, sr.pdf); q1 = true; }
+                side_env_sample(S, sf, rng, sr);
+                wf_store_ray(B, 2, slot, sr.o, sr.d, 0.0f, sr.kind);
+                if (sr.kind != SIDE_NONE) { B.side_w[(size_t)2 * n + slot] = make_float4(sr.weight.r, sr.weight.g, sr.weight.b, 0.0f); q2 = true; }
+                side_env_brdf(S, sf, rng, sr);
+                wf_store_ray(B, 3, slot, sr.o, sr.d, 0.0f, sr.kind);
+                if (sr.kind != SIDE_NONE) { B.side_w[(size_t)3 * n + slot] = make_float4(sr.weight.r, sr.weight.g, sr.weight.b, 0.0f); q3 = true; }
+
+                float bpdf;
+                v3 ndir = V(0.0f, 0.0f, 0.0f);
+                const col brdf = ct_sample(sf.m, sf.view, sf.n, ndir, bpdf, rng);        // :123
+                if (bounce == 0) sample_color = sample_color + CO(sf.m.er, sf.m.eg, sf.m.eb);
+                flags = WF_PENDING;
+                col tnext = throughput;
+                if (is_black(brdf) || bpdf < 1.0e-8f || isinf(bpdf)) flags |= WF_TERMINATED;     // :130-135
+                else
+                {
+                    tnext = throughput * ((brdf * smax(0.0f, dot(ndir, sf.n))) / bpdf);       // :137
+                    bounce++;
+                    if (bounce >= P.max_bounces) flags |= WF_TERMINATED;
+                    else
+                    {
+                        wf_store_ray(B, 4, slot, sf.p + 1.0e-4f * sf.n, ndir, 0.0f, SIDE_CLOSEST_LIGHT);
+                        flags |= WF_ALIVE;
+                        q_path = true;
+                    }
+                }
+                B.thr_next[slot] = make_float4(tnext.r, tnext.g, tnext.b, 0.0f);
+            }
+        }
+
+        // C. finish the sample: next sample of this pixel, or the pixel itself
+        if (finish)
+        {
+            float4 f4 = B.final_c[slot];
+            col final_color = CO(f4.x, f4.y, f4.z) + sample_color;
+            sample++;
+            if (sample < P.spp)
+            {
+                B.final_c[slot] = make_float4(final_color.r, final_color.g, final_color.b, 0.0f);
+                wf_start_sample(P, B, slot, x, y, rng);
+                throughput = CO(1.0f, 1.0f, 1.0f);
+                sample_color = CO(0.0f, 0.0f, 0.0f);
+                bounce = 0;
+                flags = WF_ALIVE;
+                q_path = true;
+            }
+            else
+            {
+                const float nspp = (float)P.spp;
+                const col mean = CO(final_color.r / nspp, final_color.g / nspp, final_color.b / nspp);
+                const float4 fb = fb_in_rowmajor ? fb_in_rowmajor[(size_t)y * P.cam.w + x] : make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+                out_tiles[slot] = tonemap(fb, mean);
+                flags = WF_DONE;
+                pixel_done = true;
+            }
+        }
+        B.rng[slot] = rng;
+        B.sample[slot] = sample;
+        B.bounce[slot] = bounce;
+        B.thr[slot] = make_float4(throughput.r, throughput.g, throughput.b, 0.0f);
+        B.sample_c[slot] = make_float4(sample_color.r, sample_color.g, sample_color.b, 0.0f);
+        B.flags[slot] = flags;
+    }
+    const unsigned int done_mask = __ballot_sync(0xffffffffu, pixel_done);
+    if ((threadIdx.x & 31) == 0 && done_mask) atomicSub(&B.counters[2], (unsigned int)__popc(done_mask));
+    const unsigned int s3 = (unsigned int)slot << 3;
+    wf_enqueue(B.queue, q_count, q_path, s3 | 4u);
+    wf_enqueue(B.queue, q_count, q0, s3 | 0u);
+    wf_enqueue(B.queue, q_count, q1, s3 | 1u);
+    wf_enqueue(B.queue, q_count, q2, s3 | 2u);
+    wf_enqueue(B.queue, q_count, q3, s3 | 3u);
+}
+
+template <bool DIAG>
+__global__ void __launch_bounds__(256) wf_trace(SceneDev S, WfBuffers B, int parity)
+{
+    const unsigned int n_rays = B.counters[3 + parity];
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(B.rays_total, (unsigned long long)n_rays);
+    const int n = B.n_slots;
+    for (unsigned int i = blockIdx.x * blockDim.x + threadIdx.x; i < n_rays; i += gridDim.x * blockDim.x)
+    {
+        const unsigned int e = B.queue[i];
+        const int slot = (int)(e >> 3), k = (int)(e & 7u);
+        const size_t r = (size_t)k * n + slot;
+        const float4 ro4 = B.ray_o[r], rd4 = B.ray_d[r];
+        const int kind = __float_as_int(rd4.w);
+        const int mode = kind == SIDE_SHADOW ? TRACE_SHADOW : (kind == SIDE_CLOSEST_LIGHT ? TRACE_CLOSEST : TRACE_ANY);
+        Hit h;
+        const bool found = trace_ray<DIAG>(S, V(ro4.x, ro4.y, ro4.z), V(rd4.x, rd4.y, rd4.z), ro4.w, mode, h);
+        if (mode == TRACE_CLOSEST)
+        {
+            B.res_t[r] = found ? h.t : -1.0f;
+            B.res_prim[r] = h.prim;
+            B.res_tslot[r] = h.slot;
+        }
+        else B.res_prim[r] = found ? 1 : 0;
+    }
+}
+
+// ---- host driver ---------------------------------------------------------------------------------------------------------------
+static int g_wf_sm_count = 0;
+
+cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfBuffers& B, const float4* fb_in_rowmajor, float4* out_tiles,
+                          unsigned int* host_pinned_active, cudaStream_t stream, int* launches_out)
+{
+    if (!g_wf_sm_count)
+    {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&g_wf_sm_count, cudaDevAttrMultiProcessorCount, dev);
+        if (g_wf_sm_count <= 0) g_wf_sm_count = 148;
+    }
+    int launches = 0;
+    const bool diag = S.has_diag && !(P.flags & B200RT_FLAG_AXIS_SLABS_ONLY);
+    int per_sm = 0;
+    if (diag) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace<true>, 256, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace<false>, 256, 0);
+    if (per_sm <= 0) per_sm = 1;
+    const int trace_grid = g_wf_sm_count * per_sm;
+    const int slot_grid = (B.n_slots + 255) / 256;
+    if (slot_grid <= 0) { if (launches_out) *launches_out = 0; return cudaSuccess; }
+    cudaError_t e;
+    if ((e = cudaMemsetAsync(B.counters, 0, 8 * sizeof(unsigned int), stream)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(B.rays_total, 0, sizeof(unsigned long long), stream)) != cudaSuccess) return e;
+    wf_init<<<slot_grid, 256, 0, stream>>>(S, P, B, fb_in_rowmajor, out_tiles);
+    launches++;
+    int parity = 0;      // wf_init filled queue 0
+    const long long max_iters = (long long)P.spp * (P.max_bounces + 1) + 2;
+    for (long long it = 0; it < max_iters; it++)
+    {
+        if (diag) wf_trace<true><<<trace_grid, 256, 0, stream>>>(S, B, parity);
+        else wf_trace<false><<<trace_grid, 256, 0, stream>>>(S, B, parity);
+        parity ^= 1;
+        wf_shade<<<slot_grid, 256, 0, stream>>>(S, P, B, fb_in_rowmajor, out_tiles, parity);
+        launches += 2;
+        if ((it & 3) == 3 || it + 1 == max_iters)
+        {
+            if ((e = cudaMemcpyAsync(host_pinned_active, &B.counters[2], sizeof(unsigned int), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
+            if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
+            if (*host_pinned_active == 0) break;
+        }
+    }
+    if (launches_out) *launches_out = launches;
+    return cudaGetLastError();
+}
+
+} // namespace b200rt

@@ -230,3 +230,47 @@ def test_errors(rt, golden_scenes):
     e = rt.Scene(np.zeros((0, 9), np.float32), np.zeros(0, np.int32), a["mats10"], np.zeros(0, np.int32), skysphere=rt.constant_env(0.5))
     img, st = e.render(rt.Camera.CORNELL_BOX_CAMERA, 32, 32, 1, 2)
     assert st["rays"] == 32 * 32 and np.allclose(img[..., :3], (1 - np.exp(-0.5 * 1.5)) ** (1 / 2.2), atol=1e-5)
+
+
+# ---- wavefront integrator ------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("key,fixture", RENDERS + [("cornell", "sphere_cornell.npz")])
+def test_wavefront_equals_megakernel_bit_for_bit(rt, golden_scenes, golden_cameras, key, fixture):
+    """Both integrators run the same device functions on the same per-pixel RNG streams: identical framebuffers and
+    identical ray counts."""
+    g = load_golden(fixture)
+    w, h, spp, b = int(g["w"]), int(g["h"]), int(g["spp"]), int(g["bounces"])
+    if fixture == "sphere_cornell.npz":
+        a = scene_arrays(golden_scenes, "cornell")
+        n = len(a["tri9"])
+        mat_idx = np.concatenate([a["mat_idx"], np.array([len(g["mats10"]) - 1], np.int32)])
+        sph = [((float(g["spheres4"][0, 0]), float(g["spheres4"][0, 1]), float(g["spheres4"][0, 2])), float(g["spheres4"][0, 3]), n)]
+        sc = rt.Scene(a["tri9"], mat_idx, g["mats10"], a["emissive"], spheres=sph, skysphere=g["env"])
+    else:
+        sc = make_scene(rt, golden_scenes, key, env=g["env"])
+    c = cam(rt, golden_cameras, CAM_OF[key])
+    mega, st_m = sc.render(c, w, h, spp, b, integrator=rt.INTEGRATOR_MEGAKERNEL)
+    wave, st_w = sc.render(c, w, h, spp, b, integrator=rt.INTEGRATOR_WAVEFRONT)
+    assert np.array_equal(bits(mega), bits(wave)), f"{(bits(mega) != bits(wave)).sum()} differing words"
+    assert st_m["rays"] == st_w["rays"] and st_w["gpu_launches"] > 3
+    s = image_stats(wave, g["image"])
+    assert s["frac_close"] >= 0.97 and s["rmse"] <= 0.02, s
+
+
+def test_wavefront_c3_small_and_tiles(rt, golden_cameras):
+    from sycl_ray_tracing_b200 import scenes
+    g = load_golden("render_c3small.npz")
+    c3 = scenes.c3_scene(roughness=float(g["roughness"]), nu=int(g["nu"]), nv=int(g["nv"]), sky_w=int(g["sky_w"]), sky_h=int(g["sky_h"]))
+    sc = rt.Scene(c3["tri9"], c3["mat_idx"], c3["mats10"], c3["emissive"], skysphere=c3["env"])
+    w, h, spp, b = int(g["w"]), int(g["h"]), int(g["spp"]), int(g["bounces"])
+    mega, st_m = sc.render(c3["camera"], w, h, spp, b)
+    wave, st_w = sc.render(c3["camera"], w, h, spp, b, integrator=rt.INTEGRATOR_WAVEFRONT)
+    assert np.array_equal(bits(mega), bits(wave)) and st_m["rays"] == st_w["rays"]
+    skip, st_s = sc.render(c3["camera"], w, h, spp, b, integrator=rt.INTEGRATOR_WAVEFRONT, flags=rt.FLAG_SKIP_DEAD_RAYS)
+    assert np.array_equal(bits(mega), bits(skip)) and st_s["rays"] < st_w["rays"], "no emissive material: the BRDF->light rays are dead"
+    fb = rt.Image(w, h).pixels
+    for rank in range(3):
+        sc.render(c3["camera"], w, h, spp, b, framebuffer=fb, integrator=rt.INTEGRATOR_WAVEFRONT, rank=rank, world=3)
+    assert np.array_equal(bits(fb), bits(mega))
+    zero, _ = sc.render(c3["camera"], 40, 30, 0, 4, integrator=rt.INTEGRATOR_WAVEFRONT)
+    zero_m, _ = sc.render(c3["camera"], 40, 30, 0, 4)
+    assert np.array_equal(bits(zero), bits(zero_m))
