@@ -99,6 +99,7 @@ size_t b200rt_scene_device_bytes(const b200rt_scene* scene);
 #define B200RT_FLAG_FB_IS_ZERO 1         /* caller guarantees the framebuffer is Color::Black(): skip its upload */
 #define B200RT_FLAG_SKIP_DEAD_RAYS 2     /* skip rays whose result provably cannot change the image */
 #define B200RT_FLAG_AXIS_SLABS_ONLY 4    /* ablation: ignore the 4 diagonal slabs while traversing */
+#define B200RT_FLAG_SIMPLE_TRACE 8       /* ablation: wavefront trace kernel without per-lane ray refill */
 
 typedef struct b200rt_render_options
 {

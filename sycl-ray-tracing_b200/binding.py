@@ -18,6 +18,7 @@ INTEGRATOR_WAVEFRONT = 1
 FLAG_FB_IS_ZERO = 1
 FLAG_SKIP_DEAD_RAYS = 2
 FLAG_AXIS_SLABS_ONLY = 4
+FLAG_SIMPLE_TRACE = 8
 TILE_DIM = 16
 TILE_PIXELS = 256
 

@@ -152,116 +152,173 @@ __device__ __forceinline__ bool tri_test(const float4 va, const float4 ve1, cons
     return false;
 }
 
-// Returns true when a hit was found. MODE:
+// Traversal state of one ray. MODE:
 //   TRACE_CLOSEST : exact closest hit over all triangles (== brute force, ties -> lowest index)
 //   TRACE_ANY     : any triangle hit with t > EPSILON                       (occlusion test of render_kernel.cpp:592,:615)
 //   TRACE_SHADOW  : any triangle hit with t + 1e-4f < tmax                  (evaluate_shadow_ray, :744-759)
 // MODE is a run-time value so that one copy of the loop serves every ray type of the integrators' single trace site
-// (it is only consulted when a triangle test succeeds).
+// (it is only consulted when a triangle test succeeds). The state is explicit so that the same step function serves
+// the run-to-completion traversal (megakernel, primary rays) and the persistent trace kernel that refills idle lanes
+// with new rays between steps.
+struct Trav
+{
+    v3 o, d;
+    float tmax, tbest;
+    int mode, cur, sp;
+    bool done;
+    RaySlabs rs;
+    Hit hit;
+};
+// the per-lane traversal stack lives in local memory, outside Trav, so the rest of the state stays in registers
+struct TravStack
+{
+    int ref[kStackSize];
+    float t[kStackSize];
+};
+
+template <bool use_diag>
+__device__ __forceinline__ void trav_init(Trav& T, v3 o, v3 d, float tmax, const int mode)
+{
+    T.o = o; T.d = d; T.tmax = tmax; T.mode = mode;
+    setup_slabs(o, d, use_diag, T.rs);
+    T.tbest = (mode == TRACE_SHADOW) ? tmax : __int_as_float(0x7f800000);
+    T.hit.t = -1.0f; T.hit.prim = -1; T.hit.slot = -1;
+    T.sp = 0; T.cur = 0; T.done = false;
+}
+
+// pop the next subtree, skipping those that start beyond the current best; T.done when the stack is empty
+__device__ __forceinline__ void trav_pop(Trav& T, TravStack& K)
+{
+    for (;;)
+    {
+        if (T.sp == 0) { T.done = true; return; }
+        T.sp--;
+        if (K.t[T.sp] <= T.tbest * 1.00004f) { T.cur = K.ref[T.sp]; return; }
+    }
+}
+
+// visit the inner node T.cur (>= 0): test both children, descend into the nearer hit one (pushing the other) or pop
+template <bool use_diag>
+__device__ __forceinline__ void trav_inner(const SceneDev& S, Trav& T, TravStack& K)
+{
+    const v3 o = T.o, d = T.d;
+    const RaySlabs& rs = T.rs;
+    const float tbest = T.tbest;
+    {
+        const float4* an = S.axis + 4 * (size_t)T.cur;
+        const float4 n0 = __ldg(an + 0), n1 = __ldg(an + 1), n2 = __ldg(an + 2), n3 = __ldg(an + 3);
+        // L: lo = (n0.x n0.y n0.z) hi = (n0.w n1.x n1.y); R: lo = (n1.z n1.w n2.x) hi = (n2.y n2.z n2.w)
+        float a0 = (n0.x - o.x) * rs.ix, a1 = (n0.w - o.x) * rs.ix;
+        float b0 = (n0.y - o.y) * rs.iy, b1 = (n1.x - o.y) * rs.iy;
+        float c0 = (n0.z - o.z) * rs.iz, c1 = (n1.y - o.z) * rs.iz;
+        float tnL = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), 0.0f));
+        float tfL = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), tbest));
+        a0 = (n1.z - o.x) * rs.ix; a1 = (n2.y - o.x) * rs.ix;
+        b0 = (n1.w - o.y) * rs.iy; b1 = (n2.z - o.y) * rs.iy;
+        c0 = (n2.x - o.z) * rs.iz; c1 = (n2.w - o.z) * rs.iz;
+        float tnR = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), 0.0f));
+        float tfR = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), tbest));
+        // distance-proportional widening keeps the float slab test conservative (Ize, "Robust BVH ray traversal")
+        bool hitL = tnL <= tfL * 1.000001f;
+        bool hitR = tnR <= tfR * 1.000001f;
+        if (use_diag && (hitL || hitR))
+        {
+            const float4* dn = S.diag + 4 * (size_t)T.cur;
+            if (hitL)
+            {
+                const float4 nr = __ldg(dn + 0), fr = __ldg(dn + 1);
+                float p0 = (nr.x - rs.na[0]) * rs.rc[0], q0 = (fr.x - rs.nb[0]) * rs.rc[0];
+                float p1 = (nr.y - rs.na[1]) * rs.rc[1], q1 = (fr.y - rs.nb[1]) * rs.rc[1];
+                float p2 = (nr.z - rs.na[2]) * rs.rc[2], q2 = (fr.z - rs.nb[2]) * rs.rc[2];
+                float p3 = (nr.w - rs.na[3]) * rs.rc[3], q3 = (fr.w - rs.nb[3]) * rs.rc[3];
+                float tn = fmaxf(fmaxf(fminf(p0, q0), fminf(p1, q1)), fmaxf(fminf(p2, q2), fminf(p3, q3)));
+                float tf = fminf(fminf(fmaxf(p0, q0), fmaxf(p1, q1)), fminf(fmaxf(p2, q2), fmaxf(p3, q3)));
+                tnL = fmaxf(tnL, tn); tfL = fminf(tfL, tf);
+                hitL = tnL <= tfL * 1.00004f;
+            }
+            if (hitR)
+            {
+                const float4 nr = __ldg(dn + 2), fr = __ldg(dn + 3);
+                float p0 = (nr.x - rs.na[0]) * rs.rc[0], q0 = (fr.x - rs.nb[0]) * rs.rc[0];
+                float p1 = (nr.y - rs.na[1]) * rs.rc[1], q1 = (fr.y - rs.nb[1]) * rs.rc[1];
+                float p2 = (nr.z - rs.na[2]) * rs.rc[2], q2 = (fr.z - rs.nb[2]) * rs.rc[2];
+                float p3 = (nr.w - rs.na[3]) * rs.rc[3], q3 = (fr.w - rs.nb[3]) * rs.rc[3];
+                float tn = fmaxf(fmaxf(fminf(p0, q0), fminf(p1, q1)), fmaxf(fminf(p2, q2), fminf(p3, q3)));
+                float tf = fminf(fminf(fmaxf(p0, q0), fmaxf(p1, q1)), fminf(fmaxf(p2, q2), fmaxf(p3, q3)));
+                tnR = fmaxf(tnR, tn); tfR = fminf(tfR, tf);
+                hitR = tnR <= tfR * 1.00004f;
+            }
+        }
+        const int refL = __float_as_int(n3.x), refR = __float_as_int(n3.y);
+        if (hitL && hitR)
+        {
+            const bool r_first = tnR < tnL;
+            K.ref[T.sp] = r_first ? refL : refR;
+            K.t[T.sp] = r_first ? tnL : tnR;
+            T.sp++;
+            T.cur = r_first ? refR : refL;
+            return;
+        }
+        if (hitL) { T.cur = refL; return; }
+        if (hitR) { T.cur = refR; return; }
+    }
+    trav_pop(T, K);
+}
+
+// visit the leaf T.cur (< 0): exact triangle tests, then pop
+__device__ __forceinline__ void trav_leaf(const SceneDev& S, Trav& T, TravStack& K)
+{
+    const v3 o = T.o, d = T.d;
+    {
+        const int packed = ~T.cur;
+        const int first = packed >> 4, count = packed & 15;
+        const float4* tp = S.tris + 3 * (size_t)first;
+        for (int i = 0; i < count; i++, tp += 3)
+        {
+            const float4 va = __ldg(tp), ve1 = __ldg(tp + 1), ve2 = __ldg(tp + 2);
+            float t, u, v;
+            if (tri_test(va, ve1, ve2, o, d, t, u, v))
+            {
+                if (T.mode == TRACE_ANY) { T.hit.t = t; T.done = true; return; }
+                if (T.mode == TRACE_SHADOW) { if (t + 1.0e-4f < T.tmax) { T.hit.t = t; T.done = true; return; } continue; }
+                const int prim = __float_as_int(va.w);
+                // strict "<" (bvh.h:158); equal t goes to the lower original index, as brute force would (render_kernel.cpp:464)
+                if (T.hit.prim < 0 || t < T.hit.t || (t == T.hit.t && prim < T.hit.prim))
+                {
+                    T.hit.t = t; T.hit.prim = prim; T.hit.slot = first + i; T.hit.u = u; T.hit.v = v;
+                    T.tbest = t;
+                }
+            }
+        }
+    }
+    trav_pop(T, K);
+}
+
+// one step of either kind (the persistent trace kernel advances lanes step by step)
+template <bool use_diag>
+__device__ __forceinline__ void trav_step(const SceneDev& S, Trav& T, TravStack& K)
+{
+    if (T.cur >= 0) trav_inner<use_diag>(S, T, K);
+    else trav_leaf(S, T, K);
+}
+
+// Returns true when a hit was found (see Trav for MODE). "while-while": every lane descends through inner nodes until
+// it holds a leaf (or is finished); the lanes of a warp reconverge at the end of that inner loop, so the expensive
+// exact triangle tests run with as many lanes as possible instead of interleaving with other lanes' node tests.
 template <bool use_diag>
 __device__ __forceinline__ bool traverse_tris(const SceneDev& S, v3 o, v3 d, float tmax, const int MODE, Hit& hit)
 {
-    RaySlabs rs;
-    setup_slabs(o, d, use_diag, rs);
-    float tbest = (MODE == TRACE_SHADOW) ? tmax : __int_as_float(0x7f800000);
-    hit.t = -1.0f; hit.prim = -1; hit.slot = -1;
-
-    int stack_ref[kStackSize];
-    float stack_t[kStackSize];
-    int sp = 0;
-    int cur = 0;
-    for (;;)
+    Trav T;
+    TravStack K;
+    trav_init<use_diag>(T, o, d, tmax, MODE);
+    while (!T.done)
     {
-        if (cur >= 0)
-        {
-            const float4* an = S.axis + 4 * (size_t)cur;
-            const float4 n0 = __ldg(an + 0), n1 = __ldg(an + 1), n2 = __ldg(an + 2), n3 = __ldg(an + 3);
-            // L: lo = (n0.x n0.y n0.z) hi = (n0.w n1.x n1.y); R: lo = (n1.z n1.w n2.x) hi = (n2.y n2.z n2.w)
-            float a0 = (n0.x - o.x) * rs.ix, a1 = (n0.w - o.x) * rs.ix;
-            float b0 = (n0.y - o.y) * rs.iy, b1 = (n1.x - o.y) * rs.iy;
-            float c0 = (n0.z - o.z) * rs.iz, c1 = (n1.y - o.z) * rs.iz;
-            float tnL = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), 0.0f));
-            float tfL = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), tbest));
-            a0 = (n1.z - o.x) * rs.ix; a1 = (n2.y - o.x) * rs.ix;
-            b0 = (n1.w - o.y) * rs.iy; b1 = (n2.z - o.y) * rs.iy;
-            c0 = (n2.x - o.z) * rs.iz; c1 = (n2.w - o.z) * rs.iz;
-            float tnR = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), 0.0f));
-            float tfR = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), tbest));
-            // distance-proportional widening keeps the float slab test conservative (Ize, "Robust BVH ray traversal")
-            bool hitL = tnL <= tfL * 1.000001f;
-            bool hitR = tnR <= tfR * 1.000001f;
-            if (use_diag && (hitL || hitR))
-            {
-                const float4* dn = S.diag + 4 * (size_t)cur;
-                if (hitL)
-                {
-                    const float4 nr = __ldg(dn + 0), fr = __ldg(dn + 1);
-                    float p0 = (nr.x - rs.na[0]) * rs.rc[0], q0 = (fr.x - rs.nb[0]) * rs.rc[0];
-                    float p1 = (nr.y - rs.na[1]) * rs.rc[1], q1 = (fr.y - rs.nb[1]) * rs.rc[1];
-                    float p2 = (nr.z - rs.na[2]) * rs.rc[2], q2 = (fr.z - rs.nb[2]) * rs.rc[2];
-                    float p3 = (nr.w - rs.na[3]) * rs.rc[3], q3 = (fr.w - rs.nb[3]) * rs.rc[3];
-                    float tn = fmaxf(fmaxf(fminf(p0, q0), fminf(p1, q1)), fmaxf(fminf(p2, q2), fminf(p3, q3)));
-                    float tf = fminf(fminf(fmaxf(p0, q0), fmaxf(p1, q1)), fminf(fmaxf(p2, q2), fmaxf(p3, q3)));
-                    tnL = fmaxf(tnL, tn); tfL = fminf(tfL, tf);
-                    hitL = tnL <= tfL * 1.00004f;
-                }
-                if (hitR)
-                {
-                    const float4 nr = __ldg(dn + 2), fr = __ldg(dn + 3);
-                    float p0 = (nr.x - rs.na[0]) * rs.rc[0], q0 = (fr.x - rs.nb[0]) * rs.rc[0];
-                    float p1 = (nr.y - rs.na[1]) * rs.rc[1], q1 = (fr.y - rs.nb[1]) * rs.rc[1];
-                    float p2 = (nr.z - rs.na[2]) * rs.rc[2], q2 = (fr.z - rs.nb[2]) * rs.rc[2];
-                    float p3 = (nr.w - rs.na[3]) * rs.rc[3], q3 = (fr.w - rs.nb[3]) * rs.rc[3];
-                    float tn = fmaxf(fmaxf(fminf(p0, q0), fminf(p1, q1)), fmaxf(fminf(p2, q2), fminf(p3, q3)));
-                    float tf = fminf(fminf(fmaxf(p0, q0), fmaxf(p1, q1)), fminf(fmaxf(p2, q2), fmaxf(p3, q3)));
-                    tnR = fmaxf(tnR, tn); tfR = fminf(tfR, tf);
-                    hitR = tnR <= tfR * 1.00004f;
-                }
-            }
-            const int refL = __float_as_int(n3.x), refR = __float_as_int(n3.y);
-            if (hitL && hitR)
-            {
-                const bool r_first = tnR < tnL;
-                stack_ref[sp] = r_first ? refL : refR;
-                stack_t[sp] = r_first ? tnL : tnR;
-                sp++;
-                cur = r_first ? refR : refL;
-                continue;
-            }
-            if (hitL) { cur = refL; continue; }
-            if (hitR) { cur = refR; continue; }
-        }
-        else
-        {
-            const int packed = ~cur;
-            const int first = packed >> 4, count = packed & 15;
-            const float4* tp = S.tris + 3 * (size_t)first;
-            for (int i = 0; i < count; i++, tp += 3)
-            {
-                const float4 va = __ldg(tp), ve1 = __ldg(tp + 1), ve2 = __ldg(tp + 2);
-                float t, u, v;
-                if (tri_test(va, ve1, ve2, o, d, t, u, v))
-                {
-                    if (MODE == TRACE_ANY) { hit.t = t; return true; }
-                    if (MODE == TRACE_SHADOW) { if (t + 1.0e-4f < tmax) { hit.t = t; return true; } continue; }
-                    const int prim = __float_as_int(va.w);
-                    // strict "<" (bvh.h:158); equal t goes to the lower original index, as brute force would (render_kernel.cpp:464)
-                    if (hit.prim < 0 || t < hit.t || (t == hit.t && prim < hit.prim))
-                    {
-                        hit.t = t; hit.prim = prim; hit.slot = first + i; hit.u = u; hit.v = v;
-                        tbest = t;
-                    }
-                }
-            }
-        }
-        // pop, skipping subtrees that start beyond the current best
-        for (;;)
-        {
-            if (sp == 0) return hit.t > 0.0f;
-            sp--;
-            if (stack_t[sp] <= tbest * 1.00004f) { cur = stack_ref[sp]; break; }
-        }
+        while (T.cur >= 0 && !T.done) trav_inner<use_diag>(S, T, K);
+        if (T.done) break;
+        trav_leaf(S, T, K);
     }
+    hit = T.hit;
+    return hit.t > 0.0f;
 }
 
 // Sphere::intersect, include/sphere.h:11-53
@@ -286,15 +343,9 @@ __device__ __forceinline__ bool sphere_test(const SphereDev& s, v3 o, v3 d, floa
     return true;
 }
 
-// INTERSECT_SCENE (render_kernel.cpp:485-511): BVH triangles, then every analytic sphere; "found" iff closest.t > 0.
-// mode TRACE_ANY / TRACE_SHADOW return the occlusion predicates of :592/:615 and evaluate_shadow_ray (:744-759).
-// With analytic spheres in the scene the exact "closest.t > 0" semantics need the true closest hit (a sphere can
-// report t == 0), so the early-out traversals are only used for triangle-only scenes.
-template <bool use_diag>
-__device__ __forceinline__ bool trace_ray(const SceneDev& S, v3 o, v3 d, float tmax, const int mode, Hit& hit)
+// second half of INTERSECT_SCENE: every analytic sphere after the triangles (render_kernel.cpp:491-501)
+__device__ __forceinline__ bool finish_with_spheres(const SceneDev& S, v3 o, v3 d, float tmax, const int mode, Hit& hit)
 {
-    if (S.n_spheres == 0) return traverse_tris<use_diag>(S, o, d, tmax, mode, hit);
-    traverse_tris<use_diag>(S, o, d, tmax, TRACE_CLOSEST, hit);
     for (int i = 0; i < S.n_spheres; i++)
     {
         float t;
@@ -310,6 +361,18 @@ __device__ __forceinline__ bool trace_ray(const SceneDev& S, v3 o, v3 d, float t
     bool found = hit.t > 0.0f;
     if (mode == TRACE_SHADOW) found = found && (hit.t + 1.0e-4f < tmax);
     return found;
+}
+
+// INTERSECT_SCENE (render_kernel.cpp:485-511): BVH triangles, then every analytic sphere; "found" iff closest.t > 0.
+// mode TRACE_ANY / TRACE_SHADOW return the occlusion predicates of :592/:615 and evaluate_shadow_ray (:744-759).
+// With analytic spheres in the scene the exact "closest.t > 0" semantics need the true closest hit (a sphere can
+// report t == 0), so the early-out traversals are only used for triangle-only scenes.
+template <bool use_diag>
+__device__ __forceinline__ bool trace_ray(const SceneDev& S, v3 o, v3 d, float tmax, const int mode, Hit& hit)
+{
+    if (S.n_spheres == 0) return traverse_tris<use_diag>(S, o, d, tmax, mode, hit);
+    traverse_tris<use_diag>(S, o, d, tmax, TRACE_CLOSEST, hit);
+    return finish_with_spheres(S, o, d, tmax, mode, hit);
 }
 
 // point and geometric normal of a closest hit (triangle.h:46-49: normalize(cross(e1,e2)), never flipped)

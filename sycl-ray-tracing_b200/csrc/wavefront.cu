@@ -113,7 +113,11 @@ __global__ void __launch_bounds__(256) wf_shade(SceneDev S, RenderParams P, WfBu
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
     const int n = B.n_slots;
     unsigned int* q_count = &B.counters[3 + parity];
-    if (slot == 0) B.counters[3 + (parity ^ 1)] = 0;      // the other queue was fully consumed by the previous trace pass
+    if (slot == 0)
+    {
+        B.counters[3 + (parity ^ 1)] = 0;      // the other queue was fully consumed by the previous trace pass
+        B.counters[5 + parity] = 0;            // head of the queue this pass fills
+    }
     bool q_path = false, q0 = false, q1 = false, q2 = false, q3 = false, pixel_done = false;
     const int flags_in = slot < n ? B.flags[slot] : WF_DONE;
     if (!(flags_in & WF_DONE))
@@ -274,8 +278,21 @@ __global__ void __launch_bounds__(256) wf_shade(SceneDev S, RenderParams P, WfBu
     wf_enqueue(B.queue, q_count, q3, s3 | 3u);
 }
 
+// result of one queue entry
+__device__ __forceinline__ void wf_store_result(const WfBuffers& B, size_t r, int mode, bool found, const Hit& h)
+{
+    if (mode == TRACE_CLOSEST)
+    {
+        B.res_t[r] = found ? h.t : -1.0f;
+        B.res_prim[r] = h.prim;
+        B.res_tslot[r] = h.slot;
+    }
+    else B.res_prim[r] = found ? 1 : 0;
+}
+
+// simple variant (ablation, B200RT_FLAG_SIMPLE_TRACE): one ray per lane, the warp waits for its slowest ray
 template <bool DIAG>
-__global__ void __launch_bounds__(256) wf_trace(SceneDev S, WfBuffers B, int parity)
+__global__ void __launch_bounds__(256) wf_trace_simple(SceneDev S, WfBuffers B, int parity)
 {
     const unsigned int n_rays = B.counters[3 + parity];
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(B.rays_total, (unsigned long long)n_rays);
@@ -290,13 +307,88 @@ __global__ void __launch_bounds__(256) wf_trace(SceneDev S, WfBuffers B, int par
         const int mode = kind == SIDE_SHADOW ? TRACE_SHADOW : (kind == SIDE_CLOSEST_LIGHT ? TRACE_CLOSEST : TRACE_ANY);
         Hit h;
         const bool found = trace_ray<DIAG>(S, V(ro4.x, ro4.y, ro4.z), V(rd4.x, rd4.y, rd4.z), ro4.w, mode, h);
-        if (mode == TRACE_CLOSEST)
+        wf_store_result(B, r, mode, found, h);
+    }
+}
+
+// persistent variant: every lane owns one traversal state; whenever at least kRefillThreshold lanes of a warp are idle
+// they are refilled with new rays from the warp's private block of the queue (blocks of kWarpBlock rays are claimed
+// with one atomic), so no lane waits for the slowest ray of its warp (Aila & Laine's persistent threads, per lane).
+constexpr int kWarpBlock = 128;
+constexpr int kRefillThreshold = 8;
+
+template <bool DIAG>
+__global__ void __launch_bounds__(256) wf_trace(SceneDev S, WfBuffers B, int parity)
+{
+    const unsigned int FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned int n_rays = B.counters[3 + parity];
+    unsigned int* head = &B.counters[5 + parity];
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(B.rays_total, (unsigned long long)n_rays);
+    const int n = B.n_slots;
+    const bool spheres = S.n_spheres != 0;
+
+    Trav T;
+    TravStack K;
+    T.done = true;
+    bool active = false;
+    size_t r = 0;
+    int mode = TRACE_CLOSEST;
+    unsigned int blk_next = 0, blk_end = 0;       // warp-uniform: the warp's private block of queue entries
+    bool exhausted = false;                       // warp-uniform: the queue has no more blocks
+
+    for (;;)
+    {
+        unsigned int idle = __ballot_sync(FULL, !active);
+        if (idle)
         {
-            B.res_t[r] = found ? h.t : -1.0f;
-            B.res_prim[r] = h.prim;
-            B.res_tslot[r] = h.slot;
+            if (!exhausted && (idle == FULL || __popc(idle) >= kRefillThreshold))
+            {
+                if (blk_next >= blk_end)
+                {
+                    unsigned int b = 0;
+                    if (lane == 0) b = atomicAdd(head, (unsigned int)kWarpBlock);
+                    b = __shfl_sync(FULL, b, 0);
+                    if (b >= n_rays) exhausted = true;
+                    else { blk_next = b; blk_end = min(b + (unsigned int)kWarpBlock, n_rays); }
+                }
+                if (blk_next < blk_end)
+                {
+                    const unsigned int idx = blk_next + __popc(idle & ((1u << lane) - 1u));
+                    if (!active && idx < blk_end)
+                    {
+                        const unsigned int e = B.queue[idx];
+                        const int slot = (int)(e >> 3), k = (int)(e & 7u);
+                        r = (size_t)k * n + slot;
+                        const float4 ro4 = B.ray_o[r], rd4 = B.ray_d[r];
+                        const int kind = __float_as_int(rd4.w);
+                        mode = kind == SIDE_SHADOW ? TRACE_SHADOW : (kind == SIDE_CLOSEST_LIGHT ? TRACE_CLOSEST : TRACE_ANY);
+                        trav_init<DIAG>(T, V(ro4.x, ro4.y, ro4.z), V(rd4.x, rd4.y, rd4.z), ro4.w, spheres ? TRACE_CLOSEST : mode);
+                        active = true;
+                    }
+                    blk_next = min(blk_next + (unsigned int)__popc(idle), blk_end);
+                }
+                idle = __ballot_sync(FULL, !active);
+            }
+            if (idle == FULL)
+            {
+                if (exhausted) break;
+                continue;
+            }
         }
-        else B.res_prim[r] = found ? 1 : 0;
+        if (active)
+        {
+            // while-while: descend to a leaf (lanes reconverge after this loop), then the exact triangle tests together
+            while (T.cur >= 0 && !T.done) trav_inner<DIAG>(S, T, K);
+            if (!T.done) trav_leaf(S, T, K);
+            if (T.done)
+            {
+                bool found = T.hit.t > 0.0f;
+                if (spheres) found = finish_with_spheres(S, T.o, T.d, T.tmax, mode, T.hit);
+                wf_store_result(B, r, mode, found, T.hit);
+                active = false;
+            }
+        }
     }
 }
 
@@ -315,8 +407,14 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfBuff
     }
     int launches = 0;
     const bool diag = S.has_diag && !(P.flags & B200RT_FLAG_AXIS_SLABS_ONLY);
+    const bool simple = (P.flags & B200RT_FLAG_SIMPLE_TRACE) != 0;
     int per_sm = 0;
-    if (diag) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace<true>, 256, 0);
+    if (simple)
+    {
+        if (diag) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace_simple<true>, 256, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace_simple<false>, 256, 0);
+    }
+    else if (diag) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace<true>, 256, 0);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace<false>, 256, 0);
     if (per_sm <= 0) per_sm = 1;
     const int trace_grid = g_wf_sm_count * per_sm;
@@ -331,7 +429,12 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfBuff
     const long long max_iters = (long long)P.spp * (P.max_bounces + 1) + 2;
     for (long long it = 0; it < max_iters; it++)
     {
-        if (diag) wf_trace<true><<<trace_grid, 256, 0, stream>>>(S, B, parity);
+        if (simple)
+        {
+            if (diag) wf_trace_simple<true><<<trace_grid, 256, 0, stream>>>(S, B, parity);
+            else wf_trace_simple<false><<<trace_grid, 256, 0, stream>>>(S, B, parity);
+        }
+        else if (diag) wf_trace<true><<<trace_grid, 256, 0, stream>>>(S, B, parity);
         else wf_trace<false><<<trace_grid, 256, 0, stream>>>(S, B, parity);
         parity ^= 1;
         wf_shade<<<slot_grid, 256, 0, stream>>>(S, P, B, fb_in_rowmajor, out_tiles, parity);
