@@ -37,8 +37,10 @@ struct b200rt_scene
     int* d_prim = nullptr; float* d_t = nullptr; size_t prim_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // wavefront integrator state (allocated on first use, grown on demand)
-    WfBuffers wf{}; std::vector<void*> wf_allocs; int wf_cap = 0;
-    unsigned int* h_active = nullptr;     // pinned
+    WfGroup wf[kMaxWfGroups]{}; int wf_groups = 0; std::vector<void*> wf_allocs; int wf_cap_tiles = -1; int wf_cap_world = 0, wf_cap_rank = 0;
+    int wf_w = 0, wf_h = 0;
+    unsigned int* h_active = nullptr;     // pinned, one word per group
+    cudaEvent_t fork_event = nullptr;
 };
 
 namespace {
@@ -142,21 +144,64 @@ cudaError_t wf_alloc(b200rt_scene* s, T** p, size_t n)
     return e;
 }
 
-int ensure_wavefront(b200rt_scene* s, int n_slots)
+int wavefront_group_count()
 {
-    if (!s->h_active) CU(cudaMallocHost(&s->h_active, sizeof(unsigned int)));
-    if (n_slots <= s->wf_cap) { s->wf.n_slots = n_slots; return B200RT_OK; }
-    for (void* p : s->wf_allocs) cudaFree(p);
-    s->wf_allocs.clear(); s->wf_cap = 0;
-    WfBuffers& w = s->wf;
-    const size_t n = (size_t)n_slots;
-    CU(wf_alloc(s, &w.rng, n)); CU(wf_alloc(s, &w.sample, n)); CU(wf_alloc(s, &w.bounce, n)); CU(wf_alloc(s, &w.flags, n));
-    CU(wf_alloc(s, &w.final_c, n)); CU(wf_alloc(s, &w.sample_c, n)); CU(wf_alloc(s, &w.thr, n)); CU(wf_alloc(s, &w.thr_next, n));
-    CU(wf_alloc(s, &w.ray_o, 5 * n)); CU(wf_alloc(s, &w.ray_d, 5 * n)); CU(wf_alloc(s, &w.side_w, 4 * n));
-    CU(wf_alloc(s, &w.res_t, 5 * n)); CU(wf_alloc(s, &w.res_prim, 5 * n)); CU(wf_alloc(s, &w.res_tslot, 5 * n));
-    CU(wf_alloc(s, &w.queue, 5 * n)); CU(wf_alloc(s, &w.counters, 8)); CU(wf_alloc(s, &w.rays_total, 1));
-    w.n_slots = n_slots;
-    s->wf_cap = n_slots;
+    static int n = -1;
+    if (n < 0)
+    {
+        const char* e = getenv("B200RT_WF_GROUPS");
+        n = e ? atoi(e) : 4;
+        if (n < 1) n = 1;
+        if (n > kMaxWfGroups) n = kMaxWfGroups;
+    }
+    return n;
+}
+
+int ensure_wavefront(b200rt_scene* s, const RenderParams& P)
+{
+    const int G = wavefront_group_count();
+    if (!s->h_active)
+    {
+        CU(cudaMallocHost(&s->h_active, kMaxWfGroups * sizeof(unsigned int)));
+        CU(cudaEventCreateWithFlags(&s->fork_event, cudaEventDisableTiming));
+        for (int g = 0; g < kMaxWfGroups; g++)
+        {
+            CU(cudaStreamCreateWithFlags(&s->wf[g].stream, cudaStreamNonBlocking));
+            CU(cudaEventCreateWithFlags(&s->wf[g].poll_event, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s->wf[g].join_event, cudaEventDisableTiming));
+            s->wf[g].host_active = s->h_active + g;
+        }
+    }
+    // group g of rank r == rank r + g * world of a (world * G) partition
+    int need[kMaxWfGroups];
+    bool fits = s->wf_groups == G;
+    for (int g = 0; g < G; g++)
+    {
+        need[g] = b200rt_tiles_for_rank(P.cam.w, P.cam.h, P.rank + g * P.world, P.world * G) * kTilePixels;
+        if (fits && need[g] > s->wf[g].buf.n_slots && need[g] > 0) fits = false;
+    }
+    if (!fits || s->wf_w != P.cam.w || s->wf_h != P.cam.h || s->wf_cap_world != P.world || s->wf_cap_rank != P.rank)
+    {
+        for (void* p : s->wf_allocs) cudaFree(p);
+        s->wf_allocs.clear();
+        for (int g = 0; g < G; g++)
+        {
+            WfBuffers& w = s->wf[g].buf;
+            const size_t n = (size_t)std::max(need[g], 1);
+            CU(wf_alloc(s, &w.rng, n)); CU(wf_alloc(s, &w.sample, n)); CU(wf_alloc(s, &w.bounce, n)); CU(wf_alloc(s, &w.flags, n));
+            CU(wf_alloc(s, &w.final_c, n)); CU(wf_alloc(s, &w.sample_c, n)); CU(wf_alloc(s, &w.thr, n)); CU(wf_alloc(s, &w.thr_next, n));
+            CU(wf_alloc(s, &w.ray_o, 5 * n)); CU(wf_alloc(s, &w.ray_d, 5 * n)); CU(wf_alloc(s, &w.side_w, 4 * n));
+            CU(wf_alloc(s, &w.res_t, 5 * n)); CU(wf_alloc(s, &w.res_prim, 5 * n)); CU(wf_alloc(s, &w.res_tslot, 5 * n));
+            CU(wf_alloc(s, &w.queue, 5 * n)); CU(wf_alloc(s, &w.counters, 8)); CU(wf_alloc(s, &w.rays_total, 1));
+        }
+        s->wf_groups = G; s->wf_w = P.cam.w; s->wf_h = P.cam.h; s->wf_cap_world = P.world; s->wf_cap_rank = P.rank;
+    }
+    for (int g = 0; g < G; g++)
+    {
+        s->wf[g].buf.n_slots = need[g];
+        s->wf[g].buf.tile_stride = G;
+        s->wf[g].buf.tile_offset = g;
+    }
     return B200RT_OK;
 }
 
@@ -165,11 +210,11 @@ int run_integrator(b200rt_scene* s, const RenderParams& P, int integrator, const
 {
     if (integrator == B200RT_INTEGRATOR_WAVEFRONT)
     {
-        int rc = ensure_wavefront(s, P.n_rank_tiles * kTilePixels);
+        int rc = ensure_wavefront(s, P);
         if (rc) return rc;
-        CU(run_wavefront(s->dev, P, s->wf, fb_in, out_tiles, s->h_active, st, launches));
-        // the frame's ray count lives in wf.rays_total; mirror it into the shared counter the callers read
-        CU(cudaMemcpyAsync(s->d_rays, s->wf.rays_total, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+        CU(run_wavefront(s->dev, P, s->wf, s->wf_groups, fb_in, out_tiles, st, s->fork_event, launches));
+        CU(wavefront_sum_rays(s->wf, s->wf_groups, s->d_rays, st));
+        *launches += 1;
         return B200RT_OK;
     }
     CU(launch_megakernel(s->dev, P, fb_in, out_tiles, s->d_work, s->d_rays, st));
@@ -379,7 +424,17 @@ void b200rt_scene_destroy(b200rt_scene* s)
     if (s->d_prim) cudaFree(s->d_prim);
     if (s->d_t) cudaFree(s->d_t);
     for (void* p : s->wf_allocs) cudaFree(p);
-    if (s->h_active) cudaFreeHost(s->h_active);
+    if (s->h_active)
+    {
+        for (int g = 0; g < kMaxWfGroups; g++)
+        {
+            if (s->wf[g].stream) cudaStreamDestroy(s->wf[g].stream);
+            if (s->wf[g].poll_event) cudaEventDestroy(s->wf[g].poll_event);
+            if (s->wf[g].join_event) cudaEventDestroy(s->wf[g].join_event);
+        }
+        cudaEventDestroy(s->fork_event);
+        cudaFreeHost(s->h_active);
+    }
     if (s->ev0) cudaEventDestroy(s->ev0);
     if (s->ev1) cudaEventDestroy(s->ev1);
     delete s;

@@ -62,6 +62,7 @@ struct RenderParams
 struct WfBuffers
 {
     int n_slots;
+    int tile_stride, tile_offset;             // slot s of this group writes out_tiles[((s >> 8) * tile_stride + tile_offset) * 256 + (s & 255)]
     uint32_t* rng; int* sample; int* bounce; int* flags;
     float4* final_c; float4* sample_c; float4* thr; float4* thr_next;
     float4* ray_o; float4* ray_d;             // [5 * n_slots]: k * n_slots + slot; k = 0..3 side rays, 4 = path ray; .w = tmax / ray kind
@@ -70,6 +71,17 @@ struct WfBuffers
     unsigned int* queue;                      // [5 * n_slots]: (slot << 3) | k
     unsigned int* counters;                   // [2] = pixels still rendering, [3], [4] = ping-pong queue lengths
     unsigned long long* rays_total;
+};
+
+constexpr int kMaxWfGroups = 8;
+
+// one interleaved tile group of the wavefront integrator: its state, stream and polling resources
+struct WfGroup
+{
+    WfBuffers buf;
+    cudaStream_t stream;
+    cudaEvent_t poll_event, join_event;
+    unsigned int* host_active;      // pinned
 };
 
 } // namespace b200rt

@@ -15,9 +15,10 @@ cudaError_t launch_trace_rays(const SceneDev& S, const float* rays6, int n, int 
 cudaError_t launch_untile(const float4* tiles, int tiles_per_rank_padded, int world, int only_rank, int w, int h, float4* image,
                           cudaStream_t stream);
 
-// wavefront integrator (wavefront.cu): runs the whole frame for this rank's tiles; host_pinned_active is a pinned word
-// used to poll the number of unfinished pixels
-cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfBuffers& B, const float4* fb_in_rowmajor, float4* out_tiles,
-                          unsigned int* host_pinned_active, cudaStream_t stream, int* launches_out);
+// wavefront integrator (wavefront.cu): runs the whole frame for this rank's tiles as n_groups independent interleaved
+// tile groups, each on its own stream; `stream` is forked from and joined back into
+cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGroup* groups, int n_groups, const float4* fb_in_rowmajor,
+                          float4* out_tiles, cudaStream_t stream, cudaEvent_t fork_event, int* launches_out);
+cudaError_t wavefront_sum_rays(const WfGroup* groups, int n_groups, unsigned long long* total, cudaStream_t stream);
 
 } // namespace b200rt

@@ -14,6 +14,9 @@
 //
 // No RNG draw depends on a trace result, which is what allows a whole surface interaction — all four side
 // rays and the continuation ray — to be generated in one shade pass and traced in one trace pass.
+#include <cstdio>
+#include <cstdlib>
+
 #include "kernels.h"
 #include "pt_device.cuh"
 
@@ -49,6 +52,11 @@ __device__ __forceinline__ void wf_start_sample(const RenderParams& P, const WfB
     wf_store_ray(B, 4, slot, o, d, 0.0f, SIDE_CLOSEST_LIGHT);
 }
 
+__device__ __forceinline__ size_t wf_out_index(const WfBuffers& B, int slot)
+{
+    return ((size_t)(slot >> 8) * B.tile_stride + B.tile_offset) * kTilePixels + (slot & 255);
+}
+
 __device__ __forceinline__ bool wf_slot_pixel(const RenderParams& P, int slot, int& x, int& y)
 {
     const int unit = slot >> 5, lane = slot & 31;
@@ -69,12 +77,12 @@ __global__ void __launch_bounds__(256) wf_init(SceneDev S, RenderParams P, WfBuf
     {
         int x, y;
         const bool inside = wf_slot_pixel(P, slot, x, y);
-        if (!inside) { out_tiles[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); B.flags[slot] = WF_DONE; }
+        if (!inside) { out_tiles[wf_out_index(B, slot)] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); B.flags[slot] = WF_DONE; }
         else if (P.spp <= 0 || P.max_bounces <= 0)
         {
             const float4 fb = fb_in_rowmajor ? fb_in_rowmajor[(size_t)y * P.cam.w + x] : make_float4(0.0f, 0.0f, 0.0f, 1.0f);
             const float n = (float)P.spp;
-            out_tiles[slot] = tonemap(fb, CO(0.0f / n, 0.0f / n, 0.0f / n));
+            out_tiles[wf_out_index(B, slot)] = tonemap(fb, CO(0.0f / n, 0.0f / n, 0.0f / n));
             B.flags[slot] = WF_DONE;
         }
         else
@@ -256,7 +264,7 @@ __global__ void __launch_bounds__(256) wf_shade(SceneDev S, RenderParams P, WfBu
                 const float nspp = (float)P.spp;
                 const col mean = CO(final_color.r / nspp, final_color.g / nspp, final_color.b / nspp);
                 const float4 fb = fb_in_rowmajor ? fb_in_rowmajor[(size_t)y * P.cam.w + x] : make_float4(0.0f, 0.0f, 0.0f, 1.0f);
-                out_tiles[slot] = tonemap(fb, mean);
+                out_tiles[wf_out_index(B, slot)] = tonemap(fb, mean);
                 flags = WF_DONE;
                 pixel_done = true;
             }
@@ -316,6 +324,7 @@ __global__ void __launch_bounds__(256) wf_trace_simple(SceneDev S, WfBuffers B, 
 // with one atomic), so no lane waits for the slowest ray of its warp (Aila & Laine's persistent threads, per lane).
 constexpr int kWarpBlock = 128;
 constexpr int kRefillThreshold = 8;
+constexpr int kLeafThreshold = 4;
 
 template <bool DIAG>
 __global__ void __launch_bounds__(256) wf_trace(SceneDev S, WfBuffers B, int parity)
@@ -370,33 +379,37 @@ __global__ void __launch_bounds__(256) wf_trace(SceneDev S, WfBuffers B, int par
                 }
                 idle = __ballot_sync(FULL, !active);
             }
-            if (idle == FULL)
-            {
-                if (exhausted) break;
-                continue;
-            }
         }
-        if (active)
+        // warp-level phase vote: all lanes that hold an inner node step together, or all lanes that hold a leaf run the
+        // exact triangle tests together, whichever is the majority — the two kinds of work never interleave inside a warp
+        const bool has_inner = active && T.cur >= 0, has_leaf = active && T.cur < 0;
+        const unsigned int m_inner = __ballot_sync(FULL, has_inner), m_leaf = __ballot_sync(FULL, has_leaf);
+        if (!(m_inner | m_leaf))
         {
-            // while-while: descend to a leaf (lanes reconverge after this loop), then the exact triangle tests together
-            while (T.cur >= 0 && !T.done) trav_inner<DIAG>(S, T, K);
-            if (!T.done) trav_leaf(S, T, K);
-            if (T.done)
-            {
-                bool found = T.hit.t > 0.0f;
-                if (spheres) found = finish_with_spheres(S, T.o, T.d, T.tmax, mode, T.hit);
-                wf_store_result(B, r, mode, found, T.hit);
-                active = false;
-            }
+            if (exhausted) break;
+            continue;
+        }
+        if (m_inner && __popc(m_leaf) < max(__popc(m_inner), kLeafThreshold)) { if (has_inner) trav_inner<DIAG>(S, T, K); }
+        else if (has_leaf) trav_leaf(S, T, K);
+        if (active && T.done)
+        {
+            bool found = T.hit.t > 0.0f;
+            if (spheres) found = finish_with_spheres(S, T.o, T.d, T.tmax, mode, T.hit);
+            wf_store_result(B, r, mode, found, T.hit);
+            active = false;
         }
     }
 }
 
 // ---- host driver ---------------------------------------------------------------------------------------------------------------
+// The frame's pixels are split into n_groups interleaved tile groups (group g of rank r behaves like rank r + g * world of
+// a world * n_groups partition). Each group runs its own trace/shade iteration chain on its own stream, so while one
+// group's trace pass drains its longest rays (a single ray is a dependent chain of node fetches; the slowest ray of a
+// pass bounds that pass) the other groups' kernels fill the machine. Groups never exchange data.
 static int g_wf_sm_count = 0;
 
-cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfBuffers& B, const float4* fb_in_rowmajor, float4* out_tiles,
-                          unsigned int* host_pinned_active, cudaStream_t stream, int* launches_out)
+cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGroup* groups, int n_groups, const float4* fb_in_rowmajor,
+                          float4* out_tiles, cudaStream_t stream, cudaEvent_t fork_event, int* launches_out)
 {
     if (!g_wf_sm_count)
     {
@@ -418,35 +431,126 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfBuff
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace<false>, 256, 0);
     if (per_sm <= 0) per_sm = 1;
     const int trace_grid = g_wf_sm_count * per_sm;
-    const int slot_grid = (B.n_slots + 255) / 256;
-    if (slot_grid <= 0) { if (launches_out) *launches_out = 0; return cudaSuccess; }
+    static const bool timing = getenv("B200RT_WF_TIMING") != nullptr;      // diagnostics: per-kernel times on stderr (serialises the groups)
     cudaError_t e;
-    if ((e = cudaMemsetAsync(B.counters, 0, 8 * sizeof(unsigned int), stream)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(B.rays_total, 0, sizeof(unsigned long long), stream)) != cudaSuccess) return e;
-    wf_init<<<slot_grid, 256, 0, stream>>>(S, P, B, fb_in_rowmajor, out_tiles);
-    launches++;
-    int parity = 0;      // wf_init filled queue 0
-    const long long max_iters = (long long)P.spp * (P.max_bounces + 1) + 2;
-    for (long long it = 0; it < max_iters; it++)
+
+    // fork: every group stream starts after the work already queued on the caller's stream
+    if ((e = cudaEventRecord(fork_event, stream)) != cudaSuccess) return e;
+    struct GroupRun { RenderParams P; int parity; bool finished; int slot_grid; long long it, poll_it; bool poll_pending; };
+    GroupRun run[kMaxWfGroups];
+    for (int g = 0; g < n_groups; g++)
     {
-        if (simple)
+        const WfGroup& G = groups[g];
+        GroupRun& R = run[g];
+        R.P = P;
+        R.P.rank = P.rank + g * P.world;
+        R.P.world = P.world * n_groups;
+        R.P.n_rank_tiles = G.buf.n_slots / kTilePixels;
+        R.parity = 0; R.it = 0; R.poll_it = 0; R.poll_pending = false;
+        R.slot_grid = (G.buf.n_slots + 255) / 256;
+        R.finished = R.slot_grid <= 0;
+        if (R.finished) continue;
+        if ((e = cudaStreamWaitEvent(G.stream, fork_event, 0)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(G.buf.counters, 0, 8 * sizeof(unsigned int), G.stream)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(G.buf.rays_total, 0, sizeof(unsigned long long), G.stream)) != cudaSuccess) return e;
+        wf_init<<<R.slot_grid, 256, 0, G.stream>>>(S, R.P, G.buf, fb_in_rowmajor, out_tiles);
+        launches++;
+    }
+    const long long max_iters = (long long)P.spp * (P.max_bounces + 1) + 2;
+    cudaEvent_t tev[3] = { nullptr, nullptr, nullptr };
+    double t_trace = 0.0, t_shade = 0.0;
+    if (timing) for (int i = 0; i < 3; i++) cudaEventCreate(&tev[i]);
+    int remaining = 0;
+    for (int g = 0; g < n_groups; g++) remaining += run[g].finished ? 0 : 1;
+    while (remaining > 0)
+    {
+        for (int g = 0; g < n_groups; g++)
         {
-            if (diag) wf_trace_simple<true><<<trace_grid, 256, 0, stream>>>(S, B, parity);
-            else wf_trace_simple<false><<<trace_grid, 256, 0, stream>>>(S, B, parity);
-        }
-        else if (diag) wf_trace<true><<<trace_grid, 256, 0, stream>>>(S, B, parity);
-        else wf_trace<false><<<trace_grid, 256, 0, stream>>>(S, B, parity);
-        parity ^= 1;
-        wf_shade<<<slot_grid, 256, 0, stream>>>(S, P, B, fb_in_rowmajor, out_tiles, parity);
-        launches += 2;
-        if ((it & 3) == 3 || it + 1 == max_iters)
-        {
-            if ((e = cudaMemcpyAsync(host_pinned_active, &B.counters[2], sizeof(unsigned int), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) return e;
-            if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) return e;
-            if (*host_pinned_active == 0) break;
+            GroupRun& R = run[g];
+            if (R.finished) continue;
+            const WfGroup& G = groups[g];
+            // has an earlier poll of this group's unfinished-pixel counter landed?
+            if (R.poll_pending && cudaEventQuery(G.poll_event) == cudaSuccess)
+            {
+                R.poll_pending = false;
+                if (*G.host_active == 0) { R.finished = true; remaining--; continue; }
+            }
+            // bounded run-ahead: at most kRunAhead iterations queued behind an unanswered poll (a finished group would
+            // otherwise leave a long train of empty launches behind)
+            if (R.poll_pending && R.it - R.poll_it >= 8) continue;
+            if (R.it >= max_iters)
+            {
+                // safety net: every pixel must be finished by now; wait for the last poll and stop
+                if ((e = cudaStreamSynchronize(G.stream)) != cudaSuccess) return e;
+                R.finished = true; remaining--;
+                continue;
+            }
+            if (timing) cudaEventRecord(tev[0], G.stream);
+            if (simple)
+            {
+                if (diag) wf_trace_simple<true><<<trace_grid, 256, 0, G.stream>>>(S, G.buf, R.parity);
+                else wf_trace_simple<false><<<trace_grid, 256, 0, G.stream>>>(S, G.buf, R.parity);
+            }
+            else if (diag) wf_trace<true><<<trace_grid, 256, 0, G.stream>>>(S, G.buf, R.parity);
+            else wf_trace<false><<<trace_grid, 256, 0, G.stream>>>(S, G.buf, R.parity);
+            if (timing) cudaEventRecord(tev[1], G.stream);
+            R.parity ^= 1;
+            wf_shade<<<R.slot_grid, 256, 0, G.stream>>>(S, R.P, G.buf, fb_in_rowmajor, out_tiles, R.parity);
+            launches += 2;
+            if (timing)
+            {
+                cudaEventRecord(tev[2], G.stream);
+                cudaEventSynchronize(tev[2]);
+                float a = 0, b = 0;
+                cudaEventElapsedTime(&a, tev[0], tev[1]); cudaEventElapsedTime(&b, tev[1], tev[2]);
+                unsigned int nq[8];
+                cudaMemcpy(nq, G.buf.counters, sizeof(nq), cudaMemcpyDeviceToHost);
+                t_trace += a; t_shade += b;
+                fprintf(stderr, "wf g%d it %lld: trace %.3f ms  shade %.3f ms  active px %u  next queue %u\n", g, R.it, a, b, nq[2], nq[3 + R.parity]);
+            }
+            R.it++;
+            if (!R.poll_pending && ((R.it & 3) == 0 || R.it >= max_iters))
+            {
+                if ((e = cudaMemcpyAsync(G.host_active, &G.buf.counters[2], sizeof(unsigned int), cudaMemcpyDeviceToHost, G.stream)) != cudaSuccess) return e;
+                if ((e = cudaEventRecord(G.poll_event, G.stream)) != cudaSuccess) return e;
+                R.poll_pending = true;
+                R.poll_it = R.it;
+            }
         }
     }
+    // join: the caller's stream continues after every group; the frame's ray count is the sum of the groups'
+    for (int g = 0; g < n_groups; g++)
+    {
+        const WfGroup& G = groups[g];
+        if (run[g].slot_grid <= 0) continue;
+        if ((e = cudaEventRecord(G.join_event, G.stream)) != cudaSuccess) return e;
+        if ((e = cudaStreamWaitEvent(stream, G.join_event, 0)) != cudaSuccess) return e;
+    }
+    if (timing)
+    {
+        fprintf(stderr, "wf total: trace %.3f ms  shade %.3f ms  launches %d\n", t_trace, t_shade, launches);
+        for (int i = 0; i < 3; i++) cudaEventDestroy(tev[i]);
+    }
     if (launches_out) *launches_out = launches;
+    return cudaGetLastError();
+}
+
+// sums the groups' ray counters into *total (one tiny launch on the caller's stream, after the join)
+__global__ void wf_sum_rays(const unsigned long long* a, const unsigned long long* b, const unsigned long long* c, const unsigned long long* d,
+                            const unsigned long long* e2, const unsigned long long* f, const unsigned long long* g, const unsigned long long* h,
+                            int n, unsigned long long* total)
+{
+    const unsigned long long* p[8] = { a, b, c, d, e2, f, g, h };
+    unsigned long long s = 0;
+    for (int i = 0; i < n; i++) s += *p[i];
+    *total = s;
+}
+
+cudaError_t wavefront_sum_rays(const WfGroup* groups, int n_groups, unsigned long long* total, cudaStream_t stream)
+{
+    const unsigned long long* p[8];
+    for (int i = 0; i < 8; i++) p[i] = groups[i < n_groups ? i : 0].buf.rays_total;
+    wf_sum_rays<<<1, 1, 0, stream>>>(p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], n_groups, total);
     return cudaGetLastError();
 }
 
