@@ -9,8 +9,8 @@ HDR skysphere with env-map importance sampling + BRDF importance sampling + MIS.
 OBJ nor the HDR (.MISSING_LARGE_BLOBS), so the Dragon-class procedural stand-in of SURVEY.md Appendix A is used
 (1 000 002 triangles, gold metal roughness 0.25, 2048x1024 sun+sky) — `data` says so.
 
-A step = one full frame: every rank renders its interleaved 16x16 tiles with the megakernel, the tile buffers are
-gathered to rank 0 (NCCL) and un-tiled there. value = INTERSECT_SCENE-equivalent rays of the whole frame / step time
+A step = one full frame: every rank renders its interleaved 16x16 tiles (wavefront integrator by default: wf_shade /
+wf_trace kernel pairs over 4 tile groups on 4 streams), the tile buffers are gathered to rank 0 (NCCL) and un-tiled there. value = INTERSECT_SCENE-equivalent rays of the whole frame / step time
 (CUDA events on the launching stream, max over ranks). Total work is fixed as N grows => "scaling": "strong".
 One JSON line on stdout (rank 0).
 """
@@ -142,7 +142,7 @@ def cpu_sample_shape(name, args, w, h, spp):
         a = [int(v) for v in args.cpu_sample.lower().split("x")]
         return a[0], a[1], a[2]
     if name == "c3":
-        return 384, 216, 4          # 1/25 of the pixels, 1/16 of the spp: ~10-30 s of reference CPU work
+        return 768, 432, 4          # 4/25 of the pixels, 1/16 of the spp: ~10-30 s of reference CPU work on 16 cores
     if name == "c5":
         return 192, 108, 1
     return w, h, spp                # c1 / c2 run in full on the CPU
@@ -353,6 +353,23 @@ def main():
         e2e = {"value": rays_per_frame / float(e_sec.item()) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 68,
                "d2h_bytes_per_step": w * h * 16, "api": "distributed.FrameGatherer.frame + D2H (rank 0)"}
 
+    # same frame with the rays that provably cannot change the image skipped (B200RT_FLAG_SKIP_DEAD_RAYS): reported next to
+    # the headline, which keeps the reference's full ray set
+    dead = None
+    if not primary_only:
+        g2 = D.make_cuda_gatherer(scene, cam, w, h, spp, bounces, rank, world, device, integrator=args.integrator,
+                                  flags=args.flags | rt.binding.FLAG_SKIP_DEAD_RAYS)
+        g2.frame()
+        barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); g2.frame(); b.record()
+        barrier()
+        dms = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(dms, op=dist.ReduceOp.MAX)
+        dead = {"ms_per_step": float(dms.item()), "spp_per_s": (w * h * spp) / (float(dms.item()) * 1e-3)}
+        del g2
+
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         try:
@@ -387,6 +404,7 @@ def main():
                        "l2": "256 MiB buffer written between timed iterations (L2 flush)",
                        "bvh": {k: info[k] for k in ("n_inner_nodes", "n_leaves", "max_depth", "has_diag_slabs")},
                        "scene_build_s": build_s, "scene_device_bytes": scene.device_bytes()},
+            "skip_dead_rays": dead,
             "clocks": sampler.result(),
             "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps,

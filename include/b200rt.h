@@ -93,13 +93,15 @@ int b200rt_scene_get_bvh_info(const b200rt_scene* scene, b200rt_bvh_info* out);
 size_t b200rt_scene_device_bytes(const b200rt_scene* scene);
 
 /* ---- rendering -------------------------------------------------------------------------------------------------------- */
-#define B200RT_INTEGRATOR_MEGAKERNEL 0   /* one thread = one pixel, persistent warps pulling 8x4 pixel patches */
-#define B200RT_INTEGRATOR_WAVEFRONT 1    /* path-regeneration wavefront: generate/extend/shade/connect kernels */
+#define B200RT_INTEGRATOR_MEGAKERNEL 0   /* persistent lanes, one pixel at a time per lane, single trace site */
+#define B200RT_INTEGRATOR_WAVEFRONT 1    /* path-regeneration wavefront: shade / trace kernel pairs over tile groups (default) */
 
 #define B200RT_FLAG_FB_IS_ZERO 1         /* caller guarantees the framebuffer is Color::Black(): skip its upload */
 #define B200RT_FLAG_SKIP_DEAD_RAYS 2     /* skip rays whose result provably cannot change the image */
-#define B200RT_FLAG_AXIS_SLABS_ONLY 4    /* ablation: ignore the 4 diagonal slabs while traversing */
-#define B200RT_FLAG_SIMPLE_TRACE 8       /* ablation: wavefront trace kernel without per-lane ray refill */
+#define B200RT_FLAG_DIAG_SLABS 4         /* traverse with all 7 planes (test the 4 diagonal slabs after the 3 axis slabs); default: axis slabs
+                                            only — measured faster on every workload, see DESIGN.md */
+#define B200RT_FLAG_PERSISTENT_TRACE 8   /* wavefront: persistent trace kernel with per-lane ray refill + warp phase vote instead of the
+                                            one-ray-per-lane kernel; default off — measured slower end to end, see DESIGN.md */
 
 typedef struct b200rt_render_options
 {

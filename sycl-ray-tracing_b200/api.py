@@ -288,11 +288,11 @@ class Scene:
         B.check(B.load_library().b200rt_scene_set_materials(self._h, B.fptr(self.mats), len(self.mats)))
 
     @staticmethod
-    def _opts(integrator=0, flags=0, rank=0, world=1):
+    def _opts(integrator=B.INTEGRATOR_WAVEFRONT, flags=0, rank=0, world=1):
         return B.RenderOptions(integrator, flags, rank, world)
 
     def render(self, camera: Camera, w: int, h: int, spp: int, max_bounces: int, framebuffer: np.ndarray | None = None,
-               integrator: int = 0, flags: int = 0, rank: int = 0, world: int = 1):
+               integrator: int = B.INTEGRATOR_WAVEFRONT, flags: int = 0, rank: int = 0, world: int = 1):
         """RenderKernel::render() on host buffers. Returns (framebuffer, stats)."""
         if framebuffer is None:
             framebuffer = Image(w, h).pixels
@@ -327,7 +327,7 @@ class Scene:
 
     # device-pointer variants (pointers are plain ints, e.g. torch.Tensor.data_ptr())
     def render_tiles_device(self, camera: Camera, w, h, spp, max_bounces, dev_tiles_ptr: int, stream_ptr: int = 0,
-                            integrator: int = 0, flags: int = 0, rank: int = 0, world: int = 1, want_stats: bool = False):
+                            integrator: int = B.INTEGRATOR_WAVEFRONT, flags: int = 0, rank: int = 0, world: int = 1, want_stats: bool = False):
         st = B.Stats()
         o = self._opts(integrator, flags, rank, world)
         B.check(B.load_library().b200rt_render_tiles_device(self._h, B.fptr(camera.as_array17()), w, h, spp, max_bounces,
@@ -368,7 +368,7 @@ class RenderKernel:
 
     def __init__(self, width, height, render_samples, max_bounces, image_buffer: Image, triangle_buffer, materials_buffer,
                  emissive_triangle_indices, materials_indices, analytic_spheres=None, bvh: BVH | None = None,
-                 skysphere: Image | None = None, env_map_cdf=None, integrator: int = B.INTEGRATOR_MEGAKERNEL, flags: int = 0):
+                 skysphere: Image | None = None, env_map_cdf=None, integrator: int = B.INTEGRATOR_WAVEFRONT, flags: int = 0):
         self.m_width, self.m_height = int(width), int(height)
         self.m_render_samples, self.m_max_bounces = int(render_samples), int(max_bounces)
         self.m_frame_buffer = image_buffer

@@ -17,8 +17,8 @@ INTEGRATOR_MEGAKERNEL = 0
 INTEGRATOR_WAVEFRONT = 1
 FLAG_FB_IS_ZERO = 1
 FLAG_SKIP_DEAD_RAYS = 2
-FLAG_AXIS_SLABS_ONLY = 4
-FLAG_SIMPLE_TRACE = 8
+FLAG_DIAG_SLABS = 4
+FLAG_PERSISTENT_TRACE = 8
 TILE_DIM = 16
 TILE_PIXELS = 256
 

@@ -255,7 +255,7 @@ void b200rt_bvh_default_options(b200rt_bvh_options* o)
 void b200rt_default_render_options(b200rt_render_options* o)
 {
     if (!o) return;
-    o->integrator = B200RT_INTEGRATOR_MEGAKERNEL; o->flags = 0; o->rank = 0; o->world = 1;
+    o->integrator = B200RT_INTEGRATOR_WAVEFRONT; o->flags = 0; o->rank = 0; o->world = 1;
 }
 
 int b200rt_bvh_build(const float* tri_xyz9, int n_tri, const b200rt_bvh_options* opts, b200rt_bvh** out)
@@ -468,7 +468,7 @@ int b200rt_render_tiles_device(b200rt_scene* s, const float* camera17, int w, in
     CU(cudaSetDevice(s->device));
     if ((rc = ensure_scratch(s, 0, 0, 0))) return rc;
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    const int integrator = opts ? opts->integrator : B200RT_INTEGRATOR_MEGAKERNEL;
+    const int integrator = opts ? opts->integrator : B200RT_INTEGRATOR_WAVEFRONT;
     CU(cudaMemsetAsync(s->d_rays, 0, sizeof(unsigned long long), st));
     if (stats) CU(cudaEventRecord(s->ev0, st));
     int launches = 0;
@@ -522,7 +522,7 @@ int b200rt_render(b200rt_scene* s, const float* camera17, int w, int h, int spp,
     CU(cudaMemsetAsync(s->d_rays, 0, sizeof(unsigned long long), st));
     CU(cudaEventRecord(s->ev0, st));
     const float4* fb_in = (P.flags & B200RT_FLAG_FB_IS_ZERO) ? nullptr : s->d_image;
-    const int integrator = opts ? opts->integrator : B200RT_INTEGRATOR_MEGAKERNEL;
+    const int integrator = opts ? opts->integrator : B200RT_INTEGRATOR_WAVEFRONT;
     if (integrator != B200RT_INTEGRATOR_MEGAKERNEL && integrator != B200RT_INTEGRATOR_WAVEFRONT) return fail(B200RT_ERR_ARG, "unknown integrator %d", integrator);
     int launches = 0;
     if ((rc = run_integrator(s, P, integrator, fb_in, s->d_tiles, st, &launches))) return rc;

@@ -273,7 +273,7 @@ cudaError_t launch_megakernel(const SceneDev& S, const RenderParams& P, const fl
 {
     cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned int), stream);
     if (e != cudaSuccess) return e;
-    const bool diag = S.has_diag && !(P.flags & B200RT_FLAG_AXIS_SLABS_ONLY);
+    const bool diag = S.has_diag && (P.flags & B200RT_FLAG_DIAG_SLABS);
     int per_sm = 0;
     if (diag) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pathtrace_mega<true>, 256, 0);
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pathtrace_mega<false>, 256, 0);
@@ -292,7 +292,7 @@ cudaError_t launch_primary(const SceneDev& S, const RenderParams& P, int sample,
     const int n_warps = P.n_rank_tiles * 8;
     if (n_warps <= 0) return cudaSuccess;
     const int grid = (n_warps * 32 + 255) / 256;
-    const bool diag = S.has_diag && !(P.flags & B200RT_FLAG_AXIS_SLABS_ONLY);
+    const bool diag = S.has_diag && (P.flags & B200RT_FLAG_DIAG_SLABS);
     if (diag) k_primary<true><<<grid, 256, 0, stream>>>(S, P, sample, prim_out, t_out);
     else k_primary<false><<<grid, 256, 0, stream>>>(S, P, sample, prim_out, t_out);
     return cudaGetLastError();
@@ -303,7 +303,7 @@ cudaError_t launch_trace_rays(const SceneDev& S, const float* rays6, int n, int 
 {
     if (n <= 0) return cudaSuccess;
     const int grid = (n + 255) / 256;
-    const bool diag = S.has_diag && !(flags & B200RT_FLAG_AXIS_SLABS_ONLY);
+    const bool diag = S.has_diag && (flags & B200RT_FLAG_DIAG_SLABS);
     if (diag) k_trace_rays<true><<<grid, 256, 0, stream>>>(S, rays6, n, any_hit, prim_out, t_out, extra8);
     else k_trace_rays<false><<<grid, 256, 0, stream>>>(S, rays6, n, any_hit, prim_out, t_out, extra8);
     return cudaGetLastError();

@@ -298,7 +298,7 @@ __device__ __forceinline__ void wf_store_result(const WfBuffers& B, size_t r, in
     else B.res_prim[r] = found ? 1 : 0;
 }
 
-// simple variant (ablation, B200RT_FLAG_SIMPLE_TRACE): one ray per lane, the warp waits for its slowest ray
+// default variant: one ray per lane, grid-stride over the queue (the warp waits for its slowest ray)
 template <bool DIAG>
 __global__ void __launch_bounds__(256) wf_trace_simple(SceneDev S, WfBuffers B, int parity)
 {
@@ -319,7 +319,7 @@ __global__ void __launch_bounds__(256) wf_trace_simple(SceneDev S, WfBuffers B, 
     }
 }
 
-// persistent variant: every lane owns one traversal state; whenever at least kRefillThreshold lanes of a warp are idle
+// persistent variant (B200RT_FLAG_PERSISTENT_TRACE): every lane owns one traversal state; whenever at least kRefillThreshold lanes of a warp are idle
 // they are refilled with new rays from the warp's private block of the queue (blocks of kWarpBlock rays are claimed
 // with one atomic), so no lane waits for the slowest ray of its warp (Aila & Laine's persistent threads, per lane).
 constexpr int kWarpBlock = 128;
@@ -419,8 +419,8 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
         if (g_wf_sm_count <= 0) g_wf_sm_count = 148;
     }
     int launches = 0;
-    const bool diag = S.has_diag && !(P.flags & B200RT_FLAG_AXIS_SLABS_ONLY);
-    const bool simple = (P.flags & B200RT_FLAG_SIMPLE_TRACE) != 0;
+    const bool diag = S.has_diag && (P.flags & B200RT_FLAG_DIAG_SLABS);
+    const bool simple = !(P.flags & B200RT_FLAG_PERSISTENT_TRACE);
     int per_sm = 0;
     if (simple)
     {

@@ -68,7 +68,7 @@ def test_primary_bit_exact_bundled(rt, golden_scenes, golden_cameras, key):
     prim, t, st = sc.trace_primary(cam(rt, golden_cameras, CAM_OF[key]), int(g["w"]), int(g["h"]))
     assert_primary_parity(prim, t, g["prim"], g["prim_brute"], g["t"], max_ties=0)
     # 7-plane and 3-plane traversals must agree exactly
-    prim2, t2, _ = sc.trace_primary(cam(rt, golden_cameras, CAM_OF[key]), int(g["w"]), int(g["h"]), flags=rt.FLAG_AXIS_SLABS_ONLY)
+    prim2, t2, _ = sc.trace_primary(cam(rt, golden_cameras, CAM_OF[key]), int(g["w"]), int(g["h"]), flags=rt.FLAG_DIAG_SLABS)
     assert np.array_equal(prim, prim2) and np.array_equal(bits(t), bits(t2))
 
 
@@ -135,7 +135,7 @@ def test_render_matches_reference_framebuffer(rt, golden_scenes, golden_cameras,
     assert s["frac_close"] >= 0.97, s
     assert s["rmse"] <= 0.02, s
     assert abs(s["mean_gpu"] - s["mean_ref"]) <= 0.01 * max(s["mean_ref"], 1e-6), s
-    assert st["rays"] > 0 and st["gpu_launches"] == 2
+    assert st["rays"] > 0 and st["gpu_launches"] >= 2
 
 
 def test_render_c3_small_matches_reference(rt, golden_cameras):
@@ -177,7 +177,7 @@ def test_flags_do_not_change_the_image(rt, golden_scenes, golden_cameras):
     base, st0 = sc.render(c, 96, 80, 4, 5)
     again, _ = sc.render(c, 96, 80, 4, 5)
     assert np.array_equal(bits(base), bits(again)), "render must be deterministic"
-    axis, _ = sc.render(c, 96, 80, 4, 5, flags=rt.FLAG_AXIS_SLABS_ONLY)
+    axis, _ = sc.render(c, 96, 80, 4, 5, flags=rt.FLAG_DIAG_SLABS)
     assert np.array_equal(bits(base), bits(axis)), "3-plane and 7-plane traversal must give the same closest hits"
     skip, st1 = sc.render(c, 96, 80, 4, 5, flags=rt.FLAG_SKIP_DEAD_RAYS)
     assert np.array_equal(bits(base), bits(skip))
@@ -262,9 +262,11 @@ def test_wavefront_c3_small_and_tiles(rt, golden_cameras):
     c3 = scenes.c3_scene(roughness=float(g["roughness"]), nu=int(g["nu"]), nv=int(g["nv"]), sky_w=int(g["sky_w"]), sky_h=int(g["sky_h"]))
     sc = rt.Scene(c3["tri9"], c3["mat_idx"], c3["mats10"], c3["emissive"], skysphere=c3["env"])
     w, h, spp, b = int(g["w"]), int(g["h"]), int(g["spp"]), int(g["bounces"])
-    mega, st_m = sc.render(c3["camera"], w, h, spp, b)
+    mega, st_m = sc.render(c3["camera"], w, h, spp, b, integrator=rt.INTEGRATOR_MEGAKERNEL)
     wave, st_w = sc.render(c3["camera"], w, h, spp, b, integrator=rt.INTEGRATOR_WAVEFRONT)
     assert np.array_equal(bits(mega), bits(wave)) and st_m["rays"] == st_w["rays"]
+    pers, st_p = sc.render(c3["camera"], w, h, spp, b, integrator=rt.INTEGRATOR_WAVEFRONT, flags=rt.FLAG_PERSISTENT_TRACE | rt.FLAG_DIAG_SLABS)
+    assert np.array_equal(bits(mega), bits(pers)) and st_p["rays"] == st_m["rays"], "persistent trace kernel + 7-plane traversal"
     skip, st_s = sc.render(c3["camera"], w, h, spp, b, integrator=rt.INTEGRATOR_WAVEFRONT, flags=rt.FLAG_SKIP_DEAD_RAYS)
     assert np.array_equal(bits(mega), bits(skip)) and st_s["rays"] < st_w["rays"], "no emissive material: the BRDF->light rays are dead"
     fb = rt.Image(w, h).pixels
@@ -272,5 +274,5 @@ def test_wavefront_c3_small_and_tiles(rt, golden_cameras):
         sc.render(c3["camera"], w, h, spp, b, framebuffer=fb, integrator=rt.INTEGRATOR_WAVEFRONT, rank=rank, world=3)
     assert np.array_equal(bits(fb), bits(mega))
     zero, _ = sc.render(c3["camera"], 40, 30, 0, 4, integrator=rt.INTEGRATOR_WAVEFRONT)
-    zero_m, _ = sc.render(c3["camera"], 40, 30, 0, 4)
+    zero_m, _ = sc.render(c3["camera"], 40, 30, 0, 4, integrator=rt.INTEGRATOR_MEGAKERNEL)
     assert np.array_equal(bits(zero), bits(zero_m))
