@@ -1,0 +1,80 @@
+"""-m gpu: the reference's UNMODIFIED source/main.cpp, linked against the drop-in RenderKernel
+(sycl-ray-tracing_b200/host/dropin, built in the build container where /root/reference exists; the binary travels with
+the repo snapshot), renders an OBJ + MTL + HDR from disk on the GPU and writes RT_output.png. The PNG must match a render
+of the same scene through the Python mirror."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+
+pytestmark = pytest.mark.gpu
+
+BIN = os.path.join(ROOT, "sycl-ray-tracing_b200", "host", "dropin", "_build", "SYCL_RayTracing_b200")
+
+
+def write_obj(path, tri9, mat_idx, mats10):
+    names = [f"m{i}" for i in range(len(mats10))]
+    with open(path + ".mtl", "w") as f:
+        for i in range(1, len(mats10)):            # slot 0 is parse_obj's built-in default material (utils.cpp:75)
+            m = mats10[i]
+            f.write(f"newmtl {names[i]}\nKe {m[0]:.9g} {m[1]:.9g} {m[2]:.9g}\nKd {m[4]:.9g} {m[5]:.9g} {m[6]:.9g}\n"
+                    f"Pm {m[8]:.9g}\nPr {m[9]:.9g}\nillum 2\n\n")
+    with open(path + ".obj", "w") as f:
+        f.write(f"mtllib {os.path.basename(path)}.mtl\n")
+        for t in tri9:
+            for v in range(3):
+                f.write(f"v {t[3 * v]:.9g} {t[3 * v + 1]:.9g} {t[3 * v + 2]:.9g}\n")
+        cur = -1
+        for i in range(len(tri9)):
+            if mat_idx[i] != cur:
+                cur = int(mat_idx[i])
+                f.write(f"usemtl {names[cur]}\n")
+            f.write(f"f {3 * i + 1} {3 * i + 2} {3 * i + 3}\n")
+
+
+def write_hdr_and_decode(path, env_rgb):
+    """Flat (non-RLE) Radiance RGBE; returns the float image exactly as stb_image decodes it and
+    Utils::read_image_float stores it (vertical flip on load, alpha 0; utils.cpp:100-124)."""
+    h, w, _ = env_rgb.shape
+    m = env_rgb.max(axis=-1)
+    mant, ex = np.frexp(m.astype(np.float64))
+    scale = np.where(m > 1e-32, mant * 256.0 / np.maximum(m, 1e-38), 0.0)
+    rgbe = np.zeros((h, w, 4), np.uint8)
+    rgbe[..., :3] = np.clip(env_rgb * scale[..., None], 0, 255).astype(np.uint8)
+    rgbe[..., 3] = np.where(m > 1e-32, ex + 128, 0).astype(np.uint8)
+    file_rows = rgbe[::-1]                                   # file row 0 = top = last row in memory after the flip
+    with open(path, "wb") as f:
+        f.write(b"#?RADIANCE\nFORMAT=32-bit_rle_rgbe\n\n" + f"-Y {h} +X {w}\n".encode())
+        f.write(file_rows.tobytes())
+    f1 = np.ldexp(np.float32(1.0), rgbe[..., 3].astype(np.int32) - 136).astype(np.float32)
+    dec = np.zeros((h, w, 4), np.float32)
+    dec[..., :3] = np.where(rgbe[..., 3:4] != 0, rgbe[..., :3].astype(np.float32) * f1[..., None], 0.0)
+    return dec
+
+
+@pytest.mark.skipif(not os.path.exists(BIN), reason="drop-in main.cpp binary not built (needs /root/reference at build time)")
+def test_reference_main_cpp_drives_the_b200_path(rt, tmp_path):
+    from PIL import Image as PILImage
+    from sycl_ray_tracing_b200 import scenes
+    c3 = scenes.c3_scene(nu=100, nv=50, sky_w=64, sky_h=32)
+    base = str(tmp_path / "scene")
+    write_obj(base, c3["tri9"], c3["mat_idx"], c3["mats10"])
+    env = write_hdr_and_decode(str(tmp_path / "sky.hdr"), c3["env"][..., :3])
+    w, h, spp, bounces = 96, 54, 4, 4
+    r = subprocess.run([BIN, f"--sky={tmp_path / 'sky.hdr'}", f"--w={w}", f"--h={h}", f"--samples={spp}", f"--bounces={bounces}", base + ".obj"],
+                       cwd=tmp_path, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    png = np.asarray(PILImage.open(tmp_path / "RT_output.png").convert("RGBA"))
+    assert png.shape == (h, w, 4)
+    # the same scene through the Python mirror; main.cpp hard-codes PBRT_DRAGON_CAMERA (main.cpp:110)
+    sc = rt.Scene(c3["tri9"], c3["mat_idx"], c3["mats10"], c3["emissive"], skysphere=env)
+    img, _ = sc.render(rt.Camera.PBRT_DRAGON_CAMERA, w, h, spp, bounces)
+    expect = np.clip(img * np.float32(255.0), 0, 255).astype(np.uint8)[::-1]          # write_image_png: *255, clamp, flip (image_io.cpp:165-182)
+    diff = np.abs(png.astype(np.int32) - expect.astype(np.int32))
+    assert (diff <= 1).mean() > 0.995, f"{(diff > 1).sum()} of {diff.size} bytes differ by more than one level"
+    assert png[..., :3].std() > 10, "the frame must not be blank"
+    for name in ("RT_output_denoised_1.png", "RT_output_denoised_0.75.png", "RT_output_denoised_0.5.png"):
+        assert os.path.exists(tmp_path / name)          # main.cpp:118-125 ran to the end
