@@ -53,6 +53,7 @@ def parse_args():
     p.add_argument("--flags", type=int, default=0)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-sample", default="", help="WxHxSPP of the bounded CPU sample (default per workload)")
+    p.add_argument("--verify", action="store_true", help="N>1: rank 0 also renders the frame alone and asserts the gathered frame is bit-identical")
     return p.parse_args()
 
 
@@ -272,6 +273,15 @@ def main():
     for _ in range(args.warmup):
         step()
     barrier()
+    verified = None
+    if args.verify and not primary_only:
+        img = step()
+        if rank == 0:
+            solo = D.make_cuda_gatherer(scene, cam, w, h, spp, bounces, 0, 1, device, integrator=args.integrator, flags=args.flags).frame()
+            verified = bool(torch.equal(img.view(torch.int32), solo.view(torch.int32)))
+            if not verified:
+                raise SystemExit(f"bench.py --verify: the {world}-rank frame differs from the 1-rank frame")
+        barrier()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
@@ -404,7 +414,7 @@ def main():
                        "l2": "256 MiB buffer written between timed iterations (L2 flush)",
                        "bvh": {k: info[k] for k in ("n_inner_nodes", "n_leaves", "max_depth", "has_diag_slabs")},
                        "scene_build_s": build_s, "scene_device_bytes": scene.device_bytes()},
-            "skip_dead_rays": dead,
+            "skip_dead_rays": dead, "verified_equal_to_1_rank": verified,
             "clocks": sampler.result(),
             "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps,
