@@ -149,12 +149,20 @@ def cpu_sample_shape(name, args, w, h, spp):
     return w, h, spp                # c1 / c2 run in full on the CPU
 
 
+def host_threads():
+    """All host cores (torchrun exports OMP_NUM_THREADS=1 to its workers, so the count is passed explicitly)."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
 def run_cpu_sample(oracle_scene, cam17, name, sw, sh, sspp, bounces):
-    """One pass of the reference CPU implementation over the bounded sample; returns seconds."""
+    """One pass of the reference CPU implementation over the bounded sample on all host cores; returns seconds."""
     if name == "c2":
-        _, _, sec = oracle_scene.primary(cam17, sw, sh, mode=0)
+        _, _, sec = oracle_scene.primary(cam17, sw, sh, mode=0, nthreads=host_threads())
         return sec
-    _, sec = oracle_scene.render(cam17, sw, sh, sspp, bounces)
+    _, sec = oracle_scene.render(cam17, sw, sh, sspp, bounces, nthreads=host_threads())
     return sec
 
 
@@ -175,7 +183,7 @@ def port_ray_count(s, cam17, name, sw, sh, sspp, bounces):
     po = PortOracle()
     ps = po.scene_from_arrays(s["tri9"], s["mat_idx"], s["mats10"], s["emissive"])
     ps.set_env(s["env"])
-    _, _, rays = po.render_counted(ps, cam17, sw, sh, sspp, bounces)
+    _, _, rays = po.render_counted(ps, cam17, sw, sh, sspp, bounces, nthreads=host_threads())
     return rays
 
 
@@ -201,7 +209,7 @@ def reference_arm(args):
         "warmup": args.warmup, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic", "spp_per_s": sw * sh * sspp / sec,
         "config": {"workload": desc, "width": w, "height": h, "spp": spp, "max_bounces": bounces, "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": o.max_threads(), "kind": o.kind, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "Mrays/s", "cores": host_threads(), "kind": o.kind, "sample": sample},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -393,7 +401,7 @@ def main():
                 _, sst = scene.render(cam, sw, sh, sspp, bounces, flags=args.flags & ~rt.FLAG_SKIP_DEAD_RAYS)
                 srays = sst["rays"]
             sec = run_cpu_sample(osc, cam17, args.workload, sw, sh, sspp, bounces)
-            cpu_baseline = {"value": srays / sec / 1e6, "unit": "Mrays/s", "cores": o.max_threads(), "kind": o.kind,
+            cpu_baseline = {"value": srays / sec / 1e6, "unit": "Mrays/s", "cores": host_threads(), "kind": o.kind,
                             "sample": f"{sw}x{sh} px x {sspp} spp of the {w}x{h} x {spp} spp frame ({srays} rays, {sec:.2f} s)",
                             "spp_per_s": sw * sh * sspp / sec}
         except Exception as e:          # the baseline is reported context, never a reason to lose the GPU numbers
@@ -419,7 +427,7 @@ def main():
             "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": profile_traffic(args.workload), "bytes_per_ray": bytes_per_ray, "rays_per_launch": rays_per_launch,
+                         "traffic": (profile_traffic(args.workload) / world) if profile_traffic(args.workload) else None, "bytes_per_ray": bytes_per_ray, "rays_per_launch": rays_per_launch,
                          "kernel_ms": kernel_ms, "peak_source": peak_src},
             "cpu_baseline": cpu_baseline,
         }

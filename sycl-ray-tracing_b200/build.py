@@ -21,6 +21,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-fmad=false",
+] + (["-DB200RT_PREFETCH"] if os.environ.get("B200RT_BUILD_PREFETCH") else []) + [
     "-Xcompiler", "-fPIC,-fopenmp,-O3",
     "-ccbin", "/usr/bin/g++",
 ]

@@ -288,7 +288,7 @@ void build_flat_bvh(const float* tri9, int n_tri, const b200rt_bvh_options& opts
 
     Builder builder(prims, order, max_leaf, bins);
     int root = builder.alloc();
-    const int threads = opts.num_threads > 0 ? opts.num_threads : omp_get_max_threads();
+    const int threads = opts.num_threads > 0 ? opts.num_threads : omp_get_num_procs();   // not omp_get_max_threads(): torchrun exports OMP_NUM_THREADS=1
     if (n_tri > 0)
     {
 #pragma omp parallel num_threads(threads)

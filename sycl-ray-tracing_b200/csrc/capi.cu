@@ -378,6 +378,9 @@ int b200rt_scene_create(const float* tri_xyz9, int n_tri, const int* tri_materia
             cdf_host = cdf.data();
         }
         if ((rc = upload(s, cdf_host, (size_t)env_w * env_h, &s->dev.cdf))) break;
+        std::vector<float> row_cdf((size_t)env_h);
+        for (int y = 0; y < env_h; y++) row_cdf[y] = cdf_host[(size_t)y * env_w + env_w - 1];
+        if ((rc = upload(s, row_cdf.data(), (size_t)env_h, &s->dev.row_cdf))) break;
         s->dev.cdf_total = cdf_host[(size_t)env_w * env_h - 1];
         s->dev.n_tri = n_tri; s->dev.n_emissive = n_emissive; s->dev.n_spheres = n_spheres;
         s->dev.env_w = env_w; s->dev.env_h = env_h;

@@ -34,6 +34,7 @@ struct SceneDev
     const SphereDev* spheres;
     const float4* env;         // env_w * env_h RGBA
     const float* cdf;          // running luminance sum, row-major
+    const float* row_cdf;      // cdf[y * env_w + env_w - 1] for every row (the row search's probes, contiguous)
     int n_tri, n_mats, n_emissive, n_spheres;
     int env_w, env_h;
     float cdf_total;

@@ -186,6 +186,15 @@ __device__ __forceinline__ void trav_init(Trav& T, v3 o, v3 d, float tmax, const
     T.sp = 0; T.cur = 0; T.done = false;
 }
 
+// hint: bring the record a reference points at (inner node or first leaf triangle) towards L1 ahead of its use
+__device__ __forceinline__ void prefetch_ref(const SceneDev& S, int ref)
+{
+#ifdef B200RT_PREFETCH
+    const void* p = ref >= 0 ? (const void*)(S.axis + 4 * (size_t)ref) : (const void*)(S.tris + 3 * (size_t)((~ref) >> 4));
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#endif
+}
+
 // pop the next subtree, skipping those that start beyond the current best; T.done when the stack is empty
 __device__ __forceinline__ void trav_pop(Trav& T, TravStack& K)
 {
@@ -257,6 +266,7 @@ __device__ __forceinline__ void trav_inner(const SceneDev& S, Trav& T, TravStack
             K.t[T.sp] = r_first ? tnL : tnR;
             T.sp++;
             T.cur = r_first ? refR : refL;
+            prefetch_ref(S, r_first ? refL : refR);
             return;
         }
         if (hitL) { T.cur = refL; return; }
@@ -489,11 +499,11 @@ __device__ __forceinline__ col env_from_direction(const SceneDev& S, v3 d)
 __device__ __forceinline__ void env_cdf_search(const SceneDev& S, float value, int& xo, int& yo)
 {
     int lower = 0, upper = S.env_h - 1;
-    const int x_index = S.env_w - 1;
     while (lower < upper)
     {
         int y_index = (lower + upper) / 2;
-        if (value < __ldg(S.cdf + y_index * S.env_w + x_index)) upper = y_index; else lower = y_index + 1;
+        // same probes as the reference (cdf[y_index * W + W - 1], :541-547), read from a compact copy of that column
+        if (value < __ldg(S.row_cdf + y_index)) upper = y_index; else lower = y_index + 1;
     }
     const int y = max(min(lower, S.env_h), 0);
     lower = 0; upper = S.env_w - 1;

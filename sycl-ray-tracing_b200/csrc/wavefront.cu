@@ -22,6 +22,9 @@
 
 namespace b200rt {
 
+#ifndef WF_SHADE_MIN_BLOCKS
+#define WF_SHADE_MIN_BLOCKS 4
+#endif
 enum { WF_ALIVE = 1, WF_PENDING = 2, WF_TERMINATED = 4, WF_DONE = 8 };
 
 __device__ __forceinline__ void wf_enqueue(unsigned int* queue, unsigned int* counter, bool pred, unsigned int entry)
@@ -115,7 +118,7 @@ __device__ __forceinline__ v3 wf_sphere_normal(const SceneDev& S, int prim, v3 p
     return V(0.0f, 0.0f, 0.0f);
 }
 
-__global__ void __launch_bounds__(256) wf_shade(SceneDev S, RenderParams P, WfBuffers B, const float4* __restrict__ fb_in_rowmajor,
+__global__ void __launch_bounds__(256, WF_SHADE_MIN_BLOCKS) wf_shade(SceneDev S, RenderParams P, WfBuffers B, const float4* __restrict__ fb_in_rowmajor,
                                                 float4* __restrict__ out_tiles, int parity)
 {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -300,7 +303,7 @@ __device__ __forceinline__ void wf_store_result(const WfBuffers& B, size_t r, in
 
 // default variant: one ray per lane, grid-stride over the queue (the warp waits for its slowest ray)
 template <bool DIAG>
-__global__ void __launch_bounds__(256) wf_trace_simple(SceneDev S, WfBuffers B, int parity)
+__global__ void wf_trace_simple(SceneDev S, WfBuffers B, int parity)
 {
     const unsigned int n_rays = B.counters[3 + parity];
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(B.rays_total, (unsigned long long)n_rays);
@@ -327,7 +330,7 @@ constexpr int kRefillThreshold = 8;
 constexpr int kLeafThreshold = 4;
 
 template <bool DIAG>
-__global__ void __launch_bounds__(256) wf_trace(SceneDev S, WfBuffers B, int parity)
+__global__ void wf_trace(SceneDev S, WfBuffers B, int parity)
 {
     const unsigned int FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -421,14 +424,15 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
     int launches = 0;
     const bool diag = S.has_diag && (P.flags & B200RT_FLAG_DIAG_SLABS);
     const bool simple = !(P.flags & B200RT_FLAG_PERSISTENT_TRACE);
+    static const int tb = []() { const char* e = getenv("B200RT_TRACE_BLOCK"); int v = e ? atoi(e) : 128; return (v == 64 || v == 128 || v == 256) ? v : 128; }();
     int per_sm = 0;
     if (simple)
     {
-        if (diag) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace_simple<true>, 256, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace_simple<false>, 256, 0);
+        if (diag) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace_simple<true>, tb, 0);
+        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace_simple<false>, tb, 0);
     }
-    else if (diag) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace<true>, 256, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace<false>, 256, 0);
+    else if (diag) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace<true>, tb, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace<false>, tb, 0);
     if (per_sm <= 0) per_sm = 1;
     const int trace_grid = g_wf_sm_count * per_sm;
     static const bool timing = getenv("B200RT_WF_TIMING") != nullptr;      // diagnostics: per-kernel times on stderr (serialises the groups)
@@ -488,11 +492,11 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
             if (timing) cudaEventRecord(tev[0], G.stream);
             if (simple)
             {
-                if (diag) wf_trace_simple<true><<<trace_grid, 256, 0, G.stream>>>(S, G.buf, R.parity);
-                else wf_trace_simple<false><<<trace_grid, 256, 0, G.stream>>>(S, G.buf, R.parity);
+                if (diag) wf_trace_simple<true><<<trace_grid, tb, 0, G.stream>>>(S, G.buf, R.parity);
+                else wf_trace_simple<false><<<trace_grid, tb, 0, G.stream>>>(S, G.buf, R.parity);
             }
-            else if (diag) wf_trace<true><<<trace_grid, 256, 0, G.stream>>>(S, G.buf, R.parity);
-            else wf_trace<false><<<trace_grid, 256, 0, G.stream>>>(S, G.buf, R.parity);
+            else if (diag) wf_trace<true><<<trace_grid, tb, 0, G.stream>>>(S, G.buf, R.parity);
+            else wf_trace<false><<<trace_grid, tb, 0, G.stream>>>(S, G.buf, R.parity);
             if (timing) cudaEventRecord(tev[1], G.stream);
             R.parity ^= 1;
             wf_shade<<<R.slot_grid, 256, 0, G.stream>>>(S, R.P, G.buf, fb_in_rowmajor, out_tiles, R.parity);
