@@ -100,8 +100,8 @@ size_t b200rt_scene_device_bytes(const b200rt_scene* scene);
 #define B200RT_FLAG_SKIP_DEAD_RAYS 2     /* skip rays whose result provably cannot change the image */
 #define B200RT_FLAG_DIAG_SLABS 4         /* traverse with all 7 planes (test the 4 diagonal slabs after the 3 axis slabs); default: axis slabs
                                             only — measured faster on every workload, see DESIGN.md */
-#define B200RT_FLAG_PERSISTENT_TRACE 8   /* wavefront: persistent trace kernel with per-lane ray refill + warp phase vote instead of the
-                                            one-ray-per-lane kernel; default off — measured slower end to end, see DESIGN.md */
+#define B200RT_FLAG_SIMPLE_TRACE 8       /* wavefront ablation: one-ray-per-lane grid-stride trace kernel instead of the default persistent
+                                            kernel (per-lane ray refill + warp phase vote), see DESIGN.md */
 
 typedef struct b200rt_render_options
 {

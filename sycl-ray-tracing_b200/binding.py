@@ -11,14 +11,14 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libb200rt.so")
+LIB_PATH = os.environ.get("B200RT_LIB") or os.path.join(HERE, "libb200rt.so")     # B200RT_LIB: development builds with other tunables
 
 INTEGRATOR_MEGAKERNEL = 0
 INTEGRATOR_WAVEFRONT = 1
 FLAG_FB_IS_ZERO = 1
 FLAG_SKIP_DEAD_RAYS = 2
 FLAG_DIAG_SLABS = 4
-FLAG_PERSISTENT_TRACE = 8
+FLAG_SIMPLE_TRACE = 8
 TILE_DIM = 16
 TILE_PIXELS = 256
 

@@ -13,7 +13,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
-LIB = os.path.join(HERE, "libb200rt.so")
+LIB = os.path.join(HERE, os.environ.get("B200RT_BUILD_LIB", "libb200rt.so"))
 SOURCES = ["capi.cu", "kernels.cu", "wavefront.cu", "bvh_build.cpp"]
 HEADERS = ["bvh_build.h", "device_types.h", "kernels.h", "pt_device.cuh", os.path.join("..", "..", "include", "b200rt.h")]
 
@@ -21,7 +21,7 @@ NVCC_FLAGS = [
     "-O3", "-std=c++17", "-lineinfo",
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-fmad=false",
-] + (["-DB200RT_PREFETCH"] if os.environ.get("B200RT_BUILD_PREFETCH") else []) + [
+] + (["-DB200RT_PREFETCH"] if os.environ.get("B200RT_BUILD_PREFETCH") else []) + os.environ.get("B200RT_BUILD_DEFS", "").split() + [
     "-Xcompiler", "-fPIC,-fopenmp,-O3",
     "-ccbin", "/usr/bin/g++",
 ]
@@ -39,8 +39,10 @@ def build(force: bool = False, verbose: bool = False) -> str:
     if not force and not _stale():
         return LIB
     objs = []
+    objdir = os.path.join(CSRC, "_obj_" + os.path.splitext(os.path.basename(LIB))[0])
+    os.makedirs(objdir, exist_ok=True)
     for src in SOURCES:
-        obj = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
+        obj = os.path.join(objdir, os.path.splitext(src)[0] + ".o")
         cmd = ["nvcc"] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]
         if verbose:
             print(" ".join(cmd), flush=True)

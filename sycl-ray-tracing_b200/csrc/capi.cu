@@ -150,7 +150,7 @@ int wavefront_group_count()
     if (n < 0)
     {
         const char* e = getenv("B200RT_WF_GROUPS");
-        n = e ? atoi(e) : 4;
+        n = e ? atoi(e) : 3;
         if (n < 1) n = 1;
         if (n > kMaxWfGroups) n = kMaxWfGroups;
     }

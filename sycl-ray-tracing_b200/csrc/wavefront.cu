@@ -301,7 +301,7 @@ __device__ __forceinline__ void wf_store_result(const WfBuffers& B, size_t r, in
     else B.res_prim[r] = found ? 1 : 0;
 }
 
-// default variant: one ray per lane, grid-stride over the queue (the warp waits for its slowest ray)
+// ablation variant (B200RT_FLAG_SIMPLE_TRACE): one ray per lane, grid-stride over the queue (the warp waits for its slowest ray)
 template <bool DIAG>
 __global__ void wf_trace_simple(SceneDev S, WfBuffers B, int parity)
 {
@@ -322,15 +322,29 @@ __global__ void wf_trace_simple(SceneDev S, WfBuffers B, int parity)
     }
 }
 
-// persistent variant (B200RT_FLAG_PERSISTENT_TRACE): every lane owns one traversal state; whenever at least kRefillThreshold lanes of a warp are idle
+// default variant, persistent: every lane owns one traversal state; whenever at least kRefillThreshold lanes of a warp are idle
 // they are refilled with new rays from the warp's private block of the queue (blocks of kWarpBlock rays are claimed
 // with one atomic), so no lane waits for the slowest ray of its warp (Aila & Laine's persistent threads, per lane).
-constexpr int kWarpBlock = 128;
-constexpr int kRefillThreshold = 8;
-constexpr int kLeafThreshold = 4;
+#ifndef WF_WARP_BLOCK
+#define WF_WARP_BLOCK 64
+#endif
+#ifndef WF_REFILL
+#define WF_REFILL 8
+#endif
+#ifndef WF_LEAF_MIN
+#define WF_LEAF_MIN 4
+#endif
+#ifdef WF_TRACE_MIN_BLOCKS
+#define WF_TRACE_BOUNDS __launch_bounds__(128, WF_TRACE_MIN_BLOCKS)
+#else
+#define WF_TRACE_BOUNDS
+#endif
+constexpr int kWarpBlock = WF_WARP_BLOCK;
+constexpr int kRefillThreshold = WF_REFILL;
+constexpr int kLeafThreshold = WF_LEAF_MIN;
 
 template <bool DIAG>
-__global__ void wf_trace(SceneDev S, WfBuffers B, int parity)
+__global__ void WF_TRACE_BOUNDS wf_trace(SceneDev S, WfBuffers B, int parity)
 {
     const unsigned int FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
@@ -339,6 +353,10 @@ __global__ void wf_trace(SceneDev S, WfBuffers B, int parity)
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(B.rays_total, (unsigned long long)n_rays);
     const int n = B.n_slots;
     const bool spheres = S.n_spheres != 0;
+    // rays claimed per atomic: kWarpBlock when the queue is long, down to one warp's worth when it is short (otherwise a
+    // few warps would serialise a short queue while the rest of the machine idles)
+    const unsigned int total_warps = gridDim.x * (blockDim.x >> 5);
+    const unsigned int warp_block = min((unsigned int)kWarpBlock, max(32u, (n_rays / total_warps) & ~31u));
 
     Trav T;
     TravStack K;
@@ -359,10 +377,10 @@ __global__ void wf_trace(SceneDev S, WfBuffers B, int parity)
                 if (blk_next >= blk_end)
                 {
                     unsigned int b = 0;
-                    if (lane == 0) b = atomicAdd(head, (unsigned int)kWarpBlock);
+                    if (lane == 0) b = atomicAdd(head, warp_block);
                     b = __shfl_sync(FULL, b, 0);
                     if (b >= n_rays) exhausted = true;
-                    else { blk_next = b; blk_end = min(b + (unsigned int)kWarpBlock, n_rays); }
+                    else { blk_next = b; blk_end = min(b + warp_block, n_rays); }
                 }
                 if (blk_next < blk_end)
                 {
@@ -423,7 +441,7 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
     }
     int launches = 0;
     const bool diag = S.has_diag && (P.flags & B200RT_FLAG_DIAG_SLABS);
-    const bool simple = !(P.flags & B200RT_FLAG_PERSISTENT_TRACE);
+    const bool simple = (P.flags & B200RT_FLAG_SIMPLE_TRACE) != 0;
     static const int tb = []() { const char* e = getenv("B200RT_TRACE_BLOCK"); int v = e ? atoi(e) : 128; return (v == 64 || v == 128 || v == 256) ? v : 128; }();
     int per_sm = 0;
     if (simple)

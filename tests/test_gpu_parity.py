@@ -265,8 +265,8 @@ def test_wavefront_c3_small_and_tiles(rt, golden_cameras):
     mega, st_m = sc.render(c3["camera"], w, h, spp, b, integrator=rt.INTEGRATOR_MEGAKERNEL)
     wave, st_w = sc.render(c3["camera"], w, h, spp, b, integrator=rt.INTEGRATOR_WAVEFRONT)
     assert np.array_equal(bits(mega), bits(wave)) and st_m["rays"] == st_w["rays"]
-    pers, st_p = sc.render(c3["camera"], w, h, spp, b, integrator=rt.INTEGRATOR_WAVEFRONT, flags=rt.FLAG_PERSISTENT_TRACE | rt.FLAG_DIAG_SLABS)
-    assert np.array_equal(bits(mega), bits(pers)) and st_p["rays"] == st_m["rays"], "persistent trace kernel + 7-plane traversal"
+    pers, st_p = sc.render(c3["camera"], w, h, spp, b, integrator=rt.INTEGRATOR_WAVEFRONT, flags=rt.FLAG_SIMPLE_TRACE | rt.FLAG_DIAG_SLABS)
+    assert np.array_equal(bits(mega), bits(pers)) and st_p["rays"] == st_m["rays"], "one-ray-per-lane trace kernel + 7-plane traversal"
     skip, st_s = sc.render(c3["camera"], w, h, spp, b, integrator=rt.INTEGRATOR_WAVEFRONT, flags=rt.FLAG_SKIP_DEAD_RAYS)
     assert np.array_equal(bits(mega), bits(skip)) and st_s["rays"] < st_w["rays"], "no emissive material: the BRDF->light rays are dead"
     fb = rt.Image(w, h).pixels
