@@ -236,6 +236,8 @@ def main():
     torch.cuda.set_device(local_rank)
     device = torch.device("cuda", local_rank)
     if world > 1:
+        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+            os.environ["NCCL_DEBUG"] = "WARN"          # NCCL would print its version banner on stdout: stdout carries exactly one JSON line
         dist.init_process_group("nccl", device_id=device)
 
     s, w, h, spp, bounces, desc = load_workload(args.workload, args)

@@ -37,8 +37,7 @@ struct b200rt_scene
     int* d_prim = nullptr; float* d_t = nullptr; size_t prim_cap = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     // wavefront integrator state (allocated on first use, grown on demand)
-    WfGroup wf[kMaxWfGroups]{}; int wf_groups = 0; std::vector<void*> wf_allocs; int wf_cap_tiles = -1; int wf_cap_world = 0, wf_cap_rank = 0;
-    int wf_w = 0, wf_h = 0;
+    WfGroup wf[kMaxWfGroups]{}; int wf_groups = 0; std::vector<void*> wf_allocs; int wf_cap[kMaxWfGroups] = {};   // slots allocated per group
     unsigned int* h_active = nullptr;     // pinned, one word per group
     cudaEvent_t fork_event = nullptr;
 };
@@ -175,26 +174,31 @@ int ensure_wavefront(b200rt_scene* s, const RenderParams& P)
     // group g of rank r == rank r + g * world of a (world * G) partition
     int need[kMaxWfGroups];
     bool fits = s->wf_groups == G;
+    int most = 1;
     for (int g = 0; g < G; g++)
     {
         need[g] = b200rt_tiles_for_rank(P.cam.w, P.cam.h, P.rank + g * P.world, P.world * G) * kTilePixels;
-        if (fits && need[g] > s->wf[g].buf.n_slots && need[g] > 0) fits = false;
+        most = std::max(most, need[g]);
+        if (fits && need[g] > s->wf_cap[g]) fits = false;
     }
-    if (!fits || s->wf_w != P.cam.w || s->wf_h != P.cam.h || s->wf_cap_world != P.world || s->wf_cap_rank != P.rank)
+    if (!fits)
     {
+        // (re)allocate every group at the largest group's size: the buffers are then reusable for any rank/world split of
+        // this frame size or smaller (the arrays are indexed k * n_slots + slot, so only the capacity matters)
         for (void* p : s->wf_allocs) cudaFree(p);
         s->wf_allocs.clear();
         for (int g = 0; g < G; g++)
         {
             WfBuffers& w = s->wf[g].buf;
-            const size_t n = (size_t)std::max(need[g], 1);
+            const size_t n = (size_t)most;
+            s->wf_cap[g] = most;
             CU(wf_alloc(s, &w.rng, n)); CU(wf_alloc(s, &w.sample, n)); CU(wf_alloc(s, &w.bounce, n)); CU(wf_alloc(s, &w.flags, n));
             CU(wf_alloc(s, &w.final_c, n)); CU(wf_alloc(s, &w.sample_c, n)); CU(wf_alloc(s, &w.thr, n)); CU(wf_alloc(s, &w.thr_next, n));
             CU(wf_alloc(s, &w.ray_o, 5 * n)); CU(wf_alloc(s, &w.ray_d, 5 * n)); CU(wf_alloc(s, &w.side_w, 4 * n));
             CU(wf_alloc(s, &w.res_t, 5 * n)); CU(wf_alloc(s, &w.res_prim, 5 * n)); CU(wf_alloc(s, &w.res_tslot, 5 * n));
             CU(wf_alloc(s, &w.queue, 5 * n)); CU(wf_alloc(s, &w.counters, 8)); CU(wf_alloc(s, &w.rays_total, 1));
         }
-        s->wf_groups = G; s->wf_w = P.cam.w; s->wf_h = P.cam.h; s->wf_cap_world = P.world; s->wf_cap_rank = P.rank;
+        s->wf_groups = G;
     }
     for (int g = 0; g < G; g++)
     {

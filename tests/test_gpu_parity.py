@@ -124,17 +124,18 @@ RENDERS = [("cornell", "render_cornell_c1.npz"), ("cornell", "render_cornell_env
 def test_render_matches_reference_framebuffer(rt, golden_scenes, golden_cameras, key, fixture):
     """Same scene, camera, spp, bounces and RNG streams as the compiled reference: the megakernel consumes each pixel's
     xorshift stream in the reference's order, so pixels agree to float rounding except where a libm ulp flips a branch.
-    Tolerance (stated): >= 97 % of pixels within 1e-3 on every channel of the tone-mapped framebuffer, RMSE <= 0.02,
-    mean within 1 %."""
+    Tolerance (stated): >= 99 % of pixels within 1e-3 on every channel of the tone-mapped framebuffer, RMSE <= 5e-3,
+    mean within 0.5 % (measured on B200: 100 % of pixels, max |diff| 6.6e-5, RMSE 4e-7 .. 2e-5)."""
     g = load_golden(fixture)
     w, h, spp, b = int(g["w"]), int(g["h"]), int(g["spp"]), int(g["bounces"])
     sc = make_scene(rt, golden_scenes, key, env=g["env"], env_map_cdf=g["cdf"])
     img, st = sc.render(cam(rt, golden_cameras, CAM_OF[key]), w, h, spp, b)
     s = image_stats(img, g["image"])
     print(key, fixture, s, st)
-    assert s["frac_close"] >= 0.97, s
-    assert s["rmse"] <= 0.02, s
-    assert abs(s["mean_gpu"] - s["mean_ref"]) <= 0.01 * max(s["mean_ref"], 1e-6), s
+    assert s["frac_close"] >= 0.99, s
+    assert s["rmse"] <= 5.0e-3, s
+    assert abs(s["mean_gpu"] - s["mean_ref"]) <= 0.005 * max(s["mean_ref"], 1e-6), s
+    assert s["nan_gpu"] == s["nan_ref"], "the reference's own NaN pixels (quirk 6) must reproduce"
     assert st["rays"] > 0 and st["gpu_launches"] >= 2
 
 
@@ -148,8 +149,8 @@ def test_render_c3_small_matches_reference(rt, golden_cameras):
     img, st = sc.render(c3["camera"], int(g["w"]), int(g["h"]), int(g["spp"]), int(g["bounces"]))
     s = image_stats(img, g["image"])
     print(s, st)
-    assert s["frac_close"] >= 0.95 and s["rmse"] <= 0.03, s
-    assert abs(s["mean_gpu"] - s["mean_ref"]) <= 0.01 * s["mean_ref"], s
+    assert s["frac_close"] >= 0.99 and s["rmse"] <= 5.0e-3, s
+    assert abs(s["mean_gpu"] - s["mean_ref"]) <= 0.005 * s["mean_ref"], s
 
 
 def test_sphere_scene(rt, golden_scenes, golden_cameras):
@@ -166,7 +167,7 @@ def test_sphere_scene(rt, golden_scenes, golden_cameras):
     assert np.array_equal(bits(t), bits(g["t"]))
     img, _ = sc.render(c, int(g["w"]), int(g["h"]), int(g["spp"]), int(g["bounces"]))
     s = image_stats(img, g["image"])
-    assert s["frac_close"] >= 0.97 and s["rmse"] <= 0.02, s
+    assert s["frac_close"] >= 0.99 and s["rmse"] <= 5.0e-3, s
 
 
 # ---- invariants of the product path itself -------------------------------------------------------------------------------------
@@ -253,7 +254,7 @@ def test_wavefront_equals_megakernel_bit_for_bit(rt, golden_scenes, golden_camer
     assert np.array_equal(bits(mega), bits(wave)), f"{(bits(mega) != bits(wave)).sum()} differing words"
     assert st_m["rays"] == st_w["rays"] and st_w["gpu_launches"] > 3
     s = image_stats(wave, g["image"])
-    assert s["frac_close"] >= 0.97 and s["rmse"] <= 0.02, s
+    assert s["frac_close"] >= 0.99 and s["rmse"] <= 5.0e-3, s
 
 
 def test_wavefront_c3_small_and_tiles(rt, golden_cameras):
@@ -276,3 +277,50 @@ def test_wavefront_c3_small_and_tiles(rt, golden_cameras):
     zero, _ = sc.render(c3["camera"], 40, 30, 0, 4, integrator=rt.INTEGRATOR_WAVEFRONT)
     zero_m, _ = sc.render(c3["camera"], 40, 30, 0, 4, integrator=rt.INTEGRATOR_MEGAKERNEL)
     assert np.array_equal(bits(zero), bits(zero_m))
+
+
+# ---- BASELINE full sizes: size-independent properties ------------------------------------------------------------------------------
+def test_c3_full_frame_properties(rt):
+    """Config 3 at its full 1920x1080 frame (1 000 002 triangles, 2048x1024 env map), 2 spp: the oracle would need minutes
+    here, so parity rests on properties: run-to-run determinism, megakernel == wavefront, 2-rank interleaved-tile
+    reassembly == 1-rank frame (all bit for bit), dead-ray elimination changes nothing, no NaN, and the ray budget per
+    sample matches the reference's measured 7.63."""
+    from sycl_ray_tracing_b200 import scenes
+    c3 = scenes.c3_scene()
+    sc = rt.Scene(c3["tri9"], c3["mat_idx"], c3["mats10"], c3["emissive"], skysphere=c3["env"])
+    w, h, spp, b = 1920, 1080, 2, 8
+    a, st = sc.render(c3["camera"], w, h, spp, b)
+    again, _ = sc.render(c3["camera"], w, h, spp, b)
+    assert np.array_equal(bits(a), bits(again))
+    mega, st_m = sc.render(c3["camera"], w, h, spp, b, integrator=rt.INTEGRATOR_MEGAKERNEL)
+    assert np.array_equal(bits(a), bits(mega)) and st["rays"] == st_m["rays"]
+    fb = rt.Image(w, h).pixels
+    for rank in range(2):
+        sc.render(c3["camera"], w, h, spp, b, framebuffer=fb, rank=rank, world=2)
+    assert np.array_equal(bits(a), bits(fb))
+    skip, st_s = sc.render(c3["camera"], w, h, spp, b, flags=rt.FLAG_SKIP_DEAD_RAYS)
+    assert np.array_equal(bits(a), bits(skip)) and st_s["rays"] < st["rays"]
+    assert np.isfinite(a).all() and 0.0 <= a[..., :3].min() and a[..., :3].max() <= 1.0
+    assert st["samples"] == w * h * spp and 7.3 < st["rays"] / st["samples"] < 7.9
+    # the reference's own tone-mapped mean for this scene class is 0.94 (SURVEY Appendix A, 480x270 x 4 spp)
+    assert 0.90 < float(a[..., :3].mean()) < 0.97
+
+
+def test_c3_crop_against_oracle(rt):
+    """Config 3's full scene, a 64x36 crop of the 1920x1080 frame at 4 spp against the live oracle (the crop keeps the
+    frame's pixel coordinates, hence its RNG seeds and camera rays)."""
+    from oracle.oracle import best_oracle
+    from sycl_ray_tracing_b200 import scenes
+    c3 = scenes.c3_scene(sky_w=256, sky_h=128)
+    sc = rt.Scene(c3["tri9"], c3["mat_idx"], c3["mats10"], c3["emissive"], skysphere=c3["env"])
+    w, h, spp, b = 1920, 1080, 4, 8
+    x0, y0, cw, ch = 928, 520, 64, 36
+    full, _ = sc.render(c3["camera"], w, h, spp, b)
+    o = best_oracle()
+    os_ = o.scene_from_arrays(c3["tri9"], c3["mat_idx"], c3["mats10"], c3["emissive"])
+    os_.set_env(c3["env"])
+    ref, _ = os_.render_crop(c3["camera"].as_array17(), w, h, spp, b, x0, y0, x0 + cw, y0 + ch)
+    s = image_stats(full[y0:y0 + ch, x0:x0 + cw], ref)
+    print(s)
+    assert s["frac_close"] >= 0.99 and s["rmse"] <= 5.0e-3, s
+    assert abs(s["mean_gpu"] - s["mean_ref"]) <= 0.005 * s["mean_ref"], s
