@@ -47,10 +47,13 @@ typedef struct b200rt_scene b200rt_scene;  /* device-resident scene: triangles, 
  *   ref >= 0 : index of an inner node; ref <  0 : leaf, ~ref = (first << 4) | count: triangles [first, first + count) of the leaf-ordered stream
  *   tris[j]  : 12 floats {a.xyz, as_float(original index), e1.xyz = b-a, 0, e2.xyz = c-a, 0}   (3 x float4)
  * Leaves hold (first, count) ranges, so the >8-triangle leaf overflow of the reference (bvh.h:226 vs
- * flattened_bvh.h:35) cannot happen. */
+ * flattened_bvh.h:35) cannot happen.
+ * On top of the same binary tree the builder emits the layout the kernels traverse by default: an 8-ary BVH of
+ * 80-byte nodes whose 8 child boxes are quantised to one byte per plane (csrc/bvh_build.h WideNode,
+ * csrc/pt_device.cuh); both layouts index the same leaf-ordered triangle stream. */
 typedef struct b200rt_bvh_options
 {
-    int max_leaf_size;     /* SAH may stop at <= this many triangles per leaf; default 4, max 15 */
+    int max_leaf_size;     /* SAH may stop at <= this many triangles per leaf; default 3, max 15 (the 8-ary BVH needs <= 3) */
     int sah_bins;          /* default 16 */
     int use_diag_slabs;    /* 1: emit the 4 diagonal slabs (7-plane volumes); 0: axis slabs only. default 1 */
     int num_threads;       /* builder threads; 0 = all */
@@ -61,6 +64,8 @@ typedef struct b200rt_bvh_info
     int n_triangles, n_inner_nodes, n_leaves, max_leaf_size, max_depth, has_diag_slabs;
     double build_seconds;
     double sah_cost;
+    int n_wide_nodes;      /* nodes of the 8-ary quantised BVH (0 when max_leaf_size > 3: its leaves hold at most 3 triangles) */
+    int wide_max_depth;
 } b200rt_bvh_info;
 
 void b200rt_bvh_default_options(b200rt_bvh_options* opts);
@@ -102,6 +107,9 @@ size_t b200rt_scene_device_bytes(const b200rt_scene* scene);
                                             only — measured faster on every workload, see DESIGN.md */
 #define B200RT_FLAG_SIMPLE_TRACE 8       /* wavefront ablation: one-ray-per-lane grid-stride trace kernel instead of the default persistent
                                             kernel (per-lane ray refill + warp phase vote), see DESIGN.md */
+
+#define B200RT_FLAG_BVH2 16              /* ablation: traverse the binary two-children-per-record layout instead of the default 8-ary
+                                            quantised BVH (B200RT_FLAG_DIAG_SLABS implies it) */
 
 typedef struct b200rt_render_options
 {

@@ -172,7 +172,7 @@ def compute_env_map_cdf(skysphere: "Image | np.ndarray") -> np.ndarray:
 class BVH:
     """BVH(std::vector<Triangle>*) (bvh.cpp:19-37). Holds the host-side flattened tree built by the C library."""
 
-    def __init__(self, triangles, max_leaf_size: int = 4, use_diag_slabs: bool = True, sah_bins: int = 16, num_threads: int = 0):
+    def __init__(self, triangles, max_leaf_size: int = 3, use_diag_slabs: bool = True, sah_bins: int = 16, num_threads: int = 0):
         L = B.load_library()
         self.triangles = _f32(triangles).reshape(-1, 9)
         opts = B.BvhOptions(max_leaf_size, sah_bins, 1 if use_diag_slabs else 0, num_threads)

@@ -19,6 +19,7 @@ FLAG_FB_IS_ZERO = 1
 FLAG_SKIP_DEAD_RAYS = 2
 FLAG_DIAG_SLABS = 4
 FLAG_SIMPLE_TRACE = 8
+FLAG_BVH2 = 16
 TILE_DIM = 16
 TILE_PIXELS = 256
 
@@ -33,7 +34,8 @@ class BvhOptions(C.Structure):
 
 class BvhInfo(C.Structure):
     _fields_ = [("n_triangles", C.c_int), ("n_inner_nodes", C.c_int), ("n_leaves", C.c_int), ("max_leaf_size", C.c_int),
-                ("max_depth", C.c_int), ("has_diag_slabs", C.c_int), ("build_seconds", C.c_double), ("sah_cost", C.c_double)]
+                ("max_depth", C.c_int), ("has_diag_slabs", C.c_int), ("build_seconds", C.c_double), ("sah_cost", C.c_double),
+                ("n_wide_nodes", C.c_int), ("wide_max_depth", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

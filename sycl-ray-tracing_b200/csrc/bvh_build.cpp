@@ -7,6 +7,7 @@
 #include <cmath>
 #include <cstring>
 #include <limits>
+#include <stdexcept>
 
 #include <omp.h>
 
@@ -180,33 +181,204 @@ struct Slabs
     }
 };
 
+LeafTriangle make_leaf_triangle(const float* tri9, int id)
+{
+    const float* p = tri9 + 9 * (size_t)id;
+    LeafTriangle t;
+    for (int a = 0; a < 3; a++)
+    {
+        t.a[a] = p[a];
+        t.e1[a] = p[3 + a] - p[a];
+        t.e2[a] = p[6 + a] - p[a];
+    }
+    t.prim = id; t.pad1 = 0.0f; t.pad2 = 0.0f;
+    return t;
+}
+
+// the per-axis pad both layouts apply to a child box: the float slab tests must never reject a volume whose triangle the
+// exact Moller-Trumbore test accepts
+inline float box_pad(float lo, float hi, float abs_pad) { return 1e-5f * std::max(std::fabs(lo), std::fabs(hi)) + abs_pad; }
+
+// Collapses the binary tree into the 8-ary quantised layout (WideNode) and fixes the order of the triangle stream:
+// the triangles of a node's leaf children are contiguous, in slot order.
+struct WideBuilder
+{
+    const Builder& b;
+    const float* tri9;
+    FlatBVH& out;
+    float abs_pad;
+    std::vector<int>& leaf_first;       // binary build node (leaf) -> first slot of its triangles
+    int max_depth = 0;
+    bool overflow = false;
+
+    void emit_triangles(const BuildNode& n)
+    {
+        for (int i = 0; i < n.count; i++) out.tris.push_back(make_leaf_triangle(tri9, b.order[n.first + i]));
+    }
+
+    void quantise_axis(WideNode& w, int a, const int* kids, const int* slot_of, int nk)
+    {
+        float lo = kInf, hi = -kInf;
+        float klo[8], khi[8];
+        for (int k = 0; k < nk; k++)
+        {
+            const Box& bx = b.nodes[kids[k]].box;
+            if (!(bx.lo[a] <= bx.hi[a])) { klo[k] = kInf; khi[k] = -kInf; continue; }      // empty leaf
+            const float pad = box_pad(bx.lo[a], bx.hi[a], abs_pad);
+            klo[k] = bx.lo[a] - pad; khi[k] = bx.hi[a] + pad;
+            lo = std::min(lo, klo[k]); hi = std::max(hi, khi[k]);
+        }
+        if (!(lo <= hi)) { lo = 0.0f; hi = 0.0f; }
+        // cell size 2^e: 376 cells span the extent (the grid has 382; the rest absorbs the roundings below), and a cell is
+        // never finer than the float spacing of the coordinates
+        const double extent = (double)hi - (double)lo;
+        int e = -100;
+        if (extent > 0.0) { int ex; std::frexp(extent / 376.0, &ex); e = ex; }      // 2^ex > extent / 376
+        const double amax = std::max(std::fabs((double)lo), std::fabs((double)hi));
+        if (amax > 0.0) e = std::max(e, std::ilogb(amax) - 23);
+        e = std::min(126, std::max(-100, e));
+        const double cell = std::ldexp(1.0, e);
+        const double pd = (double)lo - 128.0 * cell;
+        float pf = (float)pd;
+        if ((double)pf > pd) pf = std::nextafter(pf, -kInf);
+        w.p[a] = pf;
+        w.e[a] = (uint8_t)(e + 127);
+        uint8_t* qlo = a == 0 ? w.lox : (a == 1 ? w.loy : w.loz);
+        uint8_t* qhi = a == 0 ? w.hix : (a == 1 ? w.hiy : w.hiz);
+        for (int s = 0; s < 8; s++) { qlo[s] = 255; qhi[s] = 0; }               // empty slots: inverted, never hit
+        for (int k = 0; k < nk; k++)
+        {
+            if (!(klo[k] <= khi[k])) continue;
+            long vl = (long)std::floor(((double)klo[k] - (double)pf) / cell);
+            long vh = (long)std::ceil(((double)khi[k] - (double)pf) / cell);
+            if (vl < 128 || vh > 510) overflow = true;
+            vl = std::min(510L, std::max(128L, vl)); vh = std::min(510L, std::max(128L, vh));
+            if (vl >= 256) vl &= ~1L;
+            if (vh >= 256 && (vh & 1)) vh++;
+            if (vh > 510) { overflow = true; vh = 510; }
+            qlo[slot_of[k]] = (uint8_t)(vl < 256 ? vl - 128 : vl / 2);
+            qhi[slot_of[k]] = (uint8_t)(vh < 256 ? vh - 128 : vh / 2);
+        }
+    }
+
+    // fills wide node `me` from binary inner node `bn`
+    void emit(int bn, int me, int depth)
+    {
+        max_depth = std::max(max_depth, depth);
+        // 1. greedy collapse: keep opening the inner child with the largest surface area until 8 children
+        int kids[8]; int nk = 0;
+        kids[nk++] = b.nodes[bn].left; kids[nk++] = b.nodes[bn].right;
+        while (nk < 8)
+        {
+            int best = -1; float best_area = -1.0f;
+            for (int k = 0; k < nk; k++)
+            {
+                const BuildNode& c = b.nodes[kids[k]];
+                if (c.left < 0) continue;
+                const float ar = c.box.half_area();
+                if (ar > best_area) { best_area = ar; best = k; }
+            }
+            if (best < 0) break;
+            const BuildNode& c = b.nodes[kids[best]];
+            kids[best] = c.left; kids[nk++] = c.right;
+        }
+        // 2. slots: greedy assignment maximising sum of (child centre - node centre) . octant direction, so that
+        //    slot ^ (7 - ray octant) visits the children front to back
+        const Box& nb = b.nodes[bn].box;
+        float nc[3];
+        for (int a = 0; a < 3; a++) nc[a] = 0.5f * (nb.lo[a] + nb.hi[a]);
+        float cost[8][8];
+        for (int k = 0; k < nk; k++)
+        {
+            const Box& cb = b.nodes[kids[k]].box;
+            float cc[3];
+            for (int a = 0; a < 3; a++) cc[a] = (cb.lo[a] <= cb.hi[a]) ? 0.5f * (cb.lo[a] + cb.hi[a]) - nc[a] : 0.0f;
+            for (int s = 0; s < 8; s++) cost[k][s] = ((s & 1) ? cc[0] : -cc[0]) + ((s & 2) ? cc[1] : -cc[1]) + ((s & 4) ? cc[2] : -cc[2]);
+        }
+        int slot_of[8]; bool slot_used[8] = {}; bool kid_done[8] = {};
+        for (int round = 0; round < nk; round++)
+        {
+            int bk = -1, bs = -1; float bc = -kInf;
+            for (int k = 0; k < nk; k++)
+            {
+                if (kid_done[k]) continue;
+                for (int s = 0; s < 8; s++)
+                    if (!slot_used[s] && cost[k][s] > bc) { bc = cost[k][s]; bk = k; bs = s; }
+            }
+            slot_of[bk] = bs; kid_done[bk] = true; slot_used[bs] = true;
+        }
+        // 3. the node
+        WideNode w;
+        std::memset(&w, 0, sizeof(w));
+        int kid_in_slot[8];
+        for (int s = 0; s < 8; s++) kid_in_slot[s] = -1;
+        for (int k = 0; k < nk; k++) kid_in_slot[slot_of[k]] = k;
+        int n_inner = 0;
+        for (int s = 0; s < 8; s++)
+            if (kid_in_slot[s] >= 0 && b.nodes[kids[kid_in_slot[s]]].left >= 0) { w.imask |= (uint8_t)(1u << s); n_inner++; }
+        w.child_base = (uint32_t)out.wide.size();
+        w.tri_base = (uint32_t)out.tris.size();
+        out.wide.resize(out.wide.size() + (size_t)n_inner);
+        int tri_off = 0;
+        for (int s = 0; s < 8; s++)
+        {
+            const int k = kid_in_slot[s];
+            if (k < 0) continue;
+            const BuildNode& c = b.nodes[kids[k]];
+            if (c.left >= 0) { w.meta[s] = (uint8_t)(0x20 | (24 + s)); continue; }
+            leaf_first[kids[k]] = (int)out.tris.size();
+            emit_triangles(c);
+            w.meta[s] = c.count ? (uint8_t)((((1u << c.count) - 1u) << 5) | (unsigned)tri_off) : 0;
+            tri_off += c.count;
+        }
+        for (int a = 0; a < 3; a++) quantise_axis(w, a, kids, slot_of, nk);
+        out.wide[(size_t)me] = w;
+        int rank = 0;
+        for (int s = 0; s < 8; s++)
+            if (w.imask & (1u << s)) { emit(kids[kid_in_slot[s]], (int)w.child_base + rank, depth + 1); rank++; }
+    }
+
+    // whole tree; a root that is itself a leaf becomes the only child of the root node
+    void run(int root)
+    {
+        out.wide.clear();
+        out.wide.resize(1);
+        const BuildNode& rn = b.nodes[root];
+        if (rn.left >= 0) { emit(root, 0, 1); return; }
+        WideNode w;
+        std::memset(&w, 0, sizeof(w));
+        w.child_base = 1; w.tri_base = (uint32_t)out.tris.size();
+        leaf_first[root] = (int)out.tris.size();
+        emit_triangles(rn);
+        w.meta[0] = rn.count ? (uint8_t)((((1u << rn.count) - 1u) << 5)) : 0;
+        int kids[1] = { root }, slot_of[1] = { 0 };
+        for (int a = 0; a < 3; a++) quantise_axis(w, a, kids, slot_of, 1);
+        out.wide[0] = w;
+        max_depth = 1;
+    }
+};
+
 struct Flattener
 {
     const Builder& b;
     const float* tri9;
     FlatBVH& out;
     float abs_pad;
+    const std::vector<int>* leaf_first = nullptr;     // set when the wide builder already fixed the triangle order
     int max_depth = 0, n_leaves = 0, max_leaf = 0;
     double sah = 0.0;
 
-    // emits the triangles of a leaf, returns its first slot
-    int emit_leaf(const BuildNode& n, Slabs& s)
+    // emits the triangles of a leaf (or finds them where the wide builder put them), returns its first slot
+    int emit_leaf(int bn, Slabs& s)
     {
-        int first = (int)out.tris.size();
+        const BuildNode& n = b.nodes[bn];
+        int first = leaf_first ? (*leaf_first)[bn] : (int)out.tris.size();
         s.reset();
         for (int i = 0; i < n.count; i++)
         {
             int id = b.order[n.first + i];
             const float* p = tri9 + 9 * (size_t)id;
-            LeafTriangle t;
-            for (int a = 0; a < 3; a++)
-            {
-                t.a[a] = p[a];
-                t.e1[a] = p[3 + a] - p[a];
-                t.e2[a] = p[6 + a] - p[a];
-            }
-            t.prim = id; t.pad1 = 0.0f; t.pad2 = 0.0f;
-            out.tris.push_back(t);
+            if (!leaf_first) out.tris.push_back(make_leaf_triangle(tri9, id));
             s.grow_point(p); s.grow_point(p + 3); s.grow_point(p + 6);
         }
         n_leaves++;
@@ -223,7 +395,7 @@ struct Flattener
         for (int a = 0; a < 3; a++)
         {
             // pad: the (float) slab test must never reject a volume whose triangle the exact test accepts
-            float pad = 1e-5f * std::max(std::fabs(s.lo[a]), std::fabs(s.hi[a])) + abs_pad;
+            float pad = box_pad(s.lo[a], s.hi[a], abs_pad);
             lo[a] = s.lo[a] - pad; hi[a] = s.hi[a] + pad;
         }
         for (int k = 0; k < 4; k++)
@@ -241,7 +413,7 @@ struct Flattener
         max_depth = std::max(max_depth, depth);
         if (n.left < 0)
         {
-            int first = emit_leaf(n, s);
+            int first = emit_leaf(bn, s);
             count_out = n.count;
             return leaf_ref(first, n.count);
         }
@@ -264,8 +436,8 @@ struct Flattener
 void build_flat_bvh(const float* tri9, int n_tri, const b200rt_bvh_options& opts, FlatBVH& out)
 {
     auto t0 = std::chrono::high_resolution_clock::now();
-    out.axis.clear(); out.diag.clear(); out.tris.clear();
-    const int max_leaf = std::min(15, std::max(1, opts.max_leaf_size > 0 ? opts.max_leaf_size : 4));
+    out.wide.clear(); out.axis.clear(); out.diag.clear(); out.tris.clear();
+    const int max_leaf = std::min(15, std::max(1, opts.max_leaf_size > 0 ? opts.max_leaf_size : kWideMaxLeaf));
     const int bins = std::min(32, std::max(4, opts.sah_bins > 0 ? opts.sah_bins : 16));
 
     std::vector<Prim> prims((size_t)n_tri);
@@ -297,16 +469,30 @@ void build_flat_bvh(const float* tri9, int n_tri, const b200rt_bvh_options& opts
     }
     else builder.make_leaf(root, 0, 0);
 
-    Flattener fl{ builder, tri9, out, 2e-6f * scene_abs + 1e-30f };
+    const float abs_pad = 2e-6f * scene_abs + 1e-30f;
     out.axis.reserve((size_t)std::max(1, n_tri / 2));
     out.tris.reserve((size_t)n_tri);
+    // the 8-ary layout first (it fixes the triangle order), when the leaves are small enough for its unary counts
+    std::vector<int> leaf_first;
+    int wide_depth = 0;
+    if (max_leaf <= kWideMaxLeaf)
+    {
+        leaf_first.assign((size_t)builder.n_nodes.load(), 0);
+        out.wide.reserve((size_t)std::max(1, n_tri / 4));
+        WideBuilder wb{ builder, tri9, out, abs_pad, leaf_first };
+        wb.run(root);
+        if (wb.overflow) throw std::runtime_error("wide BVH quantisation overflow");
+        wide_depth = wb.max_depth;
+    }
+    Flattener fl{ builder, tri9, out, abs_pad };
+    if (!leaf_first.empty()) fl.leaf_first = &leaf_first;
     Slabs s; int cnt = 0;
     const BuildNode& rn = builder.nodes[root];
     if (rn.left < 0)
     {
         // a single leaf (or an empty scene): wrap it in one inner record whose right child is an empty, unhittable leaf
         out.axis.emplace_back(); out.diag.emplace_back();
-        Slabs ls; int first = fl.emit_leaf(rn, ls);
+        Slabs ls; int first = fl.emit_leaf(root, ls);
         if (rn.count == 0) ls.reset();
         fl.store_child(out.axis[0], out.diag[0], true, ls, leaf_ref(first, rn.count), rn.count);
         Slabs empty; empty.reset();
@@ -337,6 +523,77 @@ void build_flat_bvh(const float* tri9, int n_tri, const b200rt_bvh_options& opts
     out.info.has_diag_slabs = opts.use_diag_slabs ? 1 : 0;
     out.info.build_seconds = std::chrono::duration<double>(t1 - t0).count();
     out.info.sah_cost = sah;
+    out.info.n_wide_nodes = (int)out.wide.size();
+    out.info.wide_max_depth = wide_depth;
+}
+
+// 8-ary layout: every triangle slot referenced exactly once, every decoded child box contains all vertices below it
+// (decoded in double: plane = p + 2^e * v(q), exactly what the device evaluates up to its final roundings)
+static int check_wide_bvh(const FlatBVH& bvh, const float* tri9, int n_tri)
+{
+    struct Bounds { double lo[3], hi[3]; };
+    std::vector<char> seen((size_t)std::max(1, n_tri), 0);
+    int covered = 0, err = 0;
+    // recursive walk returning the exact vertex bounds of a subtree
+    struct Walker
+    {
+        const FlatBVH& bvh; const float* tri9; int n_tri; std::vector<char>& seen; int& covered; int& err;
+        void walk(size_t ni, int depth, Bounds& bd)
+        {
+            for (int a = 0; a < 3; a++) { bd.lo[a] = 1e300; bd.hi[a] = -1e300; }
+            if (err) return;
+            if (depth > kMaxTraversalDepth) { err = 25; return; }
+            if (ni >= bvh.wide.size()) { err = 20; return; }
+            const WideNode w = bvh.wide[ni];
+            int rank = 0;
+            for (int s = 0; s < 8 && !err; s++)
+            {
+                const unsigned m = w.meta[s];
+                const bool inner = (w.imask >> s) & 1;
+                if (!m) { if (inner) err = 21; continue; }
+                Bounds cb;
+                for (int a = 0; a < 3; a++) { cb.lo[a] = 1e300; cb.hi[a] = -1e300; }
+                if (inner)
+                {
+                    if (m != (0x20u | (24u + (unsigned)s))) { err = 21; return; }
+                    walk((size_t)w.child_base + rank, depth + 1, cb);
+                    rank++;
+                }
+                else
+                {
+                    const unsigned unary = m >> 5, off = m & 31u;
+                    const int count = unary == 1 ? 1 : (unary == 3 ? 2 : (unary == 7 ? 3 : -1));
+                    if (count < 0 || off + count > 24) { err = 22; return; }
+                    for (int i = 0; i < count; i++)
+                    {
+                        const size_t slot = (size_t)w.tri_base + off + i;
+                        if (slot >= bvh.tris.size()) { err = 23; return; }
+                        if (seen[slot]++) { err = 23; return; }
+                        covered++;
+                        const float* p = tri9 + 9 * (size_t)bvh.tris[slot].prim;
+                        for (int v = 0; v < 3; v++)
+                            for (int a = 0; a < 3; a++) { cb.lo[a] = std::min(cb.lo[a], (double)p[3 * v + a]); cb.hi[a] = std::max(cb.hi[a], (double)p[3 * v + a]); }
+                    }
+                }
+                if (err) return;
+                const uint8_t* ql[3] = { w.lox, w.loy, w.loz };
+                const uint8_t* qh[3] = { w.hix, w.hiy, w.hiz };
+                for (int a = 0; a < 3; a++)
+                {
+                    const double cell = std::ldexp(1.0, (int)w.e[a] - 127);
+                    const double lo = (double)w.p[a] + cell * wide_grid_value(ql[a][s]);
+                    const double hi = (double)w.p[a] + cell * wide_grid_value(qh[a][s]);
+                    if (cb.lo[a] < lo || cb.hi[a] > hi) { err = 24; return; }
+                    bd.lo[a] = std::min(bd.lo[a], cb.lo[a]); bd.hi[a] = std::max(bd.hi[a], cb.hi[a]);
+                }
+            }
+        }
+    } wk{ bvh, tri9, n_tri, seen, covered, err };
+    Bounds root;
+    wk.walk(0, 1, root);
+    if (err) return err;
+    if (covered != n_tri) return 26;
+    return 0;
 }
 
 int check_flat_bvh(const FlatBVH& bvh, const float* tri9, int n_tri)
@@ -410,6 +667,11 @@ int check_flat_bvh(const FlatBVH& bvh, const float* tri9, int n_tri)
         }
     }
     if (covered != n_tri) return 12;
+    if (!bvh.wide.empty())
+    {
+        const int r = check_wide_bvh(bvh, tri9, n_tri);
+        if (r) return r;
+    }
     return 0;
 }
 

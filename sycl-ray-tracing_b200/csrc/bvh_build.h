@@ -34,8 +34,26 @@ struct alignas(16) LeafTriangle
 };
 static_assert(sizeof(LeafTriangle) == 48, "three float4 per triangle");
 
+// node of the 8-ary quantised BVH (device twin and the plane decoding: csrc/pt_device.cuh, "wide BVH")
+struct alignas(16) WideNode
+{
+    float p[3];                 // frame origin
+    uint8_t e[3];               // per-axis cell size 2^(e - 127)
+    uint8_t imask;              // bit s set: slot s holds an inner child
+    uint32_t child_base;        // node index of the first inner child (inner children are contiguous, in slot order)
+    uint32_t tri_base;          // slot of the first triangle of this node's leaf children (contiguous, in slot order)
+    uint8_t meta[8];            // 0 empty | 0x20 | (24 + slot) inner | (unary count << 5) | offset leaf
+    uint8_t lox[8], loy[8], loz[8], hix[8], hiy[8], hiz[8];   // quantised child boxes, one byte per plane
+};
+static_assert(sizeof(WideNode) == 80, "five float4 per wide node");
+
+// plane byte -> grid value: the float with bits 0x43000000 | q << 16 (128 + q below 128, 2q from 128 on)
+inline int wide_grid_value(int q) { return q < 128 ? 128 + q : 2 * q; }
+constexpr int kWideMaxLeaf = 3;          // a leaf child's triangle count is unary-coded in 3 bits
+
 struct FlatBVH
 {
+    std::vector<WideNode> wide;
     std::vector<AxisNode> axis;
     std::vector<DiagNode> diag;
     std::vector<LeafTriangle> tris;

@@ -253,7 +253,7 @@ const char* b200rt_version(void) { return "b200rt 0.1 (sm_100a)"; }
 void b200rt_bvh_default_options(b200rt_bvh_options* o)
 {
     if (!o) return;
-    o->max_leaf_size = 4; o->sah_bins = 16; o->use_diag_slabs = 1; o->num_threads = 0;
+    o->max_leaf_size = 3; o->sah_bins = 16; o->use_diag_slabs = 1; o->num_threads = 0;
 }
 
 void b200rt_default_render_options(b200rt_render_options* o)
@@ -275,7 +275,7 @@ int b200rt_bvh_build(const float* tri_xyz9, int n_tri, const b200rt_bvh_options*
     if (!b) return fail(B200RT_ERR_ALLOC, "out of host memory");
     try { build_flat_bvh(tri_xyz9, n_tri, o, b->flat); }
     catch (const std::exception& e) { delete b; return fail(B200RT_ERR_ALLOC, "BVH build failed: %s", e.what()); }
-    if (b->flat.info.max_depth > kMaxTraversalDepth) { delete b; return fail(B200RT_ERR_ARG, "BVH depth %d exceeds the traversal stack", b->flat.info.max_depth); }
+    if (b->flat.info.wide_max_depth > kMaxTraversalDepth || b->flat.info.max_depth > kMaxTraversalDepth) { delete b; return fail(B200RT_ERR_ARG, "BVH depth %d exceeds the traversal stack", b->flat.info.max_depth); }
     *out = b;
     return B200RT_OK;
 }
@@ -353,6 +353,9 @@ int b200rt_scene_create(const float* tri_xyz9, int n_tri, const int* tri_materia
     do
     {
         const FlatBVH& f = bvh->flat;
+        if ((rc = upload(s, reinterpret_cast<const float4*>(f.wide.data()), f.wide.size() * 5, &s->dev.wide))) break;
+        s->dev.has_wide = f.wide.empty() ? 0 : 1;
+        s->dev.qmagic = 0x43000000u;
         if ((rc = upload(s, reinterpret_cast<const float4*>(f.axis.data()), f.axis.size() * 4, &s->dev.axis))) break;
         if ((rc = upload(s, reinterpret_cast<const float4*>(f.diag.data()), f.diag.size() * 4, &s->dev.diag))) break;
         if ((rc = upload(s, reinterpret_cast<const float4*>(f.tris.data()), f.tris.size() * 3, &s->dev.tris))) break;

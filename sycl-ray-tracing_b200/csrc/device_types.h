@@ -26,6 +26,7 @@ struct SceneDev
 {
     const float4* axis;        // 4 float4 per inner node (AxisNode)
     const float4* diag;        // 4 float4 per inner node (DiagNode)
+    const float4* wide;        // 5 float4 per node of the 8-ary quantised BVH (WideNode); null when the BVH has none
     const float4* tris;        // 3 float4 per triangle, leaf order (LeafTriangle)
     const int* slot_of_prim;   // original triangle index -> slot in `tris`
     const int* mat_idx;        // per primitive (triangles, then spheres)
@@ -39,6 +40,8 @@ struct SceneDev
     int env_w, env_h;
     float cdf_total;
     int has_diag;
+    int has_wide;
+    unsigned int qmagic;       // 0x43000000 (see B200RT_Q in pt_device.cuh)
     int any_emissive_material; // some material has emission > 0 (else the BRDF->light MIS ray cannot contribute)
 };
 

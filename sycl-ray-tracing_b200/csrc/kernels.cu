@@ -57,7 +57,7 @@ __device__ __forceinline__ bool slot_pixel(const RenderParams& P, unsigned int s
     return ps.inside;
 }
 
-template <bool DIAG>
+template <int TL>
 __global__ void __launch_bounds__(256) k_pathtrace_mega(SceneDev S, RenderParams P, const float4* __restrict__ fb_in_rowmajor,
                                                         float4* __restrict__ out_tiles, unsigned int* work_counter,
                                                         unsigned long long* ray_counter)
@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(256) k_pathtrace_mega(SceneDev S, RenderParams
 
         // (2) the single trace site
         Hit h;
-        const bool found = trace_ray<DIAG>(S, L.ro, L.rd, L.tmax, L.mode, h);
+        const bool found = trace_ray<TL>(S, L.ro, L.rd, L.tmax, L.mode, h);
         rays++;
 
         // (3) consume the result
@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(256) k_pathtrace_mega(SceneDev S, RenderParams
 }
 
 // ---- K1: primary closest hit (parity hook + C2 traversal microbenchmark) -----------------------------------------------
-template <bool DIAG>
+template <int TL>
 __global__ void __launch_bounds__(256) k_primary(SceneDev S, RenderParams P, int sample, int* __restrict__ prim_out, float* __restrict__ t_out)
 {
     const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -204,14 +204,14 @@ __global__ void __launch_bounds__(256) k_primary(SceneDev S, RenderParams P, int
     v3 o, d;
     camera_ray(P.cam, fx, fy, o, d);
     Hit h;
-    const bool found = trace_ray<DIAG>(S, o, d, 0.0f, TRACE_CLOSEST, h);
+    const bool found = trace_ray<TL>(S, o, d, 0.0f, TRACE_CLOSEST, h);
     const size_t idx = (size_t)ps.y * P.cam.w + ps.x;
     prim_out[idx] = found ? h.prim : -1;
     t_out[idx] = found ? h.t : -1.0f;
 }
 
 // ---- ray batches (BVH::intersect / FlattenedBVH::intersect replacement for tests and tools) ------------------------------
-template <bool DIAG>
+template <int TL>
 __global__ void __launch_bounds__(256) k_trace_rays(SceneDev S, const float* __restrict__ rays6, int n, int any_hit,
                                                     int* __restrict__ prim_out, float* __restrict__ t_out, float* __restrict__ extra8)
 {
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(256) k_trace_rays(SceneDev S, const float* __r
     const float* r = rays6 + 6 * (size_t)i;
     const v3 o = V(r[0], r[1], r[2]), d = V(r[3], r[4], r[5]);
     Hit h;
-    const bool found = trace_ray<DIAG>(S, o, d, 0.0f, any_hit ? TRACE_ANY : TRACE_CLOSEST, h);
+    const bool found = trace_ray<TL>(S, o, d, 0.0f, any_hit ? TRACE_ANY : TRACE_CLOSEST, h);
     if (any_hit) { prim_out[i] = found ? 1 : 0; t_out[i] = found ? h.t : -1.0f; return; }
     prim_out[i] = found ? h.prim : -1;
     t_out[i] = found ? h.t : -1.0f;
@@ -273,17 +273,19 @@ cudaError_t launch_megakernel(const SceneDev& S, const RenderParams& P, const fl
 {
     cudaError_t e = cudaMemsetAsync(work_counter, 0, sizeof(unsigned int), stream);
     if (e != cudaSuccess) return e;
-    const bool diag = S.has_diag && (P.flags & B200RT_FLAG_DIAG_SLABS);
+    const int tl = traversal_layout(S, P.flags);
     int per_sm = 0;
-    if (diag) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pathtrace_mega<true>, 256, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pathtrace_mega<false>, 256, 0);
+    if (tl == TL_WIDE) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pathtrace_mega<TL_WIDE>, 256, 0);
+    else if (tl == TL_DIAG) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pathtrace_mega<TL_DIAG>, 256, 0);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pathtrace_mega<TL_AXIS>, 256, 0);
     if (per_sm <= 0) per_sm = 1;
     int grid = sm_count() * per_sm;                        // persistent: a whole number of resident CTAs per SM
     const int needed = P.n_rank_tiles;                     // one CTA's worth of lanes per 16x16 tile at most
     if (grid > needed) grid = needed;
     if (grid <= 0) return cudaSuccess;
-    if (diag) k_pathtrace_mega<true><<<grid, 256, 0, stream>>>(S, P, fb_in_rowmajor, out_tiles, work_counter, ray_counter);
-    else k_pathtrace_mega<false><<<grid, 256, 0, stream>>>(S, P, fb_in_rowmajor, out_tiles, work_counter, ray_counter);
+    if (tl == TL_WIDE) k_pathtrace_mega<TL_WIDE><<<grid, 256, 0, stream>>>(S, P, fb_in_rowmajor, out_tiles, work_counter, ray_counter);
+    else if (tl == TL_DIAG) k_pathtrace_mega<TL_DIAG><<<grid, 256, 0, stream>>>(S, P, fb_in_rowmajor, out_tiles, work_counter, ray_counter);
+    else k_pathtrace_mega<TL_AXIS><<<grid, 256, 0, stream>>>(S, P, fb_in_rowmajor, out_tiles, work_counter, ray_counter);
     return cudaGetLastError();
 }
 
@@ -292,9 +294,10 @@ cudaError_t launch_primary(const SceneDev& S, const RenderParams& P, int sample,
     const int n_warps = P.n_rank_tiles * 8;
     if (n_warps <= 0) return cudaSuccess;
     const int grid = (n_warps * 32 + 255) / 256;
-    const bool diag = S.has_diag && (P.flags & B200RT_FLAG_DIAG_SLABS);
-    if (diag) k_primary<true><<<grid, 256, 0, stream>>>(S, P, sample, prim_out, t_out);
-    else k_primary<false><<<grid, 256, 0, stream>>>(S, P, sample, prim_out, t_out);
+    const int tl = traversal_layout(S, P.flags);
+    if (tl == TL_WIDE) k_primary<TL_WIDE><<<grid, 256, 0, stream>>>(S, P, sample, prim_out, t_out);
+    else if (tl == TL_DIAG) k_primary<TL_DIAG><<<grid, 256, 0, stream>>>(S, P, sample, prim_out, t_out);
+    else k_primary<TL_AXIS><<<grid, 256, 0, stream>>>(S, P, sample, prim_out, t_out);
     return cudaGetLastError();
 }
 
@@ -303,9 +306,10 @@ cudaError_t launch_trace_rays(const SceneDev& S, const float* rays6, int n, int 
 {
     if (n <= 0) return cudaSuccess;
     const int grid = (n + 255) / 256;
-    const bool diag = S.has_diag && (flags & B200RT_FLAG_DIAG_SLABS);
-    if (diag) k_trace_rays<true><<<grid, 256, 0, stream>>>(S, rays6, n, any_hit, prim_out, t_out, extra8);
-    else k_trace_rays<false><<<grid, 256, 0, stream>>>(S, rays6, n, any_hit, prim_out, t_out, extra8);
+    const int tl = traversal_layout(S, flags);
+    if (tl == TL_WIDE) k_trace_rays<TL_WIDE><<<grid, 256, 0, stream>>>(S, rays6, n, any_hit, prim_out, t_out, extra8);
+    else if (tl == TL_DIAG) k_trace_rays<TL_DIAG><<<grid, 256, 0, stream>>>(S, rays6, n, any_hit, prim_out, t_out, extra8);
+    else k_trace_rays<TL_AXIS><<<grid, 256, 0, stream>>>(S, rays6, n, any_hit, prim_out, t_out, extra8);
     return cudaGetLastError();
 }
 

@@ -7,6 +7,13 @@
 
 namespace b200rt {
 
+// which traversal a launch uses: the 8-ary quantised BVH unless the caller asks for the binary layouts (ablations) or the BVH has none
+inline int traversal_layout(const SceneDev& S, int flags)
+{
+    if (S.has_wide && !(flags & (B200RT_FLAG_BVH2 | B200RT_FLAG_DIAG_SLABS))) return 2;   // TL_WIDE
+    return (S.has_diag && (flags & B200RT_FLAG_DIAG_SLABS)) ? 1 : 0;                      // TL_DIAG : TL_AXIS
+}
+
 cudaError_t launch_megakernel(const SceneDev& S, const RenderParams& P, const float4* fb_in_rowmajor, float4* out_tiles,
                               unsigned int* work_counter, unsigned long long* ray_counter, cudaStream_t stream);
 cudaError_t launch_primary(const SceneDev& S, const RenderParams& P, int sample, int* prim_out, float* t_out, cudaStream_t stream);

@@ -302,7 +302,7 @@ __device__ __forceinline__ void wf_store_result(const WfBuffers& B, size_t r, in
 }
 
 // ablation variant (B200RT_FLAG_SIMPLE_TRACE): one ray per lane, grid-stride over the queue (the warp waits for its slowest ray)
-template <bool DIAG>
+template <int TL>
 __global__ void wf_trace_simple(SceneDev S, WfBuffers B, int parity)
 {
     const unsigned int n_rays = B.counters[3 + parity];
@@ -317,7 +317,7 @@ __global__ void wf_trace_simple(SceneDev S, WfBuffers B, int parity)
         const int kind = __float_as_int(rd4.w);
         const int mode = kind == SIDE_SHADOW ? TRACE_SHADOW : (kind == SIDE_CLOSEST_LIGHT ? TRACE_CLOSEST : TRACE_ANY);
         Hit h;
-        const bool found = trace_ray<DIAG>(S, V(ro4.x, ro4.y, ro4.z), V(rd4.x, rd4.y, rd4.z), ro4.w, mode, h);
+        const bool found = trace_ray<TL>(S, V(ro4.x, ro4.y, ro4.z), V(rd4.x, rd4.y, rd4.z), ro4.w, mode, h);
         wf_store_result(B, r, mode, found, h);
     }
 }
@@ -343,9 +343,32 @@ constexpr int kWarpBlock = WF_WARP_BLOCK;
 constexpr int kRefillThreshold = WF_REFILL;
 constexpr int kLeafThreshold = WF_LEAF_MIN;
 
-template <bool DIAG>
+// one interface over the binary and the 8-ary traversal state machines, so the persistent kernel below serves every layout
+template <int TL>
+struct TravOps
+{
+    typedef Trav State;
+    typedef TravStack Stack;
+    static __device__ __forceinline__ void init(State& T, v3 o, v3 d, float tmax, int mode) { trav_init<TL == TL_DIAG>(T, o, d, tmax, mode); }
+    static __device__ __forceinline__ bool at_node(const State& T) { return T.cur >= 0; }
+    static __device__ __forceinline__ void node(const SceneDev& S, State& T, Stack& K) { trav_inner<TL == TL_DIAG>(S, T, K); }
+    static __device__ __forceinline__ void leaf(const SceneDev& S, State& T, Stack& K) { trav_leaf(S, T, K); }
+};
+template <>
+struct TravOps<TL_WIDE>
+{
+    typedef Trav8 State;
+    typedef TravStack8 Stack;
+    static __device__ __forceinline__ void init(State& T, v3 o, v3 d, float tmax, int mode) { trav8_init(T, o, d, tmax, mode); }
+    static __device__ __forceinline__ bool at_node(const State& T) { return trav8_has_node(T); }
+    static __device__ __forceinline__ void node(const SceneDev& S, State& T, Stack& K) { trav8_node(S, T, K); }
+    static __device__ __forceinline__ void leaf(const SceneDev& S, State& T, Stack& K) { trav8_tris(S, T, K); }
+};
+
+template <int TL>
 __global__ void WF_TRACE_BOUNDS wf_trace(SceneDev S, WfBuffers B, int parity)
 {
+    typedef TravOps<TL> Ops;
     const unsigned int FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
     const unsigned int n_rays = B.counters[3 + parity];
@@ -358,8 +381,8 @@ __global__ void WF_TRACE_BOUNDS wf_trace(SceneDev S, WfBuffers B, int parity)
     const unsigned int total_warps = gridDim.x * (blockDim.x >> 5);
     const unsigned int warp_block = min((unsigned int)kWarpBlock, max(32u, (n_rays / total_warps) & ~31u));
 
-    Trav T;
-    TravStack K;
+    typename Ops::State T;
+    typename Ops::Stack K;
     T.done = true;
     bool active = false;
     size_t r = 0;
@@ -393,7 +416,7 @@ __global__ void WF_TRACE_BOUNDS wf_trace(SceneDev S, WfBuffers B, int parity)
                         const float4 ro4 = B.ray_o[r], rd4 = B.ray_d[r];
                         const int kind = __float_as_int(rd4.w);
                         mode = kind == SIDE_SHADOW ? TRACE_SHADOW : (kind == SIDE_CLOSEST_LIGHT ? TRACE_CLOSEST : TRACE_ANY);
-                        trav_init<DIAG>(T, V(ro4.x, ro4.y, ro4.z), V(rd4.x, rd4.y, rd4.z), ro4.w, spheres ? TRACE_CLOSEST : mode);
+                        Ops::init(T, V(ro4.x, ro4.y, ro4.z), V(rd4.x, rd4.y, rd4.z), ro4.w, spheres ? TRACE_CLOSEST : mode);
                         active = true;
                     }
                     blk_next = min(blk_next + (unsigned int)__popc(idle), blk_end);
@@ -403,20 +426,221 @@ __global__ void WF_TRACE_BOUNDS wf_trace(SceneDev S, WfBuffers B, int parity)
         }
         // warp-level phase vote: all lanes that hold an inner node step together, or all lanes that hold a leaf run the
         // exact triangle tests together, whichever is the majority — the two kinds of work never interleave inside a warp
-        const bool has_inner = active && T.cur >= 0, has_leaf = active && T.cur < 0;
+        const bool has_inner = active && Ops::at_node(T), has_leaf = active && !Ops::at_node(T);
         const unsigned int m_inner = __ballot_sync(FULL, has_inner), m_leaf = __ballot_sync(FULL, has_leaf);
         if (!(m_inner | m_leaf))
         {
             if (exhausted) break;
             continue;
         }
-        if (m_inner && __popc(m_leaf) < max(__popc(m_inner), kLeafThreshold)) { if (has_inner) trav_inner<DIAG>(S, T, K); }
-        else if (has_leaf) trav_leaf(S, T, K);
+        if (m_inner && __popc(m_leaf) < max(__popc(m_inner), kLeafThreshold)) { if (has_inner) Ops::node(S, T, K); }
+        else if (has_leaf) Ops::leaf(S, T, K);
         if (active && T.done)
         {
             bool found = T.hit.t > 0.0f;
             if (spheres) found = finish_with_spheres(S, T.o, T.d, T.tmax, mode, T.hit);
             wf_store_result(B, r, mode, found, T.hit);
+            active = false;
+        }
+    }
+}
+
+// ---- default trace kernel for the 8-ary layout: persistent lanes + warp-cooperative triangle tests --------------------------------
+// ncu on the phase-vote kernel above (profiles/r1b_*): the node step ran with 20.7 of 32 lanes, but the exact triangle
+// tests with only 7.3 — few lanes of a warp hold a leaf at the same time, and those that do hold different numbers of
+// triangles — and that phase took 45 % of the stall samples. Here a lane never tests its own triangles. The node step
+// leaves a lane's hit triangles as (owner lane, triangle slot) pairs in a per-warp shared-memory queue and the lane goes
+// straight on with its next node; whenever the queue holds 32 pairs, all 32 lanes test one pair each (ray from the owner's
+// shared-memory record, Moller-Trumbore exactly as triangle.h:16-60) and fold the result into the owner's 64-bit key
+// (t bits << 32 | primitive index) with a shared-memory atomicMin — which is exactly the closest-hit rule of the other
+// kernels (smaller t, ties to the lower original index). Owners pick up their new t_best after each drain. A ray is
+// finished when it has no node work and no pair left in the queue.
+constexpr int kCoopQueue = 160;         // pairs per warp; an append that does not fit drains first
+constexpr int kCoopMaxWarps = 4;         // the kernel is launched with 128-thread CTAs
+constexpr unsigned long long kNoHit = 0xffffffffffffffffull;
+
+struct CoopWarp
+{
+    float4 ro[32], rd[32];              // per lane: origin + tmax, direction + trace mode
+    unsigned long long best[32];        // per lane: (t bits << 32) | primitive index of the best accepted hit
+    unsigned int q[kCoopQueue];         // (owner lane << 27) | triangle slot
+    unsigned int pend[32];
+};
+
+// all 32 lanes: test whole batches of 32 pairs (and the last partial one if `full`), compact the rest to the queue's front,
+// tell every lane whether it still owns a queued pair
+__device__ __forceinline__ void coop_drain(const SceneDev& S, CoopWarp& W, const int lane, unsigned int& qcount, const bool full, bool& pending)
+{
+    unsigned int base = 0;
+    while (qcount - base >= 32u || (full && base < qcount))
+    {
+        const unsigned int nb = min(32u, qcount - base);
+        if ((unsigned int)lane < nb)
+        {
+            const unsigned int e = W.q[base + lane];
+            const unsigned int owner = e >> 27, slot = e & 0x07ffffffu;
+            const float4 ro4 = W.ro[owner], rd4 = W.rd[owner];
+            const float4* tp = S.tris + 3 * (size_t)slot;
+            const float4 va = __ldg(tp), ve1 = __ldg(tp + 1), ve2 = __ldg(tp + 2);
+            float t, u, v;
+            if (tri_test(va, ve1, ve2, V(ro4.x, ro4.y, ro4.z), V(rd4.x, rd4.y, rd4.z), t, u, v))
+            {
+                const int mode = __float_as_int(rd4.w);
+                if (mode != TRACE_SHADOW || t + 1.0e-4f < ro4.w)
+                {
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned int)__float_as_int(va.w);
+                    if (key < W.best[owner]) atomicMin(&W.best[owner], key);
+                }
+            }
+        }
+        base += nb;
+    }
+    __syncwarp();
+    const unsigned int rem = qcount - base;
+    const unsigned int e = (unsigned int)lane < rem ? W.q[base + lane] : 0u;
+    W.pend[lane] = 0u;
+    __syncwarp();
+    if ((unsigned int)lane < rem) { W.q[lane] = e; W.pend[e >> 27] = 1u; }
+    __syncwarp();
+    pending = W.pend[lane] != 0u;
+    qcount = rem;
+}
+
+__global__ void __launch_bounds__(32 * kCoopMaxWarps) wf_trace_coop(SceneDev S, WfBuffers B, int parity)
+{
+    __shared__ CoopWarp s_warps[kCoopMaxWarps];
+    CoopWarp& W = s_warps[threadIdx.x >> 5];
+    const unsigned int FULL = 0xffffffffu;
+    const int lane = threadIdx.x & 31;
+    const unsigned int lanes_below = (1u << lane) - 1u;
+    const unsigned int n_rays = B.counters[3 + parity];
+    unsigned int* head = &B.counters[5 + parity];
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(B.rays_total, (unsigned long long)n_rays);
+    const int n = B.n_slots;
+    const bool spheres = S.n_spheres != 0;
+    const unsigned int total_warps = gridDim.x * (blockDim.x >> 5);
+    const unsigned int warp_block = min((unsigned int)kWarpBlock, max(32u, (n_rays / total_warps) & ~31u));
+
+    Trav8 T;
+    TravStack8 K;
+    T.done = true; T.tg = make_uint2(0u, 0u);
+    bool active = false, pending = false;
+    size_t r = 0;
+    int mode = TRACE_CLOSEST;
+    unsigned int blk_next = 0, blk_end = 0, qcount = 0;       // warp-uniform
+    bool exhausted = false;                                   // warp-uniform
+
+    for (;;)
+    {
+        // (1) refill idle lanes from the warp's private block of the ray queue
+        unsigned int idle = __ballot_sync(FULL, !active);
+        if (idle && !exhausted && (idle == FULL || __popc(idle) >= kRefillThreshold))
+        {
+            if (blk_next >= blk_end)
+            {
+                unsigned int b = 0;
+                if (lane == 0) b = atomicAdd(head, warp_block);
+                b = __shfl_sync(FULL, b, 0);
+                if (b >= n_rays) exhausted = true;
+                else { blk_next = b; blk_end = min(b + warp_block, n_rays); }
+            }
+            if (blk_next < blk_end)
+            {
+                const unsigned int idx = blk_next + __popc(idle & lanes_below);
+                if (!active && idx < blk_end)
+                {
+                    const unsigned int e = B.queue[idx];
+                    const int slot = (int)(e >> 3), k = (int)(e & 7u);
+                    r = (size_t)k * n + slot;
+                    const float4 ro4 = B.ray_o[r], rd4 = B.ray_d[r];
+                    const int kind = __float_as_int(rd4.w);
+                    mode = kind == SIDE_SHADOW ? TRACE_SHADOW : (kind == SIDE_CLOSEST_LIGHT ? TRACE_CLOSEST : TRACE_ANY);
+                    const int tmode = spheres ? TRACE_CLOSEST : mode;
+                    trav8_init(T, V(ro4.x, ro4.y, ro4.z), V(rd4.x, rd4.y, rd4.z), ro4.w, tmode);
+                    W.ro[lane] = ro4;
+                    W.rd[lane] = make_float4(rd4.x, rd4.y, rd4.z, __int_as_float(tmode));
+                    W.best[lane] = kNoHit;
+                    active = true; pending = false;
+                }
+                blk_next = min(blk_next + (unsigned int)__popc(idle), blk_end);
+            }
+            __syncwarp();
+        }
+        const unsigned int m_active = __ballot_sync(FULL, active);
+        if (!m_active)
+        {
+            if (exhausted) break;
+            continue;
+        }
+        // (2) one node step for every lane that has one
+        if (active && !T.done) trav8_node(S, T, K);
+        // (3) hit triangles -> the warp's pair queue (draining first when it would overflow); the lane moves on
+        for (;;)
+        {
+            const unsigned int cnt = (active ? __popc(T.tg.y) : 0u);
+            unsigned int incl = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1)
+            {
+                const unsigned int up = __shfl_up_sync(FULL, incl, o);
+                if (lane >= o) incl += up;
+            }
+            const unsigned int total = __shfl_sync(FULL, incl, 31);
+            if (!total) break;
+            const unsigned int room = kCoopQueue - qcount;
+            unsigned int at = incl - cnt;
+            if (cnt)
+            {
+                unsigned int bits = T.tg.y;
+                while (bits && at < room)
+                {
+                    const int b = __ffs((int)bits) - 1;
+                    bits &= bits - 1u;
+                    W.q[qcount + at] = ((unsigned int)lane << 27) | (T.tg.x + (unsigned int)b);
+                    at++;
+                }
+                T.tg.y = bits;
+                pending = true;
+            }
+            __syncwarp();
+            qcount += min(total, room);
+            if (total <= room) break;
+            coop_drain(S, W, lane, qcount, false, pending);
+        }
+        if (active && !T.done && !(T.ng.y & 0xff000000u)) trav8_pop(T, K);
+        // (4) test queued pairs: whole batches of 32; everything when no lane has node work left or enough lanes wait
+        const unsigned int m_node = __ballot_sync(FULL, active && !T.done);
+        const unsigned int m_wait = __ballot_sync(FULL, active && T.done && pending);
+        const bool full = !m_node || __popc(m_wait) >= kRefillThreshold;
+        if (qcount >= 32u || (full && qcount))
+        {
+            coop_drain(S, W, lane, qcount, full, pending);
+            if (active)
+            {
+                const unsigned long long key = W.best[lane];
+                if (key != kNoHit)
+                {
+                    if (T.mode == TRACE_CLOSEST) T.tbest = __uint_as_float((unsigned int)(key >> 32));
+                    else T.done = true;           // occlusion established; the lane only waits for its queued pairs to leave
+                }
+            }
+        }
+        // (5) finished rays
+        if (active && T.done && !pending)
+        {
+            const unsigned long long key = W.best[lane];
+            Hit h;
+            bool found = key != kNoHit;
+            h.t = found ? __uint_as_float((unsigned int)(key >> 32)) : -1.0f;
+            h.prim = found ? (int)(unsigned int)key : -1;
+            h.slot = (found && T.mode == TRACE_CLOSEST) ? __ldg(S.slot_of_prim + h.prim) : -1;
+            h.u = h.v = -1.0f;
+            if (spheres)
+            {
+                const float4 ro4 = W.ro[lane], rd4 = W.rd[lane];
+                found = finish_with_spheres(S, V(ro4.x, ro4.y, ro4.z), V(rd4.x, rd4.y, rd4.z), ro4.w, mode, h);
+            }
+            wf_store_result(B, r, mode, found, h);
             active = false;
         }
     }
@@ -440,17 +664,18 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
         if (g_wf_sm_count <= 0) g_wf_sm_count = 148;
     }
     int launches = 0;
-    const bool diag = S.has_diag && (P.flags & B200RT_FLAG_DIAG_SLABS);
+    const int tl = traversal_layout(S, P.flags);
     const bool simple = (P.flags & B200RT_FLAG_SIMPLE_TRACE) != 0;
-    static const int tb = []() { const char* e = getenv("B200RT_TRACE_BLOCK"); int v = e ? atoi(e) : 128; return (v == 64 || v == 128 || v == 256) ? v : 128; }();
+    static const int tb_env = []() { const char* e = getenv("B200RT_TRACE_BLOCK"); int v = e ? atoi(e) : 128; return (v == 64 || v == 128 || v == 256) ? v : 128; }();
     int per_sm = 0;
-    if (simple)
-    {
-        if (diag) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace_simple<true>, tb, 0);
-        else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace_simple<false>, tb, 0);
-    }
-    else if (diag) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace<true>, tb, 0);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wf_trace<false>, tb, 0);
+    typedef void (*TraceKernel)(SceneDev, WfBuffers, int);
+    static const TraceKernel kernels[2][3] = { { wf_trace<TL_AXIS>, wf_trace<TL_DIAG>, wf_trace<TL_WIDE> },
+                                               { wf_trace_simple<TL_AXIS>, wf_trace_simple<TL_DIAG>, wf_trace_simple<TL_WIDE> } };
+    static const bool vote_wide = []() { const char* e = getenv("B200RT_WIDE_TRACE"); return e && e[0] == 'v'; }();   // ablation: phase-vote kernel on the 8-ary layout
+    const bool coop = tl == TL_WIDE && !simple && !vote_wide;
+    const TraceKernel trace_kernel = coop ? wf_trace_coop : kernels[simple ? 1 : 0][tl];
+    const int tb = coop ? 32 * kCoopMaxWarps : tb_env;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel, tb, 0);
     if (per_sm <= 0) per_sm = 1;
     const int trace_grid = g_wf_sm_count * per_sm;
     static const bool timing = getenv("B200RT_WF_TIMING") != nullptr;      // diagnostics: per-kernel times on stderr (serialises the groups)
@@ -508,13 +733,7 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
                 continue;
             }
             if (timing) cudaEventRecord(tev[0], G.stream);
-            if (simple)
-            {
-                if (diag) wf_trace_simple<true><<<trace_grid, tb, 0, G.stream>>>(S, G.buf, R.parity);
-                else wf_trace_simple<false><<<trace_grid, tb, 0, G.stream>>>(S, G.buf, R.parity);
-            }
-            else if (diag) wf_trace<true><<<trace_grid, tb, 0, G.stream>>>(S, G.buf, R.parity);
-            else wf_trace<false><<<trace_grid, tb, 0, G.stream>>>(S, G.buf, R.parity);
+            trace_kernel<<<trace_grid, tb, 0, G.stream>>>(S, G.buf, R.parity);
             if (timing) cudaEventRecord(tev[1], G.stream);
             R.parity ^= 1;
             wf_shade<<<R.slot_grid, 256, 0, G.stream>>>(S, R.P, G.buf, fb_in_rowmajor, out_tiles, R.parity);
