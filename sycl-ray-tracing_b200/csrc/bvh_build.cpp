@@ -319,17 +319,15 @@ struct WideBuilder
         w.child_base = (uint32_t)out.wide.size();
         w.tri_base = (uint32_t)out.tris.size();
         out.wide.resize(out.wide.size() + (size_t)n_inner);
-        int tri_off = 0;
         for (int s = 0; s < 8; s++)
         {
             const int k = kid_in_slot[s];
             if (k < 0) continue;
             const BuildNode& c = b.nodes[kids[k]];
-            if (c.left >= 0) { w.meta[s] = (uint8_t)(0x20 | (24 + s)); continue; }
+            if (c.left >= 0) continue;
             leaf_first[kids[k]] = (int)out.tris.size();
             emit_triangles(c);
-            w.meta[s] = c.count ? (uint8_t)((((1u << c.count) - 1u) << 5) | (unsigned)tri_off) : 0;
-            tri_off += c.count;
+            w.valid24 |= ((1u << c.count) - 1u) << (3 * s);
         }
         for (int a = 0; a < 3; a++) quantise_axis(w, a, kids, slot_of, nk);
         out.wide[(size_t)me] = w;
@@ -350,7 +348,7 @@ struct WideBuilder
         w.child_base = 1; w.tri_base = (uint32_t)out.tris.size();
         leaf_first[root] = (int)out.tris.size();
         emit_triangles(rn);
-        w.meta[0] = rn.count ? (uint8_t)((((1u << rn.count) - 1u) << 5)) : 0;
+        w.valid24 = (1u << rn.count) - 1u;
         int kids[1] = { root }, slot_of[1] = { 0 };
         for (int a = 0; a < 3; a++) quantise_axis(w, a, kids, slot_of, 1);
         out.wide[0] = w;
@@ -548,25 +546,26 @@ static int check_wide_bvh(const FlatBVH& bvh, const float* tri9, int n_tri)
             int rank = 0;
             for (int s = 0; s < 8 && !err; s++)
             {
-                const unsigned m = w.meta[s];
+                const unsigned m = (w.valid24 >> (3 * s)) & 7u;
                 const bool inner = (w.imask >> s) & 1;
-                if (!m) { if (inner) err = 21; continue; }
+                if (inner && m) { err = 21; return; }
+                if (!inner && !m) continue;
                 Bounds cb;
                 for (int a = 0; a < 3; a++) { cb.lo[a] = 1e300; cb.hi[a] = -1e300; }
                 if (inner)
                 {
-                    if (m != (0x20u | (24u + (unsigned)s))) { err = 21; return; }
                     walk((size_t)w.child_base + rank, depth + 1, cb);
                     rank++;
                 }
                 else
                 {
-                    const unsigned unary = m >> 5, off = m & 31u;
-                    const int count = unary == 1 ? 1 : (unary == 3 ? 2 : (unary == 7 ? 3 : -1));
-                    if (count < 0 || off + count > 24) { err = 22; return; }
+                    const int count = m == 1 ? 1 : (m == 3 ? 2 : (m == 7 ? 3 : -1));
+                    if (count < 0) { err = 22; return; }
+                    unsigned below = 0;
+                    for (int b2 = 0; b2 < 3 * s; b2++) below += (w.valid24 >> b2) & 1u;
                     for (int i = 0; i < count; i++)
                     {
-                        const size_t slot = (size_t)w.tri_base + off + i;
+                        const size_t slot = (size_t)w.tri_base + below + i;
                         if (slot >= bvh.tris.size()) { err = 23; return; }
                         if (seen[slot]++) { err = 23; return; }
                         covered++;

@@ -42,7 +42,8 @@ struct alignas(16) WideNode
     uint8_t imask;              // bit s set: slot s holds an inner child
     uint32_t child_base;        // node index of the first inner child (inner children are contiguous, in slot order)
     uint32_t tri_base;          // slot of the first triangle of this node's leaf children (contiguous, in slot order)
-    uint8_t meta[8];            // 0 empty | 0x20 | (24 + slot) inner | (unary count << 5) | offset leaf
+    uint32_t valid24;           // bit 3s + i: slot s is a leaf child with a triangle i; triangles are stored compactly in that bit order
+    uint32_t spare;
     uint8_t lox[8], loy[8], loz[8], hix[8], hiy[8], hiz[8];   // quantised child boxes, one byte per plane
 };
 static_assert(sizeof(WideNode) == 80, "five float4 per wide node");

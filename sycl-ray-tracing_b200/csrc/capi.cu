@@ -40,6 +40,8 @@ struct b200rt_scene
     WfGroup wf[kMaxWfGroups]{}; int wf_groups = 0; std::vector<void*> wf_allocs; int wf_cap[kMaxWfGroups] = {};   // slots allocated per group
     unsigned int* h_active = nullptr;     // pinned, one word per group
     cudaEvent_t fork_event = nullptr;
+    void* bvh_window = nullptr; size_t bvh_window_bytes = 0;   // 8-ary nodes + triangles, kept resident in L2 (see pin_bvh_in_l2)
+    bool l2_pinned = false, l2_window_set = false;
 };
 
 namespace {
@@ -209,6 +211,38 @@ int ensure_wavefront(b200rt_scene* s, const RenderParams& P)
     return B200RT_OK;
 }
 
+// Node caching in L2 (opt-in, B200RT_L2_PERSIST=1): a persisting access-policy window over [8-ary nodes | triangles] on every
+// stream that launches traversal kernels keeps what rays fetch resident while the wavefront state streams through L2.
+// Measured on C3 (1080p, 64 spp): 1958 Mrays/s with the window vs 2129 without — the set-aside takes L2 away from the
+// wavefront state that the shade pass re-reads right after the trace pass wrote it, which costs more than the BVH's
+// 78 % -> higher L2 hit rate gains. Off by default for that reason.
+int pin_bvh_in_l2(b200rt_scene* s, cudaStream_t extra)
+{
+    static const bool enabled = []() { const char* e = getenv("B200RT_L2_PERSIST"); return e && atoi(e) != 0; }();
+    if (!enabled || !s->bvh_window_bytes) return B200RT_OK;
+    int max_persist = 0, max_window = 0;
+    cudaDeviceGetAttribute(&max_persist, cudaDevAttrMaxPersistingL2CacheSize, s->device);
+    cudaDeviceGetAttribute(&max_window, cudaDevAttrMaxAccessPolicyWindowSize, s->device);
+    if (max_persist <= 0 || max_window <= 0) return B200RT_OK;
+    if (!s->l2_pinned)
+    {
+        CU(cudaDeviceSetLimit(cudaLimitPersistingL2CacheSize, (size_t)max_persist));
+        s->l2_pinned = true;
+    }
+    cudaStreamAttrValue attr;
+    std::memset(&attr, 0, sizeof(attr));
+    attr.accessPolicyWindow.base_ptr = s->bvh_window;
+    attr.accessPolicyWindow.num_bytes = std::min(s->bvh_window_bytes, (size_t)max_window);
+    // a window larger than the set-aside would thrash itself: pin the fraction that fits
+    attr.accessPolicyWindow.hitRatio = (float)std::min(1.0, (double)max_persist / (double)attr.accessPolicyWindow.num_bytes);
+    attr.accessPolicyWindow.hitProp = cudaAccessPropertyPersisting;
+    attr.accessPolicyWindow.missProp = cudaAccessPropertyStreaming;
+    for (int g = 0; g < kMaxWfGroups; g++)
+        if (s->wf[g].stream) CU(cudaStreamSetAttribute(s->wf[g].stream, cudaStreamAttributeAccessPolicyWindow, &attr));
+    if (extra) CU(cudaStreamSetAttribute(extra, cudaStreamAttributeAccessPolicyWindow, &attr));
+    return B200RT_OK;
+}
+
 // runs the selected integrator for this rank's tiles on `st`; *launches receives the number of kernels launched
 int run_integrator(b200rt_scene* s, const RenderParams& P, int integrator, const float4* fb_in, float4* out_tiles, cudaStream_t st, int* launches)
 {
@@ -216,6 +250,7 @@ int run_integrator(b200rt_scene* s, const RenderParams& P, int integrator, const
     {
         int rc = ensure_wavefront(s, P);
         if (rc) return rc;
+        if (!s->l2_window_set) { if ((rc = pin_bvh_in_l2(s, nullptr))) return rc; s->l2_window_set = true; }
         CU(run_wavefront(s->dev, P, s->wf, s->wf_groups, fb_in, out_tiles, st, s->fork_event, launches));
         CU(wavefront_sum_rays(s->wf, s->wf_groups, s->d_rays, st));
         *launches += 1;
@@ -353,12 +388,32 @@ int b200rt_scene_create(const float* tri_xyz9, int n_tri, const int* tri_materia
     do
     {
         const FlatBVH& f = bvh->flat;
-        if ((rc = upload(s, reinterpret_cast<const float4*>(f.wide.data()), f.wide.size() * 5, &s->dev.wide))) break;
+        {
+            // the 8-ary nodes and the triangle stream share one allocation: one L2 access-policy window covers everything a ray fetches
+            const size_t nw = f.wide.size() * 5, nt = f.tris.size() * 3;
+            std::vector<float4> both(std::max<size_t>(nw + nt, 1));
+            if (nw) std::memcpy(both.data(), f.wide.data(), nw * sizeof(float4));
+            if (nt) std::memcpy(both.data() + nw, f.tris.data(), nt * sizeof(float4));
+            if ((rc = upload(s, both.data(), nw + nt, &s->dev.wide))) break;
+            s->dev.tris = s->dev.wide + nw;
+            s->bvh_window = const_cast<float4*>(s->dev.wide);
+            s->bvh_window_bytes = (nw + nt) * sizeof(float4);
+        }
         s->dev.has_wide = f.wide.empty() ? 0 : 1;
         s->dev.qmagic = 0x43000000u;
+        {
+            std::vector<unsigned char> lut(8 * 256);
+            for (int o = 0; o < 8; o++)
+                for (int m = 0; m < 256; m++)
+                {
+                    unsigned r = 0;
+                    for (int b = 0; b < 8; b++) if (m & (1 << b)) r |= 1u << (b ^ o);
+                    lut[(size_t)o * 256 + m] = (unsigned char)r;
+                }
+            if ((rc = upload(s, lut.data(), lut.size(), &s->dev.oct_lut))) break;
+        }
         if ((rc = upload(s, reinterpret_cast<const float4*>(f.axis.data()), f.axis.size() * 4, &s->dev.axis))) break;
         if ((rc = upload(s, reinterpret_cast<const float4*>(f.diag.data()), f.diag.size() * 4, &s->dev.diag))) break;
-        if ((rc = upload(s, reinterpret_cast<const float4*>(f.tris.data()), f.tris.size() * 3, &s->dev.tris))) break;
         std::vector<int> slot_of_prim((size_t)std::max(n_tri, 1), 0);
         for (size_t i = 0; i < f.tris.size(); i++) slot_of_prim[f.tris[i].prim] = (int)i;
         if ((rc = upload(s, slot_of_prim.data(), (size_t)n_tri, &s->dev.slot_of_prim))) break;

@@ -27,6 +27,7 @@ struct SceneDev
     const float4* axis;        // 4 float4 per inner node (AxisNode)
     const float4* diag;        // 4 float4 per inner node (DiagNode)
     const float4* wide;        // 5 float4 per node of the 8-ary quantised BVH (WideNode); null when the BVH has none
+    const unsigned char* oct_lut; // [8][256]: hit mask by slot -> hit mask in front-to-back order for ray octant class o (bit s -> bit s ^ o)
     const float4* tris;        // 3 float4 per triangle, leaf order (LeafTriangle)
     const int* slot_of_prim;   // original triangle index -> slot in `tris`
     const int* mat_idx;        // per primitive (triangles, then spheres)

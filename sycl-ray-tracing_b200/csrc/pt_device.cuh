@@ -210,7 +210,7 @@ __device__ __forceinline__ void trav_pop(Trav& T, TravStack& K)
 template <bool use_diag>
 __device__ __forceinline__ void trav_inner(const SceneDev& S, Trav& T, TravStack& K)
 {
-    const v3 o = T.o, d = T.d;
+    const v3 o = T.o;
     const RaySlabs& rs = T.rs;
     const float tbest = T.tbest;
     {
@@ -333,20 +333,21 @@ __device__ __forceinline__ bool traverse_tris(const SceneDev& S, v3 o, v3 d, flo
 
 // ---- wide (8-ary, quantised) BVH ----------------------------------------------------------------------------------------------
 // The default acceleration structure on the device: 80-byte nodes (5 x LDG.128) holding 8 children whose boxes are
-// quantised to one byte per plane relative to the node's own frame (Ylitie, Karras, Laine, "Efficient incoherent ray
-// traversal on GPUs through compressed wide BVHs", HPG 2017). One node fetch advances a ray three binary levels, so
-// the dependent fetch chain that bounds a trace pass is ~3.5x shorter than with the binary layout above and a ray
-// touches ~3x fewer bytes. Layout (host twin: WideNode in bvh_build.h):
+// quantised to one byte per plane relative to the node's own frame (after Ylitie, Karras, Laine, "Efficient incoherent ray
+// traversal on GPUs through compressed wide BVHs", HPG 2017, re-encoded for this machine). One node fetch advances a
+// ray three binary levels, so the dependent fetch chain that bounds a trace pass is ~3x shorter than with the binary
+// layout above and a ray touches ~3x fewer bytes. Layout (host twin: WideNode in bvh_build.h):
 //   n0 = { p.x, p.y, p.z, [ex | ey << 8 | ez << 16 | imask << 24] }   frame origin, per-axis cell size 2^(e - 127), inner-child mask by slot
-//   n1 = { child_base, tri_base, meta[0..3], meta[4..7] }               first inner child (node index), first triangle slot, per-child meta
+//   n1 = { child_base, tri_base, valid24, 0 }                           first inner child (node index), first triangle slot, triangle map
 //   n2 = { lox[0..3], lox[4..7], loy[0..3], loy[4..7] }  n3 = { loz, loz, hix, hix }  n4 = { hiy, hiy, hiz, hiz }
 // A plane byte q decodes — with ONE byte permute, no int->float conversion — to the float whose bits are
 // 0x43000000 | q << 16, i.e. v(q) = 128 + q for q < 128 and 2q for q >= 128: a monotone 256-level grid over
 // [128, 510] cells (fine near the frame origin, twice as coarse beyond). plane = p + 2^e * v(q); the builder rounds
 // lo planes down and hi planes up on that grid, so a decoded box always contains the padded float box.
-// meta: 0 = empty slot; inner child: 0x20 | (24 + slot); leaf: (unary triangle count, 1..3 bits) << 5 | offset of its
-// first triangle from tri_base (0..23). Children sit in the slot whose octant (bit a set = positive side of axis a) best
-// matches their position, so that "slot ^ (7 - ray octant)" orders them front to back for any ray direction.
+// valid24: bit 3s + i set = slot s is a leaf child holding a triangle i (at most 3); the node's triangles are stored
+// compactly from tri_base in that bit order, so triangle (s, i) is at tri_base + popc(valid24 below bit 3s + i).
+// Children sit in the slot whose octant (bit a set = positive side of axis a) best matches their position, so that
+// "slot ^ (7 - ray octant)" orders them front to back for any ray direction.
 struct Trav8
 {
     v3 o, d;
@@ -354,9 +355,10 @@ struct Trav8
     int mode, sp;
     bool done;
     float ix, iy, iz;          // clamped reciprocals of the direction
-    unsigned int oct4;         // (7 - ray octant) replicated in the 4 bytes
+    unsigned int oct;          // 7 - ray octant
     uint2 ng;                  // node group: x = index of the first inner child, y = hit bits (24..31, front-to-back order) | imask
-    uint2 tg;                  // triangle group: x = first triangle slot, y = hit bits (0..23)
+    uint2 tg;                  // triangle group: x = first triangle slot of the node, y = hit bits in valid24 positions
+    unsigned int tvalid;       // valid24 of the node the triangle group belongs to
     Hit hit;
 };
 struct TravStack8 { uint2 e[kStackSize]; };
@@ -370,13 +372,13 @@ __device__ __forceinline__ void trav8_init(Trav8& T, v3 o, v3 d, float tmax, con
 {
     T.o = o; T.d = d; T.tmax = tmax; T.mode = mode;
     T.ix = safe_rcp8(d.x); T.iy = safe_rcp8(d.y); T.iz = safe_rcp8(d.z);
-    const unsigned int oct = (T.ix < 0.0f ? 1u : 0u) | (T.iy < 0.0f ? 2u : 0u) | (T.iz < 0.0f ? 4u : 0u);
-    T.oct4 = (7u - oct) * 0x01010101u;
+    T.oct = 7u - ((T.ix < 0.0f ? 1u : 0u) | (T.iy < 0.0f ? 2u : 0u) | (T.iz < 0.0f ? 4u : 0u));
     T.tbest = (mode == TRACE_SHADOW) ? tmax : __int_as_float(0x7f800000);
     T.hit.t = -1.0f; T.hit.prim = -1; T.hit.slot = -1;
     T.sp = 0; T.done = false;
     T.ng = make_uint2(0u, 0x80000000u);      // the root as the only member of a node group with an empty imask
     T.tg = make_uint2(0u, 0u);
+    T.tvalid = 0u;
 }
 
 __device__ __forceinline__ bool trav8_has_node(const Trav8& T) { return T.tg.y == 0u; }     // else: triangles pending
@@ -387,33 +389,34 @@ __device__ __forceinline__ void trav8_pop(Trav8& T, TravStack8& K)
     T.ng = K.e[--T.sp];
 }
 
-// plane byte j of w -> float v(q) (see above)
-// (the constant 0x43000000 comes from the kernel's parameter block, opaque to ptxas, so that it lives in a register and the
-// selector can be the PRMT's immediate; otherwise every PRMT needs an extra move of its selector into a register)
+// slot of the triangle behind bit b of a triangle group
+__device__ __forceinline__ int trav8_tri_slot(const Trav8& T, int b) { return (int)(T.tg.x + __popc(T.tvalid & ((1u << b) - 1u))); }
+
+// plane byte j of w -> float v(q) (see above). The constant 0x43000000 comes from the kernel's parameter block, opaque to
+// ptxas, so that it lives in a register and the selector can be the PRMT's immediate; otherwise every PRMT needs an
+// extra move of its selector into a register.
 #define B200RT_Q(w, j) __uint_as_float(__byte_perm((w), qmagic, 0x7044u | ((j) << 8)))
 
-// tests the 4 children whose plane bytes are in (nx, fx, ny, fy, nz, fz) = near / far planes per axis
-__device__ __forceinline__ unsigned int wide_test4(unsigned int meta4, unsigned int oct4, unsigned int nx, unsigned int fx, unsigned int ny,
-                                                   unsigned int fy, unsigned int nz, unsigned int fz, float sx, float sy, float sz, float ox,
-                                                   float oy, float oz, float tbest, unsigned int qmagic)
-{
-    const unsigned int is_inner4 = (meta4 & (meta4 << 1)) & 0x10101010u;
-    const unsigned int inner_mask4 = (is_inner4 >> 4) * 0xffu;
-    const unsigned int bit_index4 = (meta4 ^ (oct4 & inner_mask4)) & 0x1f1f1f1fu;
-    const unsigned int child_bits4 = (meta4 >> 5) & 0x07070707u;
-    unsigned int hitmask = 0u;
-#pragma unroll
-    for (int j = 0; j < 4; j++)
-    {
-        const float tnx = fmaf(B200RT_Q(nx, j), sx, ox), tfx = fmaf(B200RT_Q(fx, j), sx, ox);
-        const float tny = fmaf(B200RT_Q(ny, j), sy, oy), tfy = fmaf(B200RT_Q(fy, j), sy, oy);
-        const float tnz = fmaf(B200RT_Q(nz, j), sz, oz), tfz = fmaf(B200RT_Q(fz, j), sz, oz);
-        const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));
-        const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tbest));
-        // distance-proportional widening keeps the float slab test conservative (Ize); the boxes themselves are padded by the builder
-        if (tn <= tf * 1.000001f) hitmask |= ((child_bits4 >> (8 * j)) & 0xffu) << ((bit_index4 >> (8 * j)) & 0xffu);
+// Tests child j (bytes j of the near / far plane words) and shifts its miss bit (the sign of t_far * (1 + 2^-20) - t_near:
+// distance-proportional widening keeps the float slab test conservative, Ize; the boxes themselves are padded by the
+// builder) into acc. One funnel shift instead of compare + select + shift + or. A NaN counts as a hit.
+#define B200RT_WIDE_CHILD(j)                                                                                                   \
+    {                                                                                                                          \
+        const float tnx = fmaf(B200RT_Q(nx, j), sx, ox), tfx = fmaf(B200RT_Q(fx, j), sx, ox);                                  \
+        const float tny = fmaf(B200RT_Q(ny, j), sy, oy), tfy = fmaf(B200RT_Q(fy, j), sy, oy);                                  \
+        const float tnz = fmaf(B200RT_Q(nz, j), sz, oz), tfz = fmaf(B200RT_Q(fz, j), sz, oz);                                  \
+        const float tn = fmaxf(fmaxf(tnx, tny), fmaxf(tnz, 0.0f));                                                             \
+        const float tf = fminf(fminf(tfx, tfy), fminf(tfz, tbest));                                                            \
+        acc = __funnelshift_l(__float_as_uint(fmaf(tf, 1.000001f, -tn)), acc, 1);                                              \
     }
-    return hitmask;
+
+// children 3, 2, 1, 0 of one half, in that order (child j of the node ends up at bit j of ~acc)
+__device__ __forceinline__ unsigned int wide_test4(unsigned int acc, unsigned int nx, unsigned int fx, unsigned int ny, unsigned int fy,
+                                                   unsigned int nz, unsigned int fz, float sx, float sy, float sz, float ox, float oy,
+                                                   float oz, float tbest, unsigned int qmagic)
+{
+    B200RT_WIDE_CHILD(3) B200RT_WIDE_CHILD(2) B200RT_WIDE_CHILD(1) B200RT_WIDE_CHILD(0)
+    return acc;
 }
 
 // pre: trav8_has_node(T) and the node group holds at least one hit. Takes the front-most child node of the group, tests
@@ -424,7 +427,7 @@ __device__ __forceinline__ void trav8_node(const SceneDev& S, Trav8& T, TravStac
     const int bit = 31 - __clz((int)hits);
     T.ng.y = hits & ~(1u << bit);
     if (T.ng.y & 0xff000000u) K.e[T.sp++] = T.ng;          // the group's remaining members wait on the stack
-    const unsigned int slot = (unsigned int)(bit - 24) ^ (T.oct4 & 7u);
+    const unsigned int slot = (unsigned int)(bit - 24) ^ T.oct;
     const unsigned int rel = __popc(hits & 0xffu & ~(0xffffffffu << slot));
     const float4* np = S.wide + 5 * (size_t)(T.ng.x + rel);
     const float4 n0 = __ldg(np), n1 = __ldg(np + 1), n2 = __ldg(np + 2), n3 = __ldg(np + 3), n4 = __ldg(np + 4);
@@ -437,16 +440,36 @@ __device__ __forceinline__ void trav8_node(const SceneDev& S, Trav8& T, TravStac
     const unsigned int lox0 = __float_as_uint(n2.x), lox1 = __float_as_uint(n2.y), loy0 = __float_as_uint(n2.z), loy1 = __float_as_uint(n2.w);
     const unsigned int loz0 = __float_as_uint(n3.x), loz1 = __float_as_uint(n3.y), hix0 = __float_as_uint(n3.z), hix1 = __float_as_uint(n3.w);
     const unsigned int hiy0 = __float_as_uint(n4.x), hiy1 = __float_as_uint(n4.y), hiz0 = __float_as_uint(n4.z), hiz1 = __float_as_uint(n4.w);
-    const unsigned int qmagic = S.qmagic;      // 0x43000000, from the parameter block: see B200RT_Q
-    unsigned int hitmask = wide_test4(__float_as_uint(n1.z), T.oct4, bx ? hix0 : lox0, bx ? lox0 : hix0, by ? hiy0 : loy0, by ? loy0 : hiy0,
-                                      bz ? hiz0 : loz0, bz ? loz0 : hiz0, sx, sy, sz, ox, oy, oz, T.tbest, qmagic);
-    hitmask |= wide_test4(__float_as_uint(n1.w), T.oct4, bx ? hix1 : lox1, bx ? lox1 : hix1, by ? hiy1 : loy1, by ? loy1 : hiy1,
-                          bz ? hiz1 : loz1, bz ? loz1 : hiz1, sx, sy, sz, ox, oy, oz, T.tbest, qmagic);
+    const unsigned int qmagic = S.qmagic;
+    unsigned int acc = wide_test4(0u, bx ? hix1 : lox1, bx ? lox1 : hix1, by ? hiy1 : loy1, by ? loy1 : hiy1, bz ? hiz1 : loz1, bz ? loz1 : hiz1,
+                                  sx, sy, sz, ox, oy, oz, T.tbest, qmagic);
+    acc = wide_test4(acc, bx ? hix0 : lox0, bx ? lox0 : hix0, by ? hiy0 : loy0, by ? loy0 : hiy0, bz ? hiz0 : loz0, bz ? loz0 : hiz0,
+                     sx, sy, sz, ox, oy, oz, T.tbest, qmagic);
+    const unsigned int imask = ew >> 24;
+    const unsigned int hit8 = ~acc & 0xffu;                // bit s: the box in slot s is hit (empty slots are filtered by imask / valid24)
+    // inner children: reorder the hit bits front to back for this ray's octant (bit s -> bit s ^ oct) with a 2 KB table
+    const unsigned int inner = __ldg(S.oct_lut + ((T.oct << 8) | (hit8 & imask)));
+    // leaf children: spread bit s to bits 3s..3s+2 (multiplies stand in for shift-or: the operands never overlap) and keep the real triangles
+    unsigned int x = hit8 & ~imask;
+    x = (x * 0x101u) & 0x0000f00fu;
+    x = (x * 0x11u) & 0x000c30c3u;
+    x = (x * 0x5u) & 0x00249249u;
+    T.tvalid = __float_as_uint(n1.z);
     T.ng.x = __float_as_uint(n1.x);
-    T.ng.y = (hitmask & 0xff000000u) | (ew >> 24);
+    T.ng.y = (inner << 24) | imask;
     T.tg.x = __float_as_uint(n1.y);
-    T.tg.y = hitmask & 0x00ffffffu;
-    if (T.tg.y == 0u && !(T.ng.y & 0xff000000u)) trav8_pop(T, K);
+    T.tg.y = (x * 7u) & T.tvalid;
+    if (T.tg.y == 0u && !inner) trav8_pop(T, K);
+#ifdef B200RT_WIDE_PREFETCH
+    // the node this lane fetches next is already known: start bringing its lines towards L1 while the warp does its housekeeping
+    if (!T.done && (T.ng.y & 0xff000000u))
+    {
+        const unsigned int nslot = (unsigned int)(31 - __clz((int)T.ng.y) - 24) ^ T.oct;
+        const char* nx = (const char*)(S.wide + 5 * (size_t)(T.ng.x + __popc(T.ng.y & 0xffu & ~(0xffffffffu << nslot))));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(nx));
+        asm volatile("prefetch.global.L1 [%0];" ::"l"(nx + 64));
+    }
+#endif
 }
 
 // pre: !trav8_has_node(T). Exact triangle tests of the pending triangle group, then the next node group.
@@ -459,7 +482,7 @@ __device__ __forceinline__ void trav8_tris(const SceneDev& S, Trav8& T, TravStac
     {
         const int b = __ffs((int)bits) - 1;
         bits &= bits - 1u;
-        const int slot = (int)T.tg.x + b;
+        const int slot = trav8_tri_slot(T, b);
         const float4* tp = S.tris + 3 * (size_t)slot;
         const float4 va = __ldg(tp), ve1 = __ldg(tp + 1), ve2 = __ldg(tp + 2);
         float t, u, v;

@@ -506,7 +506,10 @@ __device__ __forceinline__ void coop_drain(const SceneDev& S, CoopWarp& W, const
     qcount = rem;
 }
 
-__global__ void __launch_bounds__(32 * kCoopMaxWarps) wf_trace_coop(SceneDev S, WfBuffers B, int parity)
+#ifndef WF_COOP_MIN_BLOCKS
+#define WF_COOP_MIN_BLOCKS 7            // <= 72 registers: 28 warps per SM; 32 (64 registers) measured the same, 16 (117 registers) 20 % slower
+#endif
+__global__ void __launch_bounds__(32 * kCoopMaxWarps, WF_COOP_MIN_BLOCKS) wf_trace_coop(SceneDev S, WfBuffers B, int parity)
 {
     __shared__ CoopWarp s_warps[kCoopMaxWarps];
     CoopWarp& W = s_warps[threadIdx.x >> 5];
@@ -596,7 +599,7 @@ __global__ void __launch_bounds__(32 * kCoopMaxWarps) wf_trace_coop(SceneDev S, 
                 {
                     const int b = __ffs((int)bits) - 1;
                     bits &= bits - 1u;
-                    W.q[qcount + at] = ((unsigned int)lane << 27) | (T.tg.x + (unsigned int)b);
+                    W.q[qcount + at] = ((unsigned int)lane << 27) | (unsigned int)trav8_tri_slot(T, b);
                     at++;
                 }
                 T.tg.y = bits;

@@ -32,9 +32,13 @@ if os.environ.get("C5", "1") == "1":
     prim, t, stp = s5.trace_primary(c5["camera"], 3840, 2160)
     s5.render(c5["camera"], 3840, 2160, 1, 8)
     img, st = s5.render(c5["camera"], 3840, 2160, 4, 8)
+    img2, st2 = s5.render(c5["camera"], 3840, 2160, 4, 8, flags=rt.FLAG_BVH2)          # ablation: binary layout on the HBM-bound scene
+    _, _, stp2 = s5.trace_primary(c5["camera"], 3840, 2160, flags=rt.FLAG_BVH2)
     out["c5"] = dict(triangles=len(c5["tri9"]), gen_s=t_gen, scene_create_s=t_scene, bvh=info, device_bytes=s5.device_bytes(),
                      primary_mrays_s=3840 * 2160 / stp["kernel_ms"] / 1e3, primary_hits=int((prim >= 0).sum()),
                      spp=4, mrays_s=st["rays"] / st["kernel_ms"] / 1e3, mspp_s=st["samples"] / st["kernel_ms"] / 1e3,
+                     bvh2_mrays_s=st2["rays"] / st2["kernel_ms"] / 1e3, bvh2_primary_mrays_s=3840 * 2160 / stp2["kernel_ms"] / 1e3,
+                     bvh2_image_equal=bool(np.array_equal(img.view(np.uint32), img2.view(np.uint32))),
                      rays_per_sample=st["rays"] / st["samples"], kernel_ms=st["kernel_ms"], bytes_per_ray=scenes.algorithmic_bytes_per_ray(len(c5["tri9"])))
     print(out["c5"], flush=True)
 json.dump(out, open(os.path.join(ROOT, "gpurun_out", "configs.json"), "w"), indent=1)
