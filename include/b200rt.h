@@ -94,6 +94,10 @@ int b200rt_scene_create(const float* tri_xyz9, int n_tri,
 void b200rt_scene_destroy(b200rt_scene* scene);
 /* replace the materials in place (C4 roughness/metalness sweeps re-use the resident geometry) */
 int b200rt_scene_set_materials(b200rt_scene* scene, const float* materials10, int n_materials);
+/* Builds the alias table of the environment map's luminance (Vose, in double; 8 bytes per texel on the device) that
+ * B200RT_FLAG_ENV_ALIAS samples from. Replaces Utils::compute_env_map_cdf (utils.cpp:126-142) + env_map_cdf_search
+ * (render_kernel.cpp:532-567) for callers that opt in. */
+int b200rt_scene_build_env_alias(b200rt_scene* scene);
 int b200rt_scene_get_bvh_info(const b200rt_scene* scene, b200rt_bvh_info* out);
 size_t b200rt_scene_device_bytes(const b200rt_scene* scene);
 
@@ -110,6 +114,13 @@ size_t b200rt_scene_device_bytes(const b200rt_scene* scene);
 
 #define B200RT_FLAG_BVH2 16              /* ablation: traverse the binary two-children-per-record layout instead of the default 8-ary
                                             quantised BVH (B200RT_FLAG_DIAG_SLABS implies it) */
+
+#define B200RT_FLAG_BVH8 64              /* b200rt_trace_primary: use the 8-ary layout too (coherent camera rays default to the binary one, which is
+                                            faster for them; every other entry point already defaults to the 8-ary layout) */
+#define B200RT_FLAG_ENV_ALIAS 32         /* sample_environment_map's texel pick (render_kernel.cpp:532-567, two dependent binary searches over the float
+                                            running-sum CDF, ~21 dependent loads) is replaced by one alias-table lookup with the same single RNG draw.
+                                            Same per-texel probability lum/total in exact arithmetic, different draw -> texel map: the image agrees
+                                            with the default statistically, not bit for bit. Needs b200rt_scene_build_env_alias(). */
 
 typedef struct b200rt_render_options
 {

@@ -283,6 +283,10 @@ class Scene:
     def device_bytes(self) -> int:
         return int(B.load_library().b200rt_scene_device_bytes(self._h))
 
+    def build_env_alias(self) -> None:
+        """Alias table of the env map's luminance for FLAG_ENV_ALIAS renders (b200rt_scene_build_env_alias)."""
+        B.check(B.load_library().b200rt_scene_build_env_alias(self._h))
+
     def set_materials(self, materials) -> None:
         self.mats = materials_to_array(materials)
         B.check(B.load_library().b200rt_scene_set_materials(self._h, B.fptr(self.mats), len(self.mats)))

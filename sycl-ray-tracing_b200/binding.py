@@ -20,6 +20,8 @@ FLAG_SKIP_DEAD_RAYS = 2
 FLAG_DIAG_SLABS = 4
 FLAG_SIMPLE_TRACE = 8
 FLAG_BVH2 = 16
+FLAG_ENV_ALIAS = 32
+FLAG_BVH8 = 64
 TILE_DIM = 16
 TILE_PIXELS = 256
 
@@ -56,7 +58,7 @@ class Stats(C.Structure):
 # every symbol include/b200rt.h declares (tests check the library exports each of them)
 EXPORTS = [
     "b200rt_bvh_default_options", "b200rt_bvh_build", "b200rt_bvh_get_info", "b200rt_bvh_get_arrays", "b200rt_bvh_check",
-    "b200rt_bvh_destroy", "b200rt_scene_create", "b200rt_scene_destroy", "b200rt_scene_set_materials",
+    "b200rt_bvh_destroy", "b200rt_scene_create", "b200rt_scene_destroy", "b200rt_scene_set_materials", "b200rt_scene_build_env_alias",
     "b200rt_scene_get_bvh_info", "b200rt_scene_device_bytes", "b200rt_default_render_options", "b200rt_render",
     "b200rt_trace_primary", "b200rt_trace_rays", "b200rt_tiles_for_rank", "b200rt_render_tiles_device",
     "b200rt_untile_device", "b200rt_trace_primary_device", "b200rt_trace_rays_device", "b200rt_last_error", "b200rt_version",
@@ -88,6 +90,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     L.b200rt_scene_destroy.argtypes = [VP]
     L.b200rt_scene_destroy.restype = None
     L.b200rt_scene_set_materials.argtypes = [VP, FP, I]
+    L.b200rt_scene_build_env_alias.argtypes = [VP]
     L.b200rt_scene_get_bvh_info.argtypes = [VP, C.POINTER(BvhInfo)]
     L.b200rt_scene_device_bytes.argtypes = [VP]
     L.b200rt_scene_device_bytes.restype = C.c_size_t

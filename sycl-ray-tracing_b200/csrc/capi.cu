@@ -40,6 +40,8 @@ struct b200rt_scene
     WfGroup wf[kMaxWfGroups]{}; int wf_groups = 0; std::vector<void*> wf_allocs; int wf_cap[kMaxWfGroups] = {};   // slots allocated per group
     unsigned int* h_active = nullptr;     // pinned, one word per group
     cudaEvent_t fork_event = nullptr;
+    std::vector<float> env_lum;           // per-texel luminance as the integrator computes it (image.h:80-85), kept for the alias table
+    float2* d_alias = nullptr; float alias_total = 0.0f;
     void* bvh_window = nullptr; size_t bvh_window_bytes = 0;   // 8-ary nodes + triangles, kept resident in L2 (see pin_bvh_in_l2)
     bool l2_pinned = false, l2_window_set = false;
 };
@@ -246,17 +248,24 @@ int pin_bvh_in_l2(b200rt_scene* s, cudaStream_t extra)
 // runs the selected integrator for this rank's tiles on `st`; *launches receives the number of kernels launched
 int run_integrator(b200rt_scene* s, const RenderParams& P, int integrator, const float4* fb_in, float4* out_tiles, cudaStream_t st, int* launches)
 {
+    SceneDev dev = s->dev;
+    if (P.flags & B200RT_FLAG_ENV_ALIAS)
+    {
+        if (!s->d_alias) return fail(B200RT_ERR_ARG, "B200RT_FLAG_ENV_ALIAS needs b200rt_scene_build_env_alias() first");
+        dev.use_alias = 1;
+        dev.cdf_total = s->alias_total;      // the normalisation the table was built with (the float running sum can be far off)
+    }
     if (integrator == B200RT_INTEGRATOR_WAVEFRONT)
     {
         int rc = ensure_wavefront(s, P);
         if (rc) return rc;
         if (!s->l2_window_set) { if ((rc = pin_bvh_in_l2(s, nullptr))) return rc; s->l2_window_set = true; }
-        CU(run_wavefront(s->dev, P, s->wf, s->wf_groups, fb_in, out_tiles, st, s->fork_event, launches));
+        CU(run_wavefront(dev, P, s->wf, s->wf_groups, fb_in, out_tiles, st, s->fork_event, launches));
         CU(wavefront_sum_rays(s->wf, s->wf_groups, s->d_rays, st));
         *launches += 1;
         return B200RT_OK;
     }
-    CU(launch_megakernel(s->dev, P, fb_in, out_tiles, s->d_work, s->d_rays, st));
+    CU(launch_megakernel(dev, P, fb_in, out_tiles, s->d_work, s->d_rays, st));
     *launches = 1;
     return B200RT_OK;
 }
@@ -439,6 +448,12 @@ int b200rt_scene_create(const float* tri_xyz9, int n_tri, const int* tri_materia
             }
             cdf_host = cdf.data();
         }
+        s->env_lum.resize((size_t)env_w * env_h);
+        for (size_t i = 0; i < s->env_lum.size(); i++)
+        {
+            const float* p = env_rgba + 4 * i;
+            s->env_lum[i] = (float)(0.3086 * p[0] + 0.6094 * p[1] + 0.0820 * p[2]);
+        }
         if ((rc = upload(s, cdf_host, (size_t)env_w * env_h, &s->dev.cdf))) break;
         std::vector<float> row_cdf((size_t)env_h);
         for (int y = 0; y < env_h; y++) row_cdf[y] = cdf_host[(size_t)y * env_w + env_w - 1];
@@ -453,6 +468,51 @@ int b200rt_scene_create(const float* tri_xyz9, int n_tri, const int* tri_materia
     rc = b200rt_scene_set_materials(s, materials10, n_materials);
     if (rc) { b200rt_scene_destroy(s); return rc; }
     *out = s;
+    return B200RT_OK;
+}
+
+int b200rt_scene_build_env_alias(b200rt_scene* s)
+{
+    if (!s) return fail(B200RT_ERR_ARG, "NULL scene");
+    if (s->d_alias) return B200RT_OK;
+    CU(cudaSetDevice(s->device));
+    const size_t n = s->env_lum.size();
+    if (!n) return fail(B200RT_ERR_ARG, "scene has no environment map");
+    // Vose's alias method in double: texel i is accepted with probability q[i], otherwise its alias is taken
+    double total = 0.0;
+    for (float l : s->env_lum) total += l > 0.0f ? (double)l : 0.0;
+    if (!(total > 0.0)) return fail(B200RT_ERR_ARG, "environment map has no luminance to sample");
+    std::vector<double> q(n);
+    std::vector<unsigned int> alias(n), small, large;
+    small.reserve(n); large.reserve(n);
+    for (size_t i = 0; i < n; i++)
+    {
+        q[i] = (s->env_lum[i] > 0.0f ? (double)s->env_lum[i] : 0.0) / total * (double)n;
+        alias[i] = (unsigned int)i;
+        (q[i] < 1.0 ? small : large).push_back((unsigned int)i);
+    }
+    while (!small.empty() && !large.empty())
+    {
+        const unsigned int lo = small.back(), hi = large.back();
+        small.pop_back();
+        alias[lo] = hi;
+        q[hi] = (q[hi] + q[lo]) - 1.0;
+        if (q[hi] < 1.0) { large.pop_back(); small.push_back(hi); }
+    }
+    for (unsigned int i : large) q[i] = 1.0;
+    for (unsigned int i : small) q[i] = 1.0;          // numerical leftovers
+    std::vector<float2> table(n);
+    for (size_t i = 0; i < n; i++)
+    {
+        table[i].x = (float)q[i];
+        int a = (int)alias[i];
+        std::memcpy(&table[i].y, &a, sizeof(int));
+    }
+    CU(cudaMalloc(&s->d_alias, n * sizeof(float2)));
+    s->bytes += n * sizeof(float2);
+    CU(cudaMemcpy(s->d_alias, table.data(), n * sizeof(float2), cudaMemcpyHostToDevice));
+    s->alias_total = (float)total;
+    s->dev.env_alias = s->d_alias;
     return B200RT_OK;
 }
 
@@ -482,6 +542,7 @@ void b200rt_scene_destroy(b200rt_scene* s)
     cudaSetDevice(s->device);
     for (void* p : s->allocs) cudaFree(p);
     if (s->d_mats) cudaFree(s->d_mats);
+    if (s->d_alias) cudaFree(s->d_alias);
     if (s->d_work) cudaFree(s->d_work);
     if (s->d_rays) cudaFree(s->d_rays);
     if (s->d_tiles) cudaFree(s->d_tiles);

@@ -36,12 +36,14 @@ struct SceneDev
     const SphereDev* spheres;
     const float4* env;         // env_w * env_h RGBA
     const float* cdf;          // running luminance sum, row-major
+    const float2* env_alias;   // per texel {acceptance probability, as_float(alias texel)}; null until b200rt_scene_build_env_alias
     const float* row_cdf;      // cdf[y * env_w + env_w - 1] for every row (the row search's probes, contiguous)
     int n_tri, n_mats, n_emissive, n_spheres;
     int env_w, env_h;
     float cdf_total;
     int has_diag;
     int has_wide;
+    int use_alias;             // this launch samples the env map through env_alias (B200RT_FLAG_ENV_ALIAS)
     unsigned int qmagic;       // 0x43000000 (see B200RT_Q in pt_device.cuh)
     int any_emissive_material; // some material has emission > 0 (else the BRDF->light MIS ray cannot contribute)
 };

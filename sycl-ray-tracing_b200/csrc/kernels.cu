@@ -294,7 +294,7 @@ cudaError_t launch_primary(const SceneDev& S, const RenderParams& P, int sample,
     const int n_warps = P.n_rank_tiles * 8;
     if (n_warps <= 0) return cudaSuccess;
     const int grid = (n_warps * 32 + 255) / 256;
-    const int tl = traversal_layout(S, P.flags);
+    const int tl = traversal_layout(S, P.flags, true);
     if (tl == TL_WIDE) k_primary<TL_WIDE><<<grid, 256, 0, stream>>>(S, P, sample, prim_out, t_out);
     else if (tl == TL_DIAG) k_primary<TL_DIAG><<<grid, 256, 0, stream>>>(S, P, sample, prim_out, t_out);
     else k_primary<TL_AXIS><<<grid, 256, 0, stream>>>(S, P, sample, prim_out, t_out);

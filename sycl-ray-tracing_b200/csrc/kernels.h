@@ -7,10 +7,14 @@
 
 namespace b200rt {
 
-// which traversal a launch uses: the 8-ary quantised BVH unless the caller asks for the binary layouts (ablations) or the BVH has none
-inline int traversal_layout(const SceneDev& S, int flags)
+// Which traversal a launch uses. Incoherent rays (the integrators, ray batches) default to the 8-ary quantised BVH: fewer
+// dependent fetches and bytes per ray. Coherent camera rays (k_primary) default to the binary layout: its exact
+// near-first order with per-entry distance culling does less work per ray when a whole warp walks the same nodes
+// (C2: 5.9 vs 3.8 Grays/s, C5 primary: 2.0 vs 1.1 Grays/s). B200RT_FLAG_BVH2 / B200RT_FLAG_BVH8 force one or the other.
+inline int traversal_layout(const SceneDev& S, int flags, bool coherent = false)
 {
-    if (S.has_wide && !(flags & (B200RT_FLAG_BVH2 | B200RT_FLAG_DIAG_SLABS))) return 2;   // TL_WIDE
+    const bool binary = (flags & (B200RT_FLAG_BVH2 | B200RT_FLAG_DIAG_SLABS)) || (coherent && !(flags & B200RT_FLAG_BVH8));
+    if (S.has_wide && !binary) return 2;                                                  // TL_WIDE
     return (S.has_diag && (flags & B200RT_FLAG_DIAG_SLABS)) ? 1 : 0;                      // TL_DIAG : TL_AXIS
 }
 

@@ -809,7 +809,17 @@ __device__ __forceinline__ void side_env_sample(const SceneDev& S, const Surface
     r.kind = SIDE_NONE;
     const float total = S.cdf_total;
     int x, y;
-    env_cdf_search(S, xs_float(rng) * total, x, y);
+    if (S.use_alias)
+    {
+        // the same single draw, taken as its 32 raw bits: texel = floor(r * N / 2^32), the low word of the product is the coin
+        const unsigned int n_texels = (unsigned int)(S.env_w * S.env_h);
+        const unsigned long long m = (unsigned long long)xs_next(rng) * n_texels;
+        unsigned int i = (unsigned int)(m >> 32);
+        const float2 a = __ldg(S.env_alias + i);
+        if (!((float)(unsigned int)m * 2.3283064365386962890625e-10f < a.x)) i = (unsigned int)__float_as_int(a.y);
+        y = (int)(i / (unsigned int)S.env_w); x = (int)(i - (unsigned int)y * (unsigned int)S.env_w);
+    }
+    else env_cdf_search(S, xs_float(rng) * total, x, y);
     const float u = (float)x / (float)S.env_w;
     const float v = (float)y / (float)S.env_h;
     const float phi = (float)((double)(u * 2.0f) * B200RT_PI_D);             // double in the reference (:578-579)

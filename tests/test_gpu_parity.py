@@ -70,6 +70,9 @@ def test_primary_bit_exact_bundled(rt, golden_scenes, golden_cameras, key):
     # 7-plane and 3-plane traversals must agree exactly
     prim2, t2, _ = sc.trace_primary(cam(rt, golden_cameras, CAM_OF[key]), int(g["w"]), int(g["h"]), flags=rt.FLAG_DIAG_SLABS)
     assert np.array_equal(prim, prim2) and np.array_equal(bits(t), bits(t2))
+    # ... and so must the 8-ary quantised layout (the integrators' default)
+    prim8, t8, _ = sc.trace_primary(cam(rt, golden_cameras, CAM_OF[key]), int(g["w"]), int(g["h"]), flags=rt.FLAG_BVH8)
+    assert np.array_equal(prim, prim8) and np.array_equal(bits(t), bits(t8))
 
 
 def test_primary_bit_exact_c2_small(rt, golden_cameras):
@@ -183,6 +186,41 @@ def test_flags_do_not_change_the_image(rt, golden_scenes, golden_cameras):
     skip, st1 = sc.render(c, 96, 80, 4, 5, flags=rt.FLAG_SKIP_DEAD_RAYS)
     assert np.array_equal(bits(base), bits(skip))
     assert st1["rays"] == st0["rays"], "cornell has emissive materials: nothing is dead"
+    # every traversal layout / trace kernel finds the same exact closest hits -> the same image and the same ray count
+    for name, flags in (("binary BVH", rt.FLAG_BVH2), ("8-ary BVH, one ray per lane", rt.FLAG_SIMPLE_TRACE),
+                        ("binary BVH, one ray per lane", rt.FLAG_BVH2 | rt.FLAG_SIMPLE_TRACE)):
+        img, st = sc.render(c, 96, 80, 4, 5, flags=flags)
+        assert np.array_equal(bits(base), bits(img)), name
+        assert st["rays"] == st0["rays"], name
+    for name, flags in (("binary", rt.FLAG_BVH2), ("8-ary", 0)):
+        mega, stm = sc.render(c, 96, 80, 4, 5, integrator=rt.INTEGRATOR_MEGAKERNEL, flags=flags)
+        assert np.array_equal(bits(base), bits(mega)) and stm["rays"] == st0["rays"], name
+
+
+def test_env_alias_sampling_is_statistically_equal(rt, golden_scenes, golden_cameras):
+    """B200RT_FLAG_ENV_ALIAS changes the draw -> texel map of the env-map light sample, not its distribution: against a
+    converged default render, the alias render's error must be the default render's own Monte-Carlo error (same spp),
+    and the two 16 spp image means must agree. Stated tolerance: RMSE ratio <= 1.25, relative mean difference <= 1 %."""
+    g = load_golden("render_cornell_env.npz")          # cornell + a random env map: float CDF accurate, so both estimators are unbiased
+    sc = make_scene(rt, golden_scenes, "cornell", env=g["env"])
+    c = cam(rt, golden_cameras, "cornell")
+    with pytest.raises(rt.B200RTError):
+        sc.render(c, 32, 32, 1, 2, flags=rt.FLAG_ENV_ALIAS)       # table not built yet: must fail loudly
+    sc.build_env_alias()
+    w, h = 96, 80
+    ref, _ = sc.render(c, w, h, 1024, 4)
+    a, st_a = sc.render(c, w, h, 16, 4)
+    b, st_b = sc.render(c, w, h, 16, 4, flags=rt.FLAG_ENV_ALIAS)
+    assert not np.array_equal(bits(a), bits(b)), "the alias table must actually be used"
+    m, _ = sc.render(c, w, h, 16, 4, flags=rt.FLAG_ENV_ALIAS, integrator=rt.INTEGRATOR_MEGAKERNEL)
+    assert np.array_equal(bits(b), bits(m)), "both integrators sample the same table with the same draws"
+    r64 = ref[..., :3].astype(np.float64)
+    ea = np.sqrt(((a[..., :3] - r64) ** 2).mean()); eb = np.sqrt(((b[..., :3] - r64) ** 2).mean())
+    assert eb <= 1.25 * ea, (ea, eb)
+    # the framebuffer holds tone-mapped (concave) values, so a 16 spp mean sits below the converged one for either sampler:
+    # compare the two 16 spp means with each other
+    assert abs(float(b[..., :3].mean()) - float(a[..., :3].mean())) <= 0.01 * float(a[..., :3].mean()), (a[..., :3].mean(), b[..., :3].mean(), r64.mean())
+    assert abs(st_b["rays"] - st_a["rays"]) <= 0.02 * st_a["rays"]
 
 
 def test_interleaved_tiles_reassemble_bit_exact(rt, golden_scenes, golden_cameras):
