@@ -172,12 +172,17 @@ def compute_env_map_cdf(skysphere: "Image | np.ndarray") -> np.ndarray:
 class BVH:
     """BVH(std::vector<Triangle>*) (bvh.cpp:19-37). Holds the host-side flattened tree built by the C library."""
 
-    def __init__(self, triangles, max_leaf_size: int = 3, use_diag_slabs: bool = True, sah_bins: int = 16, num_threads: int = 0):
+    def __init__(self, triangles, max_leaf_size: int = 3, use_diag_slabs: bool = True, sah_bins: int = 16, num_threads: int = 0,
+                 on_device: bool = False, device: int = -1):
+        """on_device=True: linear BVH built by the GPU (b200rt_bvh_build_device) instead of the host's binned-SAH builder."""
         L = B.load_library()
         self.triangles = _f32(triangles).reshape(-1, 9)
-        opts = B.BvhOptions(max_leaf_size, sah_bins, 1 if use_diag_slabs else 0, num_threads)
         h = C.c_void_p()
-        B.check(L.b200rt_bvh_build(B.fptr(self.triangles), len(self.triangles), C.byref(opts), C.byref(h)))
+        if on_device:
+            B.check(L.b200rt_bvh_build_device(B.fptr(self.triangles), len(self.triangles), device, C.byref(h)))
+        else:
+            opts = B.BvhOptions(max_leaf_size, sah_bins, 1 if use_diag_slabs else 0, num_threads)
+            B.check(L.b200rt_bvh_build(B.fptr(self.triangles), len(self.triangles), C.byref(opts), C.byref(h)))
         self._h = h
 
     def __del__(self):

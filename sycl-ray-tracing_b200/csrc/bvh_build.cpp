@@ -619,7 +619,8 @@ int check_flat_bvh(const FlatBVH& bvh, const float* tri9, int n_tri)
         if (it.depth > kMaxTraversalDepth) return 5;
         if (it.node < 0 || it.node >= (int)bvh.axis.size()) return 6;
         const AxisNode& an = bvh.axis[it.node];
-        const DiagNode& dn = bvh.diag[it.node];
+        static const DiagNode no_diag = { { -kInf, -kInf, -kInf, -kInf }, { kInf, kInf, kInf, kInf }, { -kInf, -kInf, -kInf, -kInf }, { kInf, kInf, kInf, kInf } };
+        const DiagNode& dn = bvh.diag.empty() ? no_diag : bvh.diag[it.node];      // the device builder emits no diagonal slabs
         for (int side = 0; side < 2; side++)
         {
             const float* lo = side ? an.r_lo : an.l_lo; const float* hi = side ? an.r_hi : an.l_hi;
@@ -631,7 +632,7 @@ int check_flat_bvh(const FlatBVH& bvh, const float* tri9, int n_tri)
                 // child's children must be inside this volume
                 if (ref >= (int)bvh.axis.size()) return 6;
                 const AxisNode& cn = bvh.axis[ref];
-                const DiagNode& cd = bvh.diag[ref];
+                const DiagNode& cd = bvh.diag.empty() ? no_diag : bvh.diag[ref];
                 for (int cs = 0; cs < 2; cs++)
                 {
                     const float* clo = cs ? cn.r_lo : cn.l_lo; const float* chi = cs ? cn.r_hi : cn.l_hi;

@@ -5,6 +5,7 @@
 // (include/bounding_volume.h:9-127, plane normals source/bvh.cpp:8-16).
 #pragma once
 #include <cstdint>
+#include <string>
 #include <vector>
 
 #include "../../include/b200rt.h"
@@ -76,5 +77,7 @@ inline float diag_dist(int k, float x, float y, float z)
 
 void build_flat_bvh(const float* tri9, int n_tri, const b200rt_bvh_options& opts, FlatBVH& out);
 int check_flat_bvh(const FlatBVH& bvh, const float* tri9, int n_tri);
+// device builder (bvh_build_gpu.cu): 0 = ok, 1 = CUDA error, 2 = input outside what it handles (err says why)
+int build_flat_bvh_device(const float* tri9_host, int n_tri, int device, FlatBVH& out, std::string& err);
 
 } // namespace b200rt

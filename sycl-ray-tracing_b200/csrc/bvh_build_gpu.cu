@@ -1,0 +1,540 @@
+// BVH construction on the device (sm_100a): replaces BVH::BVH / OctreeNode::insert / compute_volume / flatten of the
+// reference (source/bvh.cpp:19-60, include/bvh.h:55-125, :211-250) for callers that cannot afford the host builder
+// (at 20 M triangles the host SAH build is ~13 s, the reference's own octree insert is sequential).
+// Only the closest-hit RESULT is contractual, not the tree shape, so this is a linear BVH:
+//   1. per-triangle boxes, scene bounds                                   (lb_bounds)
+//   2. 63-bit Morton codes of the box centres, radix sort                 (lb_morton, cub::DeviceRadixSort — library call, one-shot setup)
+//   3. binary radix tree over the sorted codes, all nodes in parallel     (lb_tree; Karras, "Maximizing parallelism in the construction of BVHs...", HPG 2012)
+//   4. bottom-up box fit with one atomic counter per node                 (lb_fit)
+//   5. subtrees of <= 3 triangles become leaves; level-by-level collapse into the 8-ary layout: every wide node opens its
+//      largest children until it has 8, assigns them to octant slots     (lw_expand, lw_link; prefix sums give child_base / tri_base)
+//   6. emit: quantised 80-byte wide nodes + the leaf-ordered triangle stream (lw_emit), binary two-children records (lb_emit)
+// Output is the same FlatBVH the host builder produces (b200rt_bvh_check validates either), except that it carries no
+// diagonal slabs (has_diag_slabs = 0: the 7-plane ablation needs the host builder).
+#include <cfloat>
+#include <chrono>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cuda_runtime.h>
+
+#include "bvh_build.h"
+
+namespace b200rt {
+namespace {
+
+constexpr int kLeafBit = 0x40000000;        // child reference of the radix tree: index | kLeafBit = sorted triangle position
+
+struct DevArrays
+{
+    const float* tri9;
+    float4 *plo, *phi;                       // per triangle box
+    unsigned long long *keys, *keys_alt;
+    int *vals, *vals_alt;                    // sorted position -> triangle index
+    int *left, *right, *first, *last, *parent_node, *parent_leaf;
+    float4 *nlo, *nhi;                       // per internal node box
+    unsigned int* visits;
+    int* scene;                              // 7 ordered ints: centre-bounds min xyz, max xyz, max |coord|
+    int n;
+};
+
+__device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
+__device__ __host__ __forceinline__ float ord2f(int i) { int j = i >= 0 ? i : i ^ 0x7fffffff; float f; memcpy(&f, &j, 4); return f; }
+
+__global__ void lb_bounds(DevArrays A)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float lo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, hi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX }, c[3] = { 0, 0, 0 }, am = 0.0f;
+    const bool live = i < A.n;
+    if (live)
+    {
+        const float* p = A.tri9 + 9 * (size_t)i;
+        for (int a = 0; a < 3; a++)
+        {
+            lo[a] = fminf(fminf(p[a], p[3 + a]), p[6 + a]);
+            hi[a] = fmaxf(fmaxf(p[a], p[3 + a]), p[6 + a]);
+            c[a] = 0.5f * (lo[a] + hi[a]);
+            am = fmaxf(am, fmaxf(fabsf(lo[a]), fabsf(hi[a])));
+        }
+        A.plo[i] = make_float4(lo[0], lo[1], lo[2], 0.0f);
+        A.phi[i] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+    }
+    for (int a = 0; a < 3; a++)
+    {
+        float mn = live ? c[a] : FLT_MAX, mx = live ? c[a] : -FLT_MAX;
+        for (int o = 16; o > 0; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+        if ((threadIdx.x & 31) == 0 && mn <= mx) { atomicMin(&A.scene[a], f2ord(mn)); atomicMax(&A.scene[3 + a], f2ord(mx)); }
+    }
+    for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(&A.scene[6], f2ord(am));
+}
+
+__device__ __forceinline__ unsigned long long spread3(unsigned long long x)       // 21 bits -> every third bit
+{
+    x &= 0x1fffffull;
+    x = (x | x << 32) & 0x1f00000000ffffull;
+    x = (x | x << 16) & 0x1f0000ff0000ffull;
+    x = (x | x << 8) & 0x100f00f00f00f00full;
+    x = (x | x << 4) & 0x10c30c30c30c30c3ull;
+    x = (x | x << 2) & 0x1249249249249249ull;
+    return x;
+}
+
+__global__ void lb_morton(DevArrays A)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    const float4 lo = A.plo[i], hi = A.phi[i];
+    const float c[3] = { 0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z) };
+    unsigned long long code = 0;
+    for (int a = 0; a < 3; a++)
+    {
+        const double mn = ord2f(A.scene[a]), mx = ord2f(A.scene[3 + a]);
+        const double ext = mx - mn;
+        double u = ext > 0.0 ? ((double)c[a] - mn) / ext : 0.0;
+        u = fmin(fmax(u, 0.0), 1.0);
+        const unsigned long long q = (unsigned long long)fmin(u * 2097152.0, 2097151.0);
+        code |= spread3(q) << a;
+    }
+    A.keys[i] = code;
+    A.vals[i] = i;
+}
+
+// common-prefix length of sorted keys i and j, ties broken by position; -1 outside the array
+__device__ __forceinline__ int lb_delta(const unsigned long long* k, int n, int i, int j)
+{
+    if (j < 0 || j >= n) return -1;
+    const unsigned long long a = k[i], b = k[j];
+    if (a == b) return 64 + __clz(i ^ j);
+    return __clzll((long long)(a ^ b));
+}
+
+__global__ void lb_tree(DevArrays A)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int n = A.n;
+    if (i >= n - 1) return;
+    const unsigned long long* k = A.keys;
+    const int d = (lb_delta(k, n, i, i + 1) - lb_delta(k, n, i, i - 1)) >= 0 ? 1 : -1;
+    const int dmin = lb_delta(k, n, i, i - d);
+    int lmax = 2;
+    while (lb_delta(k, n, i, i + lmax * d) > dmin) lmax <<= 1;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+        if (lb_delta(k, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = lb_delta(k, n, i, j);
+    int s = 0;
+    for (int t = (l + 1) >> 1;; t = (t + 1) >> 1)
+    {
+        if (lb_delta(k, n, i, i + (s + t) * d) > dnode) s += t;
+        if (t <= 1) break;
+    }
+    const int gamma = i + s * d + min(d, 0);
+    const int lo = min(i, j), hi = max(i, j);
+    const int L = (lo == gamma) ? (gamma | kLeafBit) : gamma;
+    const int R = (hi == gamma + 1) ? ((gamma + 1) | kLeafBit) : gamma + 1;
+    A.left[i] = L; A.right[i] = R; A.first[i] = lo; A.last[i] = hi;
+    if (L & kLeafBit) A.parent_leaf[gamma] = i; else A.parent_node[gamma] = i;
+    if (R & kLeafBit) A.parent_leaf[gamma + 1] = i; else A.parent_node[gamma + 1] = i;
+    if (i == 0) A.parent_node[0] = -1;
+}
+
+// one thread per sorted triangle walks up; the second arrival at a node fits its box. Also the depth of every leaf.
+__global__ void lb_fit(DevArrays A, int* max_depth)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= A.n) return;
+    int node = A.parent_leaf[p];
+    int depth = 1;
+    bool fitting = true;
+    while (node >= 0)
+    {
+        depth++;
+        if (fitting)
+        {
+            __threadfence();
+            if (atomicAdd(&A.visits[node], 1u) == 0u) fitting = false;        // first arrival: the sibling subtree is not done yet
+            else
+            {
+                const int L = A.left[node], R = A.right[node];
+                // inner children were written by other threads of this launch: read them at L2 (__ldcg), not through this SM's L1
+                const float4 llo = (L & kLeafBit) ? A.plo[A.vals[L & ~kLeafBit]] : __ldcg(A.nlo + L), lhi = (L & kLeafBit) ? A.phi[A.vals[L & ~kLeafBit]] : __ldcg(A.nhi + L);
+                const float4 rlo = (R & kLeafBit) ? A.plo[A.vals[R & ~kLeafBit]] : __ldcg(A.nlo + R), rhi = (R & kLeafBit) ? A.phi[A.vals[R & ~kLeafBit]] : __ldcg(A.nhi + R);
+                A.nlo[node] = make_float4(fminf(llo.x, rlo.x), fminf(llo.y, rlo.y), fminf(llo.z, rlo.z), 0.0f);
+                A.nhi[node] = make_float4(fmaxf(lhi.x, rhi.x), fmaxf(lhi.y, rhi.y), fmaxf(lhi.z, rhi.z), 0.0f);
+            }
+        }
+        node = A.parent_node[node];
+    }
+    for (int o = 16; o > 0; o >>= 1) depth = max(depth, __shfl_xor_sync(0xffffffffu, depth, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(max_depth, depth);
+}
+
+// ---- 8-ary collapse ------------------------------------------------------------------------------------------------------------
+struct WideArrays
+{
+    int* root;            // wide node -> radix-tree node it was opened from
+    int* slots;           // [8 per wide node] child reference by octant slot, kEmpty when unused
+    int* n_inner;         // inner children per wide node
+    int* n_tris;          // triangles in leaf children per wide node
+    int* child_base;
+    int* tri_base;
+    int* node_first;      // radix-tree node collapsed into a leaf -> first slot of its triangles in the final stream
+    int* leaf_first;      // sorted triangle position that is a leaf child on its own -> its slot in the final stream
+};
+constexpr int kEmpty = -1;
+
+__device__ __forceinline__ int ref_size(const DevArrays& A, int ref) { return (ref & kLeafBit) ? 1 : A.last[ref] - A.first[ref] + 1; }
+__device__ __forceinline__ bool ref_inner(const DevArrays& A, int ref) { return ref_size(A, ref) > kWideMaxLeaf; }
+__device__ __forceinline__ void ref_box(const DevArrays& A, int ref, float4& lo, float4& hi)
+{
+    if (ref & kLeafBit) { const int t = A.vals[ref & ~kLeafBit]; lo = A.plo[t]; hi = A.phi[t]; }
+    else { lo = A.nlo[ref]; hi = A.nhi[ref]; }
+}
+__device__ __forceinline__ float half_area(float4 lo, float4 hi)
+{
+    const float dx = hi.x - lo.x, dy = hi.y - lo.y, dz = hi.z - lo.z;
+    return dx * dy + dy * dz + dz * dx;
+}
+
+// wide nodes [begin, end): open the largest inner child until 8, give every child its octant slot
+__global__ void lw_expand(DevArrays A, WideArrays W, int begin, int end)
+{
+    const int w = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= end) return;
+    const int rn = W.root[w];
+    int kids[8]; int nk = 0;
+    kids[nk++] = A.left[rn]; kids[nk++] = A.right[rn];
+    while (nk < 8)
+    {
+        int best = -1; float best_area = -1.0f;
+        for (int k = 0; k < nk; k++)
+        {
+            if (!ref_inner(A, kids[k])) continue;
+            float4 lo, hi; ref_box(A, kids[k], lo, hi);
+            const float ar = half_area(lo, hi);
+            if (ar > best_area) { best_area = ar; best = k; }
+        }
+        if (best < 0) break;
+        const int c = kids[best];
+        kids[best] = A.left[c]; kids[nk++] = A.right[c];
+    }
+    const float4 blo = A.nlo[rn], bhi = A.nhi[rn];
+    const float nc[3] = { 0.5f * (blo.x + bhi.x), 0.5f * (blo.y + bhi.y), 0.5f * (blo.z + bhi.z) };
+    float cost[8][8];
+    for (int k = 0; k < nk; k++)
+    {
+        float4 lo, hi; ref_box(A, kids[k], lo, hi);
+        const float cc[3] = { 0.5f * (lo.x + hi.x) - nc[0], 0.5f * (lo.y + hi.y) - nc[1], 0.5f * (lo.z + hi.z) - nc[2] };
+        for (int s = 0; s < 8; s++) cost[k][s] = ((s & 1) ? cc[0] : -cc[0]) + ((s & 2) ? cc[1] : -cc[1]) + ((s & 4) ? cc[2] : -cc[2]);
+    }
+    int slot_ref[8];
+    for (int s = 0; s < 8; s++) slot_ref[s] = kEmpty;
+    unsigned int kid_done = 0, slot_used = 0;
+    for (int round = 0; round < nk; round++)
+    {
+        int bk = -1, bs = -1; float bc = -FLT_MAX;
+        for (int k = 0; k < nk; k++)
+        {
+            if (kid_done & (1u << k)) continue;
+            for (int s = 0; s < 8; s++)
+                if (!(slot_used & (1u << s)) && (bk < 0 || cost[k][s] > bc)) { bc = cost[k][s]; bk = k; bs = s; }
+        }
+        slot_ref[bs] = kids[bk]; kid_done |= 1u << bk; slot_used |= 1u << bs;
+    }
+    int ni = 0, nt = 0;
+    for (int s = 0; s < 8; s++)
+    {
+        W.slots[8 * (size_t)w + s] = slot_ref[s];
+        if (slot_ref[s] == kEmpty) continue;
+        if (ref_inner(A, slot_ref[s])) ni++; else nt += ref_size(A, slot_ref[s]);
+    }
+    W.n_inner[w] = ni; W.n_tris[w] = nt;
+}
+
+__global__ void lw_shift(int* p, int n, int by)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) p[i] += by;
+}
+
+// the inner children of wide nodes [begin, end) become the wide nodes of the next level (child_base already scanned)
+__global__ void lw_link(DevArrays A, WideArrays W, int begin, int end)
+{
+    const int w = begin + blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= end) return;
+    int at = W.child_base[w];
+    for (int s = 0; s < 8; s++)
+    {
+        const int r = W.slots[8 * (size_t)w + s];
+        if (r != kEmpty && ref_inner(A, r)) W.root[at++] = r;
+    }
+}
+
+__device__ __forceinline__ float box_pad_dev(float lo, float hi, float abs_pad) { return 1e-5f * fmaxf(fabsf(lo), fabsf(hi)) + abs_pad; }
+
+__device__ __forceinline__ void emit_triangle(const DevArrays& A, int tri, float4* out)
+{
+    const float* p = A.tri9 + 9 * (size_t)tri;
+    out[0] = make_float4(p[0], p[1], p[2], __int_as_float(tri));
+    out[1] = make_float4(p[3] - p[0], p[4] - p[1], p[5] - p[2], 0.0f);       // same float subtraction as triangle.h:21-22 / the host builder
+    out[2] = make_float4(p[6] - p[0], p[7] - p[1], p[8] - p[2], 0.0f);
+}
+
+// quantised node + its leaf children's triangles (device twin of WideBuilder::quantise_axis / emit in bvh_build.cpp)
+__global__ void lw_emit(DevArrays A, WideArrays W, int n_wide, float abs_pad, WideNode* nodes, float4* tris, int* overflow)
+{
+    const int w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w >= n_wide) return;
+    WideNode node;
+    memset(&node, 0, sizeof(node));
+    node.child_base = (uint32_t)W.child_base[w];
+    node.tri_base = (uint32_t)W.tri_base[w];
+    int refs[8];
+    float klo[8][3], khi[8][3];
+    int at = W.tri_base[w];
+    for (int s = 0; s < 8; s++)
+    {
+        const int r = refs[s] = W.slots[8 * (size_t)w + s];
+        if (r == kEmpty) continue;
+        float4 lo, hi; ref_box(A, r, lo, hi);
+        const float l3[3] = { lo.x, lo.y, lo.z }, h3[3] = { hi.x, hi.y, hi.z };
+        for (int a = 0; a < 3; a++)
+        {
+            const float pad = box_pad_dev(l3[a], h3[a], abs_pad);
+            klo[s][a] = l3[a] - pad; khi[s][a] = h3[a] + pad;
+        }
+        if (ref_inner(A, r)) { node.imask |= (uint8_t)(1u << s); continue; }
+        const int cnt = ref_size(A, r);
+        const int p0 = (r & kLeafBit) ? (r & ~kLeafBit) : A.first[r];
+        if (r & kLeafBit) W.leaf_first[p0] = at; else W.node_first[r] = at;
+        for (int i = 0; i < cnt; i++) emit_triangle(A, A.vals[p0 + i], tris + 3 * (size_t)(at + i));
+        node.valid24 |= ((1u << cnt) - 1u) << (3 * s);
+        at += cnt;
+    }
+    for (int a = 0; a < 3; a++)
+    {
+        float lo = FLT_MAX, hi = -FLT_MAX;
+        for (int s = 0; s < 8; s++)
+            if (refs[s] != kEmpty) { lo = fminf(lo, klo[s][a]); hi = fmaxf(hi, khi[s][a]); }
+        if (!(lo <= hi)) { lo = 0.0f; hi = 0.0f; }
+        const double extent = (double)hi - (double)lo;
+        int e = -100;
+        if (extent > 0.0) { int ex; frexp(extent / 376.0, &ex); e = ex; }
+        const double amax = fmax(fabs((double)lo), fabs((double)hi));
+        if (amax > 0.0) e = max(e, ilogb(amax) - 23);
+        e = min(126, max(-100, e));
+        const double cell = ldexp(1.0, e);
+        const double pd = (double)lo - 128.0 * cell;
+        float pf = (float)pd;
+        if ((double)pf > pd) pf = nextafterf(pf, -FLT_MAX);
+        node.p[a] = pf;
+        node.e[a] = (uint8_t)(e + 127);
+        uint8_t* qlo = a == 0 ? node.lox : (a == 1 ? node.loy : node.loz);
+        uint8_t* qhi = a == 0 ? node.hix : (a == 1 ? node.hiy : node.hiz);
+        for (int s = 0; s < 8; s++)
+        {
+            qlo[s] = 255; qhi[s] = 0;
+            if (refs[s] == kEmpty) continue;
+            long long vl = (long long)floor(((double)klo[s][a] - (double)pf) / cell);
+            long long vh = (long long)ceil(((double)khi[s][a] - (double)pf) / cell);
+            if (vl < 128 || vh > 510) *overflow = 1;
+            vl = min(510LL, max(128LL, vl)); vh = min(510LL, max(128LL, vh));
+            if (vl >= 256) vl &= ~1LL;
+            if (vh >= 256 && (vh & 1)) vh++;
+            if (vh > 510) { *overflow = 1; vh = 510; }
+            qlo[s] = (uint8_t)(vl < 256 ? vl - 128 : vl / 2);
+            qhi[s] = (uint8_t)(vh < 256 ? vh - 128 : vh / 2);
+        }
+    }
+    nodes[w] = node;
+}
+
+// ---- binary records over the same tree and the same triangle stream ---------------------------------------------------------------------
+__global__ void lb_mark_live(DevArrays A, int* live)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < A.n - 1) live[i] = (A.last[i] - A.first[i] + 1) > kWideMaxLeaf ? 1 : 0;
+}
+
+__global__ void lb_emit(DevArrays A, WideArrays W, const int* live, const int* axis_idx, float abs_pad, AxisNode* axis)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n - 1 || !live[i]) return;
+    AxisNode an;
+    for (int side = 0; side < 2; side++)
+    {
+        const int r = side ? A.right[i] : A.left[i];
+        float4 lo, hi; ref_box(A, r, lo, hi);
+        float* olo = side ? an.r_lo : an.l_lo; float* ohi = side ? an.r_hi : an.l_hi;
+        const float l3[3] = { lo.x, lo.y, lo.z }, h3[3] = { hi.x, hi.y, hi.z };
+        for (int a = 0; a < 3; a++)
+        {
+            const float pad = box_pad_dev(l3[a], h3[a], abs_pad);
+            olo[a] = l3[a] - pad; ohi[a] = h3[a] + pad;
+        }
+        int ref, count = 0;
+        if (ref_inner(A, r)) ref = axis_idx[r];
+        else
+        {
+            count = ref_size(A, r);
+            const int first = (r & kLeafBit) ? W.leaf_first[r & ~kLeafBit] : W.node_first[r];
+            ref = ~((first << 4) | count);
+        }
+        if (side) { an.r_ref = ref; an.r_count = count; } else { an.l_ref = ref; an.l_count = count; }
+    }
+    axis[axis_idx[i]] = an;
+}
+
+struct Pool       // frees everything it handed out
+{
+    std::vector<void*> p;
+    ~Pool() { for (void* q : p) cudaFree(q); }
+    template <typename T> cudaError_t get(T** out, size_t n)
+    {
+        void* d = nullptr;
+        cudaError_t e = cudaMalloc(&d, std::max<size_t>(n, 1) * sizeof(T));
+        if (e == cudaSuccess) { p.push_back(d); *out = (T*)d; }
+        return e;
+    }
+};
+
+} // namespace
+
+#define GCU(expr)                                                                                    \
+    do {                                                                                             \
+        cudaError_t e__ = (expr);                                                                    \
+        if (e__ != cudaSuccess) { err = std::string(#expr) + ": " + cudaGetErrorString(e__); return 1; } \
+    } while (0)
+
+// 0 = ok; 1 = CUDA error; 2 = the input is outside what this builder handles (caller falls back to the host builder)
+int build_flat_bvh_device(const float* tri9_host, int n_tri, int device, FlatBVH& out, std::string& err)
+{
+    const auto t0 = std::chrono::high_resolution_clock::now();
+    if (n_tri <= kWideMaxLeaf) { err = "fewer than 4 triangles"; return 2; }
+    GCU(cudaSetDevice(device));
+    Pool pool;
+    DevArrays A;
+    memset(&A, 0, sizeof(A));
+    A.n = n_tri;
+    const size_t n = (size_t)n_tri;
+    float* d_tri9 = nullptr;
+    GCU(pool.get(&d_tri9, 9 * n));
+    GCU(cudaMemcpy(d_tri9, tri9_host, 9 * n * sizeof(float), cudaMemcpyHostToDevice));
+    A.tri9 = d_tri9;
+    GCU(pool.get(&A.plo, n)); GCU(pool.get(&A.phi, n));
+    GCU(pool.get(&A.keys, n)); GCU(pool.get(&A.keys_alt, n)); GCU(pool.get(&A.vals, n)); GCU(pool.get(&A.vals_alt, n));
+    GCU(pool.get(&A.left, n)); GCU(pool.get(&A.right, n)); GCU(pool.get(&A.first, n)); GCU(pool.get(&A.last, n));
+    GCU(pool.get(&A.parent_node, n)); GCU(pool.get(&A.parent_leaf, n));
+    GCU(pool.get(&A.nlo, n)); GCU(pool.get(&A.nhi, n)); GCU(pool.get(&A.visits, n));
+    GCU(pool.get(&A.scene, 8));
+    int* d_misc = nullptr;                   // [0] max depth, [1] overflow flag
+    GCU(pool.get(&d_misc, 4));
+    GCU(cudaMemset(d_misc, 0, 4 * sizeof(int)));
+    GCU(cudaMemset(A.visits, 0, n * sizeof(unsigned int)));
+    {
+        const int init[8] = { INT32_MAX, INT32_MAX, INT32_MAX, INT32_MIN, INT32_MIN, INT32_MIN, INT32_MIN, 0 };
+        GCU(cudaMemcpy(A.scene, init, sizeof(init), cudaMemcpyHostToDevice));
+    }
+    const int tb = 256, grid_n = (n_tri + tb - 1) / tb;
+    lb_bounds<<<grid_n, tb>>>(A);
+    lb_morton<<<grid_n, tb>>>(A);
+    {
+        cub::DoubleBuffer<unsigned long long> dk(A.keys, A.keys_alt);
+        cub::DoubleBuffer<int> dv(A.vals, A.vals_alt);
+        size_t tmp_bytes = 0;
+        GCU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, n_tri, 0, 63));
+        char* tmp = nullptr;
+        GCU(pool.get(&tmp, tmp_bytes));
+        GCU(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, n_tri, 0, 63));
+        A.keys = dk.Current(); A.vals = dv.Current();
+    }
+    lb_tree<<<grid_n, tb>>>(A);
+    lb_fit<<<grid_n, tb>>>(A, d_misc);
+    int scene_h[8];
+    int misc_h[4];
+    GCU(cudaMemcpy(scene_h, A.scene, sizeof(scene_h), cudaMemcpyDeviceToHost));
+    GCU(cudaMemcpy(misc_h, d_misc, sizeof(misc_h), cudaMemcpyDeviceToHost));
+    if (misc_h[0] > kMaxTraversalDepth) { err = "radix tree deeper than the traversal stack (" + std::to_string(misc_h[0]) + ")"; return 2; }
+    float scene_abs = ord2f(scene_h[6]);
+    if (!(scene_abs < FLT_MAX)) scene_abs = 1.0f;
+    const float abs_pad = 2e-6f * scene_abs + 1e-30f;
+
+    // 8-ary collapse, one level at a time
+    WideArrays W;
+    memset(&W, 0, sizeof(W));
+    // wide nodes are radix-tree inner nodes: fewer than n
+    GCU(pool.get(&W.root, n)); GCU(pool.get(&W.slots, 8 * n)); GCU(pool.get(&W.n_inner, n)); GCU(pool.get(&W.n_tris, n));
+    GCU(pool.get(&W.child_base, n)); GCU(pool.get(&W.tri_base, n)); GCU(pool.get(&W.node_first, n)); GCU(pool.get(&W.leaf_first, n));
+    size_t scan_bytes = 0;
+    GCU(cub::DeviceScan::ExclusiveSum(nullptr, scan_bytes, W.n_inner, W.child_base, n_tri));
+    char* scan_tmp = nullptr;
+    GCU(pool.get(&scan_tmp, scan_bytes));
+    {
+        const int zero = 0;
+        GCU(cudaMemcpy(W.root, &zero, sizeof(int), cudaMemcpyHostToDevice));
+    }
+    int begin = 0, end = 1, wide_depth = 0;
+    while (begin < end)
+    {
+        wide_depth++;
+        const int cnt = end - begin, g = (cnt + 127) / 128;
+        lw_expand<<<g, 128>>>(A, W, begin, end);
+        GCU(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, W.n_inner + begin, W.child_base + begin, cnt));
+        int last_base = 0, last_cnt = 0;
+        GCU(cudaMemcpy(&last_base, W.child_base + end - 1, sizeof(int), cudaMemcpyDeviceToHost));
+        GCU(cudaMemcpy(&last_cnt, W.n_inner + end - 1, sizeof(int), cudaMemcpyDeviceToHost));
+        const int next_cnt = last_base + last_cnt;
+        if (wide_depth > kMaxTraversalDepth) { err = "wide tree deeper than the traversal stack"; return 2; }
+        if ((size_t)end + next_cnt > n) { err = "wide node count exceeds its bound"; return 1; }
+        lw_shift<<<g, 128>>>(W.child_base + begin, cnt, end);      // the scan is relative to the level's first child, which gets index `end`
+        lw_link<<<g, 128>>>(A, W, begin, end);
+        begin = end; end += next_cnt;
+    }
+    const int n_wide = end;
+    GCU(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, W.n_tris, W.tri_base, n_wide));
+    WideNode* d_wide = nullptr; float4* d_tris = nullptr;
+    GCU(pool.get(&d_wide, (size_t)n_wide)); GCU(pool.get(&d_tris, 3 * n));
+    lw_emit<<<(n_wide + 127) / 128, 128>>>(A, W, n_wide, abs_pad, d_wide, d_tris, d_misc + 1);
+
+    // binary records
+    int *d_live = nullptr, *d_axis_idx = nullptr;
+    GCU(pool.get(&d_live, n)); GCU(pool.get(&d_axis_idx, n));
+    lb_mark_live<<<grid_n, tb>>>(A, d_live);
+    GCU(cub::DeviceScan::ExclusiveSum(scan_tmp, scan_bytes, d_live, d_axis_idx, n_tri - 1));
+    int n_axis = 0, last_live = 0;
+    GCU(cudaMemcpy(&n_axis, d_axis_idx + (n_tri - 2), sizeof(int), cudaMemcpyDeviceToHost));
+    GCU(cudaMemcpy(&last_live, d_live + (n_tri - 2), sizeof(int), cudaMemcpyDeviceToHost));
+    n_axis += last_live;
+    AxisNode* d_axis = nullptr;
+    GCU(pool.get(&d_axis, (size_t)std::max(n_axis, 1)));
+    lb_emit<<<grid_n, tb>>>(A, W, d_live, d_axis_idx, abs_pad, d_axis);
+    GCU(cudaMemcpy(misc_h, d_misc, sizeof(misc_h), cudaMemcpyDeviceToHost));
+    GCU(cudaGetLastError());
+    if (misc_h[1]) { err = "wide BVH quantisation overflow"; return 1; }
+
+    out.wide.resize((size_t)n_wide); out.tris.resize(n); out.axis.resize((size_t)n_axis); out.diag.clear();
+    GCU(cudaMemcpy(out.wide.data(), d_wide, (size_t)n_wide * sizeof(WideNode), cudaMemcpyDeviceToHost));
+    GCU(cudaMemcpy(out.tris.data(), d_tris, n * sizeof(LeafTriangle), cudaMemcpyDeviceToHost));
+    GCU(cudaMemcpy(out.axis.data(), d_axis, (size_t)n_axis * sizeof(AxisNode), cudaMemcpyDeviceToHost));
+    const auto t1 = std::chrono::high_resolution_clock::now();
+    memset(&out.info, 0, sizeof(out.info));
+    out.info.n_triangles = n_tri;
+    out.info.n_inner_nodes = n_axis;
+    out.info.n_leaves = n_axis + 1;
+    out.info.max_leaf_size = kWideMaxLeaf;
+    out.info.max_depth = misc_h[0];
+    out.info.has_diag_slabs = 0;
+    out.info.build_seconds = std::chrono::duration<double>(t1 - t0).count();
+    out.info.sah_cost = 0.0;
+    out.info.n_wide_nodes = n_wide;
+    out.info.wide_max_depth = wide_depth;
+    return 0;
+}
+
+} // namespace b200rt

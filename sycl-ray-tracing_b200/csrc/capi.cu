@@ -324,6 +324,28 @@ int b200rt_bvh_build(const float* tri_xyz9, int n_tri, const b200rt_bvh_options*
     return B200RT_OK;
 }
 
+int b200rt_bvh_build_device(const float* tri_xyz9, int n_tri, int device, b200rt_bvh** out)
+{
+    if (!out) return fail(B200RT_ERR_ARG, "out must not be NULL");
+    *out = nullptr;
+    if (n_tri < 0 || (n_tri > 0 && !tri_xyz9)) return fail(B200RT_ERR_ARG, "bad triangle buffer");
+    if (n_tri >= (1 << 27)) return fail(B200RT_ERR_ARG, "at most 2^27-1 triangles (leaf references pack first<<4|count)");
+    if (n_tri <= kWideMaxLeaf) return b200rt_bvh_build(tri_xyz9, n_tri, nullptr, out);      // a single leaf: nothing to build in parallel
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) return fail(B200RT_ERR_CUDA, "no CUDA device: b200rt_bvh_build_device has no CPU fallback");
+    if (device < 0) CU(cudaGetDevice(&device));
+    if (device >= n_dev) return fail(B200RT_ERR_ARG, "device %d of %d", device, n_dev);
+    b200rt_bvh* b = new (std::nothrow) b200rt_bvh;
+    if (!b) return fail(B200RT_ERR_ALLOC, "out of host memory");
+    std::string err;
+    int rc = 1;
+    try { rc = build_flat_bvh_device(tri_xyz9, n_tri, device, b->flat, err); }
+    catch (const std::exception& e) { err = e.what(); rc = 1; }
+    if (rc) { delete b; return fail(rc == 2 ? B200RT_ERR_ARG : B200RT_ERR_CUDA, "device BVH build: %s", err.c_str()); }
+    *out = b;
+    return B200RT_OK;
+}
+
 int b200rt_bvh_get_info(const b200rt_bvh* bvh, b200rt_bvh_info* out)
 {
     if (!bvh || !out) return fail(B200RT_ERR_ARG, "NULL argument");

@@ -362,3 +362,47 @@ def test_c3_crop_against_oracle(rt):
     print(s)
     assert s["frac_close"] >= 0.99 and s["rmse"] <= 5.0e-3, s
     assert abs(s["mean_gpu"] - s["mean_ref"]) <= 0.005 * s["mean_ref"], s
+
+
+# ---- BVH built on the device ----------------------------------------------------------------------------------
+@pytest.mark.parametrize("key", ["cornell", "mis", "area"])
+def test_device_built_bvh_same_hits_and_image(rt, golden_scenes, golden_cameras, key):
+    """b200rt_bvh_build_device: another tree shape, the same exact closest hits -> bit-identical primary maps and images."""
+    g = load_golden(f"primary_{key}.npz")
+    tri = golden_scenes[f"{key}_tri9"]
+    bvh = rt.BVH(tri, on_device=True)
+    bvh.check()                                     # every triangle once, every (de-quantised) child box contains its triangles
+    info = bvh.info()
+    assert info["n_triangles"] == len(tri) and info["n_wide_nodes"] >= 1 and info["has_diag_slabs"] == 0
+    assert info["max_depth"] <= 60 and info["wide_max_depth"] <= 60
+    sc_d = make_scene(rt, golden_scenes, key, bvh=bvh)
+    sc_h = make_scene(rt, golden_scenes, key)
+    c = cam(rt, golden_cameras, CAM_OF[key])
+    w, h = int(g["w"]), int(g["h"])
+    for flags in (0, rt.FLAG_BVH8):
+        prim, t, _ = sc_d.trace_primary(c, w, h, flags=flags)
+        assert_primary_parity(prim, t, g["prim"], g["prim_brute"], g["t"], max_ties=0)
+    a, sa = sc_d.render(c, 96, 72, 3, 5)
+    b, sb = sc_h.render(c, 96, 72, 3, 5)
+    assert np.array_equal(bits(a), bits(b)) and sa["rays"] == sb["rays"]
+    a2, _ = sc_d.render(c, 96, 72, 3, 5, flags=rt.FLAG_BVH2)
+    assert np.array_equal(bits(a), bits(a2))
+
+
+def test_device_built_bvh_c2_full_size(rt):
+    """1 M triangles: device build, structural check, primary rays bit-exact against the host-built tree; build time reported."""
+    from sycl_ray_tracing_b200 import scenes
+    c2 = scenes.c2_scene()
+    bvh = rt.BVH(c2["tri9"], on_device=True)
+    bvh.check()
+    info = bvh.info()
+    assert info["n_triangles"] == 1_000_000 and info["max_depth"] <= 60
+    sc_d = rt.Scene(c2["tri9"], c2["mat_idx"], c2["mats10"], c2["emissive"], bvh=bvh)
+    sc_h = rt.Scene(c2["tri9"], c2["mat_idx"], c2["mats10"], c2["emissive"])
+    pd, td, _ = sc_d.trace_primary(c2["camera"], 1920, 1080)
+    ph, th, _ = sc_h.trace_primary(c2["camera"], 1920, 1080)
+    assert int((ph >= 0).sum()) == 502_161                      # SURVEY Appendix A KAT
+    assert np.array_equal(pd, ph) and np.array_equal(bits(td), bits(th))
+    p8, t8, _ = sc_d.trace_primary(c2["camera"], 1920, 1080, flags=rt.FLAG_BVH8)
+    assert np.array_equal(p8, ph) and np.array_equal(bits(t8), bits(th))
+    print(f"device build {info['build_seconds']:.3f} s vs host {sc_h.bvh_info()['build_seconds']:.3f} s")
