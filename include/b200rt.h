@@ -187,6 +187,13 @@ int b200rt_trace_rays_device(b200rt_scene* scene, const void* dev_rays6, int n_r
                              void* dev_extra8_or_null, const b200rt_render_options* opts_or_null, void* cuda_stream,
                              b200rt_stats* stats_or_null);
 
+/* ---- output stage -------------------------------------------------------------------------------------------------------
+ * The quantisation loop of write_image_png (source/image_io.cpp:165-182): out = (unsigned char)clamp(rgba * 255, 0, 255),
+ * flip_y != 0 writes image row 0 (the bottom row) last, as stbi_flip_vertically_on_write does. 16 B in, 4 B out per
+ * pixel: run it on the device right after a render and the frame leaves the GPU at a quarter of the bytes. */
+int b200rt_quantise_rgba8(const float* image_rgba, int width, int height, int flip_y, unsigned char* out_rgba8);
+int b200rt_quantise_rgba8_device(const void* dev_image_rgba, int width, int height, int flip_y, void* dev_out_rgba8, void* cuda_stream);
+
 const char* b200rt_last_error(void);
 const char* b200rt_version(void);
 

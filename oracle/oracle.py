@@ -272,6 +272,15 @@ class PortOracle(_OracleBase):
         return out, float(sec), int(rays.value)
 
 
+def quantise_rgba8(image, flip_y: bool = True):
+    """numpy restatement of write_image_png's quantisation loop (source/image_io.cpp:165-182 with clamp() :157-162):
+    pixel = image * 255 in float, clamp to [0, 255], truncate to unsigned char; flipY writes row 0 last. Pinned against a
+    PNG written by the reference itself (tests/golden/quantise.npz). Test infrastructure, like the rest of oracle/."""
+    p = np.ascontiguousarray(image, np.float32) * np.float32(255)
+    c = np.where(p < 0, np.float32(0), np.where(p > 255, np.float32(255), p)).astype(np.uint8)
+    return c[::-1].copy() if flip_y else c
+
+
 def have_ref() -> bool:
     return os.path.exists(REF_SO)
 

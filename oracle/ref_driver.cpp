@@ -31,6 +31,7 @@
 #include "image.h"
 #include "render_kernel.h"
 #include "utils.h"
+#include "image_io.h"
 #include "bvh_tests.h"
 
 namespace {
@@ -408,6 +409,14 @@ uint32_t refo_xorshift(uint32_t seed, int n_warmup, int n, float* out)
     uint32_t state_after_warmup = g.m_state.a;
     for (int i = 0; i < n; i++) out[i] = g();
     return state_after_warmup;
+}
+
+// the reference's own output stage: write_image_png (source/image_io.cpp:165-182) of a caller-supplied RGBA float image
+int refo_write_png(const float* rgba, int w, int h, const char* path, int flip_y)
+{
+    Image img(w, h);
+    for (int i = 0; i < w * h; i++) img[i] = Color(rgba[4 * i], rgba[4 * i + 1], rgba[4 * i + 2], rgba[4 * i + 3]);
+    return write_image_png(img, path, flip_y != 0) ? 0 : 1;
 }
 
 // octree statistics (diagnostics only)

@@ -168,6 +168,15 @@ def compute_env_map_cdf(skysphere: "Image | np.ndarray") -> np.ndarray:
     return np.cumsum(lum, dtype=np.float32)          # add.accumulate in float32 == the reference's serial loop
 
 
+def quantise_rgba8(image, flip_y: bool = True) -> np.ndarray:
+    """write_image_png's quantisation (image_io.cpp:165-182) on the GPU: (h, w, 4) float32 -> (h, w, 4) uint8."""
+    img = _f32(image)
+    h, w = img.shape[:2]
+    out = np.empty((h, w, 4), np.uint8)
+    B.check(B.load_library().b200rt_quantise_rgba8(B.fptr(img), w, h, 1 if flip_y else 0, out.ctypes.data_as(C.POINTER(C.c_ubyte))))
+    return out
+
+
 # ---- BVH / FlattenedBVH ---------------------------------------------------------------------------------------------------
 class BVH:
     """BVH(std::vector<Triangle>*) (bvh.cpp:19-37). Holds the host-side flattened tree built by the C library."""

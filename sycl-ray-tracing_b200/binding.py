@@ -61,7 +61,7 @@ EXPORTS = [
     "b200rt_bvh_destroy", "b200rt_scene_create", "b200rt_scene_destroy", "b200rt_scene_set_materials", "b200rt_scene_build_env_alias",
     "b200rt_scene_get_bvh_info", "b200rt_scene_device_bytes", "b200rt_default_render_options", "b200rt_render",
     "b200rt_trace_primary", "b200rt_trace_rays", "b200rt_tiles_for_rank", "b200rt_render_tiles_device",
-    "b200rt_untile_device", "b200rt_trace_primary_device", "b200rt_trace_rays_device", "b200rt_last_error", "b200rt_version",
+    "b200rt_untile_device", "b200rt_trace_primary_device", "b200rt_trace_rays_device", "b200rt_quantise_rgba8", "b200rt_quantise_rgba8_device", "b200rt_last_error", "b200rt_version",
 ]
 
 _lib = None
@@ -92,6 +92,8 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     L.b200rt_scene_destroy.restype = None
     L.b200rt_scene_set_materials.argtypes = [VP, FP, I]
     L.b200rt_scene_build_env_alias.argtypes = [VP]
+    L.b200rt_quantise_rgba8.argtypes = [FP, I, I, I, C.POINTER(C.c_ubyte)]
+    L.b200rt_quantise_rgba8_device.argtypes = [VP, I, I, I, VP, VP]
     L.b200rt_scene_get_bvh_info.argtypes = [VP, C.POINTER(BvhInfo)]
     L.b200rt_scene_device_bytes.argtypes = [VP]
     L.b200rt_scene_device_bytes.restype = C.c_size_t

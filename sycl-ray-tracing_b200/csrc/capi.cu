@@ -700,6 +700,34 @@ int b200rt_render(b200rt_scene* s, const float* camera17, int w, int h, int spp,
     return B200RT_OK;
 }
 
+int b200rt_quantise_rgba8_device(const void* dev_image_rgba, int w, int h, int flip_y, void* dev_out_rgba8, void* cuda_stream)
+{
+    if (!dev_image_rgba || !dev_out_rgba8 || w <= 0 || h <= 0) return fail(B200RT_ERR_ARG, "bad quantise arguments");
+    CU(launch_quantise_rgba8((const float4*)dev_image_rgba, w, h, flip_y, dev_out_rgba8, (cudaStream_t)cuda_stream));
+    return B200RT_OK;
+}
+
+int b200rt_quantise_rgba8(const float* image_rgba, int w, int h, int flip_y, unsigned char* out_rgba8)
+{
+    if (!image_rgba || !out_rgba8 || w <= 0 || h <= 0) return fail(B200RT_ERR_ARG, "bad quantise arguments");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) return fail(B200RT_ERR_CUDA, "no CUDA device: b200rt has no CPU fallback");
+    const size_t px = (size_t)w * h;
+    float4* d_in = nullptr; void* d_out = nullptr;
+    cudaError_t e = cudaSuccess;
+    do
+    {
+        if ((e = cudaMalloc(&d_in, px * sizeof(float4))) != cudaSuccess) break;
+        if ((e = cudaMalloc(&d_out, px * 4)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(d_in, image_rgba, px * sizeof(float4), cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = launch_quantise_rgba8(d_in, w, h, flip_y, d_out, 0)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(out_rgba8, d_out, px * 4, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+    } while (0);
+    cudaFree(d_in); cudaFree(d_out);
+    if (e != cudaSuccess) return fail(B200RT_ERR_CUDA, "quantise_rgba8: %s", cudaGetErrorString(e));
+    return B200RT_OK;
+}
+
 int b200rt_trace_primary_device(b200rt_scene* s, const float* camera17, int w, int h, int sample, int spp_for_seed,
                                 void* dev_prim, void* dev_t, const b200rt_render_options* opts, void* cuda_stream, b200rt_stats* stats)
 {

@@ -254,6 +254,25 @@ __global__ void __launch_bounds__(256) k_untile(const float4* __restrict__ tiles
     image[(size_t)y * w + x] = tiles[src];
 }
 
+// ---- output stage: the quantisation loop of write_image_png (source/image_io.cpp:165-182), 16 B in -> 4 B out per pixel -----
+// Color pixel = image(i) * 255; tmp = clamp(pixel, 0, 255) -> unsigned char (truncation); flipY puts image row 0 (bottom) last.
+__device__ __forceinline__ unsigned int quantise_channel(float v)
+{
+    const float p = v * 255.0f;
+    const float c = p < 0.0f ? 0.0f : (p > 255.0f ? 255.0f : p);       // clamp() of image_io.cpp:157-162 (a NaN falls through)
+    return (unsigned int)__float2int_rz(c) & 0xffu;
+}
+__global__ void __launch_bounds__(256) k_quantise_rgba8(const float4* __restrict__ image, int w, int h, int flip_y, uchar4* __restrict__ out)
+{
+    const int x = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int y = blockIdx.y * 8 + (threadIdx.x >> 5);
+    if (x >= w || y >= h) return;
+    const float4 p = image[(size_t)y * w + x];
+    const int oy = flip_y ? h - 1 - y : y;
+    out[(size_t)oy * w + x] = make_uchar4((unsigned char)quantise_channel(p.x), (unsigned char)quantise_channel(p.y),
+                                          (unsigned char)quantise_channel(p.z), (unsigned char)quantise_channel(p.w));
+}
+
 // ---- launchers ----------------------------------------------------------------------------------------------------------------
 static int g_sm_count = 0;
 static int sm_count()
@@ -310,6 +329,14 @@ cudaError_t launch_trace_rays(const SceneDev& S, const float* rays6, int n, int 
     if (tl == TL_WIDE) k_trace_rays<TL_WIDE><<<grid, 256, 0, stream>>>(S, rays6, n, any_hit, prim_out, t_out, extra8);
     else if (tl == TL_DIAG) k_trace_rays<TL_DIAG><<<grid, 256, 0, stream>>>(S, rays6, n, any_hit, prim_out, t_out, extra8);
     else k_trace_rays<TL_AXIS><<<grid, 256, 0, stream>>>(S, rays6, n, any_hit, prim_out, t_out, extra8);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_quantise_rgba8(const float4* image, int w, int h, int flip_y, void* out_rgba8, cudaStream_t stream)
+{
+    if (w <= 0 || h <= 0) return cudaSuccess;
+    dim3 grid((w + 31) / 32, (h + 7) / 8);
+    k_quantise_rgba8<<<grid, 256, 0, stream>>>(image, w, h, flip_y, (uchar4*)out_rgba8);
     return cudaGetLastError();
 }
 

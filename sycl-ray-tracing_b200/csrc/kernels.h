@@ -26,6 +26,8 @@ cudaError_t launch_trace_rays(const SceneDev& S, const float* rays6, int n, int 
 cudaError_t launch_untile(const float4* tiles, int tiles_per_rank_padded, int world, int only_rank, int w, int h, float4* image,
                           cudaStream_t stream);
 
+cudaError_t launch_quantise_rgba8(const float4* image, int w, int h, int flip_y, void* out_rgba8, cudaStream_t stream);
+
 // wavefront integrator (wavefront.cu): runs the whole frame for this rank's tiles as n_groups independent interleaved
 // tile groups, each on its own stream; `stream` is forked from and joined back into
 cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGroup* groups, int n_groups, const float4* fb_in_rowmajor,

@@ -406,3 +406,13 @@ def test_device_built_bvh_c2_full_size(rt):
     p8, t8, _ = sc_d.trace_primary(c2["camera"], 1920, 1080, flags=rt.FLAG_BVH8)
     assert np.array_equal(p8, ph) and np.array_equal(bits(t8), bits(th))
     print(f"device build {info['build_seconds']:.3f} s vs host {sc_h.bvh_info()['build_seconds']:.3f} s")
+
+
+# ---- output stage ------------------------------------------------------------------------------------------
+def test_quantise_rgba8_matches_reference_png(rt):
+    """b200rt_quantise_rgba8 against the bytes the reference's own write_image_png put into a PNG (tests/golden/quantise.npz,
+    made by make_golden_quantise.py): bit-exact, both flip settings, clamp edge values included."""
+    g = load_golden("quantise.npz")
+    for flip in (1, 0):
+        out = rt.quantise_rgba8(g["image"], flip_y=bool(flip))
+        assert out.dtype == np.uint8 and np.array_equal(out, g[f"rgba8_flip{flip}"]), flip
