@@ -277,7 +277,7 @@ def main():
             dist.all_reduce(rays_t)
         rays_per_frame = int(rays_t.item())
         del tiles_probe
-        kernel_name = "k_pathtrace_mega" if args.integrator == 0 else "wf_trace (+ wf_shade), all launches of the frame"
+        kernel_name = "k_pathtrace_mega" if args.integrator == 0 else "wf_trace_coop + wf_shade, all launches of the frame"
         launches_per_step = int(st["gpu_launches"]) + (1 if rank == 0 else 0)
 
     for _ in range(args.warmup):
@@ -335,6 +335,21 @@ def main():
     peak, peak_src = measured_peak()
     rays_per_launch = rays_per_frame / world
     achieved = rays_per_launch * bytes_per_ray / (kernel_ms * 1e-3) / 1e9
+
+    # the dominant kernel by itself: one more frame with every trace / shade launch bracketed by CUDA events on its launching
+    # stream (B200RT_FLAG_TIME_KERNELS; the tile groups then run one after the other, so this frame is slower than a timed step)
+    dominant = None
+    if not primary_only and args.integrator == 1:
+        flush.fill_(7)
+        kst = scene.render_tiles_device(cam, w, h, spp, bounces, probe.data_ptr(), stream_ptr=torch.cuda.current_stream(device).cuda_stream,
+                                        integrator=args.integrator, flags=args.flags | rt.FLAG_TIME_KERNELS, rank=rank, world=world, want_stats=True)
+        if kst["trace_launches"] > 0 and kst["trace_ms"] > 0:
+            t_ach = kst["rays"] * bytes_per_ray / (kst["trace_ms"] * 1e-3) / 1e9
+            dominant = {"kernel": "wf_trace_coop" if not (args.flags & (rt.FLAG_BVH2 | rt.FLAG_DIAG_SLABS | rt.FLAG_SIMPLE_TRACE)) else "wf_trace",
+                        "launches": kst["trace_launches"], "avg_launch_ms": kst["trace_ms"] / kst["trace_launches"],
+                        "rays_per_launch": kst["rays"] / kst["trace_launches"], "achieved": t_ach, "frac": t_ach / peak,
+                        "share_of_kernel_time": kst["trace_ms"] / (kst["trace_ms"] + kst["shade_ms"]),
+                        "shade_avg_launch_ms": kst["shade_ms"] / max(1, kst["shade_launches"])}
 
     # end to end through the public host API: host buffers in, host framebuffer out, copies inside the timed region
     e2e = None
@@ -422,7 +437,7 @@ def main():
                        "integrator": "megakernel" if args.integrator == 0 else "wavefront", "flags": args.flags,
                        "partition": f"interleaved 16x16 tiles over {world} rank(s), scene replicated, NCCL gather to rank 0",
                        "l2": "256 MiB buffer written between timed iterations (L2 flush)",
-                       "bvh": {k: info[k] for k in ("n_inner_nodes", "n_leaves", "max_depth", "has_diag_slabs")},
+                       "bvh": {k: info[k] for k in ("n_inner_nodes", "n_leaves", "max_depth", "has_diag_slabs", "n_wide_nodes", "wide_max_depth")},
                        "scene_build_s": build_s, "scene_device_bytes": scene.device_bytes()},
             "skip_dead_rays": dead, "verified_equal_to_1_rank": verified,
             "clocks": sampler.result(),
@@ -430,7 +445,7 @@ def main():
             "gpu_launches": launches_per_step * args.steps,
             "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": (profile_traffic(args.workload) / world) if profile_traffic(args.workload) else None, "bytes_per_ray": bytes_per_ray, "rays_per_launch": rays_per_launch,
-                         "kernel_ms": kernel_ms, "peak_source": peak_src},
+                         "kernel_ms": kernel_ms, "peak_source": peak_src, "dominant_kernel": dominant},
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)

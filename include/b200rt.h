@@ -123,6 +123,8 @@ size_t b200rt_scene_device_bytes(const b200rt_scene* scene);
 
 #define B200RT_FLAG_BVH8 64              /* b200rt_trace_primary: use the 8-ary layout too (coherent camera rays default to the binary one, which is
                                             faster for them; every other entry point already defaults to the 8-ary layout) */
+#define B200RT_FLAG_TIME_KERNELS 128     /* wavefront: bracket every trace and shade launch with CUDA events and report the sums in b200rt_stats
+                                            (the tile groups then run one after the other: a measurement mode, slower than the default) */
 #define B200RT_FLAG_ENV_ALIAS 32         /* sample_environment_map's texel pick (render_kernel.cpp:532-567, two dependent binary searches over the float
                                             running-sum CDF, ~21 dependent loads) is replaced by one alias-table lookup with the same single RNG draw.
                                             Same per-texel probability lum/total in exact arithmetic, different draw -> texel map: the image agrees
@@ -143,6 +145,9 @@ typedef struct b200rt_stats
     double total_ms;                /* including host<->device copies done by this call */
     int gpu_launches;               /* kernels launched by this call */
     unsigned long long h2d_bytes, d2h_bytes;
+    /* only with B200RT_FLAG_TIME_KERNELS (wavefront integrator): CUDA-event time of every trace / shade launch, summed */
+    double trace_ms, shade_ms;
+    int trace_launches, shade_launches;
 } b200rt_stats;
 
 void b200rt_default_render_options(b200rt_render_options* opts);

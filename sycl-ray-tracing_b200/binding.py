@@ -22,6 +22,7 @@ FLAG_SIMPLE_TRACE = 8
 FLAG_BVH2 = 16
 FLAG_ENV_ALIAS = 32
 FLAG_BVH8 = 64
+FLAG_TIME_KERNELS = 128
 TILE_DIM = 16
 TILE_PIXELS = 256
 
@@ -49,7 +50,8 @@ class RenderOptions(C.Structure):
 
 class Stats(C.Structure):
     _fields_ = [("rays", C.c_ulonglong), ("samples", C.c_ulonglong), ("kernel_ms", C.c_double), ("total_ms", C.c_double),
-                ("gpu_launches", C.c_int), ("h2d_bytes", C.c_ulonglong), ("d2h_bytes", C.c_ulonglong)]
+                ("gpu_launches", C.c_int), ("h2d_bytes", C.c_ulonglong), ("d2h_bytes", C.c_ulonglong),
+                ("trace_ms", C.c_double), ("shade_ms", C.c_double), ("trace_launches", C.c_int), ("shade_launches", C.c_int)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}

@@ -44,6 +44,7 @@ struct b200rt_scene
     float2* d_alias = nullptr; float alias_total = 0.0f;
     void* bvh_window = nullptr; size_t bvh_window_bytes = 0;   // 8-ary nodes + triangles, kept resident in L2 (see pin_bvh_in_l2)
     bool l2_pinned = false, l2_window_set = false;
+    double kernel_times[4] = {};          // B200RT_FLAG_TIME_KERNELS: trace ms, shade ms, trace launches, shade launches of the last render
 };
 
 namespace {
@@ -248,6 +249,7 @@ int pin_bvh_in_l2(b200rt_scene* s, cudaStream_t extra)
 // runs the selected integrator for this rank's tiles on `st`; *launches receives the number of kernels launched
 int run_integrator(b200rt_scene* s, const RenderParams& P, int integrator, const float4* fb_in, float4* out_tiles, cudaStream_t st, int* launches)
 {
+    s->kernel_times[0] = s->kernel_times[1] = s->kernel_times[2] = s->kernel_times[3] = 0.0;
     SceneDev dev = s->dev;
     if (P.flags & B200RT_FLAG_ENV_ALIAS)
     {
@@ -260,7 +262,7 @@ int run_integrator(b200rt_scene* s, const RenderParams& P, int integrator, const
         int rc = ensure_wavefront(s, P);
         if (rc) return rc;
         if (!s->l2_window_set) { if ((rc = pin_bvh_in_l2(s, nullptr))) return rc; s->l2_window_set = true; }
-        CU(run_wavefront(dev, P, s->wf, s->wf_groups, fb_in, out_tiles, st, s->fork_event, launches));
+        CU(run_wavefront(dev, P, s->wf, s->wf_groups, fb_in, out_tiles, st, s->fork_event, launches, s->kernel_times));
         CU(wavefront_sum_rays(s->wf, s->wf_groups, s->d_rays, st));
         *launches += 1;
         return B200RT_OK;
@@ -630,6 +632,8 @@ int b200rt_render_tiles_device(b200rt_scene* s, const float* camera17, int w, in
         std::memset(stats, 0, sizeof(*stats));
         CU(cudaMemcpy(&stats->rays, s->d_rays, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         stats->kernel_ms = ms; stats->total_ms = ms; stats->gpu_launches = launches;
+        stats->trace_ms = s->kernel_times[0]; stats->shade_ms = s->kernel_times[1];
+        stats->trace_launches = (int)s->kernel_times[2]; stats->shade_launches = (int)s->kernel_times[3];
         // pixels of this rank that lie inside the frame
         unsigned long long px = 0;
         for (int k = 0; k < P.n_rank_tiles; k++)
@@ -693,6 +697,8 @@ int b200rt_render(b200rt_scene* s, const float* camera17, int w, int h, int spp,
         }
         stats->samples = px * (unsigned long long)spp;
         stats->kernel_ms = ms;
+        stats->trace_ms = s->kernel_times[0]; stats->shade_ms = s->kernel_times[1];
+        stats->trace_launches = (int)s->kernel_times[2]; stats->shade_launches = (int)s->kernel_times[3];
         stats->gpu_launches = launches + 1;
         stats->h2d_bytes = h2d; stats->d2h_bytes = d2h;
         stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();

@@ -31,7 +31,7 @@ cudaError_t launch_quantise_rgba8(const float4* image, int w, int h, int flip_y,
 // wavefront integrator (wavefront.cu): runs the whole frame for this rank's tiles as n_groups independent interleaved
 // tile groups, each on its own stream; `stream` is forked from and joined back into
 cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGroup* groups, int n_groups, const float4* fb_in_rowmajor,
-                          float4* out_tiles, cudaStream_t stream, cudaEvent_t fork_event, int* launches_out);
+                          float4* out_tiles, cudaStream_t stream, cudaEvent_t fork_event, int* launches_out, double* kernel_times4 = nullptr);
 cudaError_t wavefront_sum_rays(const WfGroup* groups, int n_groups, unsigned long long* total, cudaStream_t stream);
 
 } // namespace b200rt

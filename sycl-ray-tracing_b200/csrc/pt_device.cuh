@@ -624,7 +624,19 @@ __device__ __forceinline__ float ct_pdf(const MaterialDev& m, v3 view, v3 to_lig
     return D * NoH / (4.0f * VoH);
 }
 
-__device__ __forceinline__ col ct_terms(const MaterialDev& m, float NoV, float NoL, float NoH, float VoH, float* pdf_out)   // :272-298 / :424-448
+// B200RT_CT_NOINLINE: the BRDF evaluation / sampling bodies become real functions (5 + 3 call sites per surface interaction):
+// the shade kernel shrinks and stalls less on instruction fetch
+#ifdef B200RT_CT_NOINLINE
+#define B200RT_CT_INLINE static __noinline__
+#else
+#define B200RT_CT_INLINE __forceinline__
+#endif
+#if defined(B200RT_CT_NOINLINE) && B200RT_CT_NOINLINE >= 2
+#define B200RT_CT_INLINE2 static __noinline__
+#else
+#define B200RT_CT_INLINE2 __forceinline__
+#endif
+__device__ B200RT_CT_INLINE2 col ct_terms(const MaterialDev& m, float NoV, float NoL, float NoH, float VoH, float* pdf_out)   // :272-298 / :424-448
 {
     const float metalness = m.metalness;
     const float alpha = m.roughness * m.roughness;
@@ -655,7 +667,7 @@ __device__ __forceinline__ col ct_brdf(const MaterialDev& m, v3 to_light, v3 vie
 }
 
 // cook_torrance_brdf_importance_sample :392-451 — consumes exactly two draws
-__device__ __forceinline__ col ct_sample(const MaterialDev& m, v3 view, v3 n, v3& out_dir, float& pdf, uint32_t& rng)
+__device__ B200RT_CT_INLINE col ct_sample(const MaterialDev& m, v3 view, v3 n, v3& out_dir, float& pdf, uint32_t& rng)
 {
     pdf = 0.0f;
     const float alpha = m.roughness * m.roughness;

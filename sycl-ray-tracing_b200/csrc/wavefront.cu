@@ -657,7 +657,7 @@ __global__ void __launch_bounds__(32 * kCoopMaxWarps, WF_COOP_MIN_BLOCKS) wf_tra
 static int g_wf_sm_count = 0;
 
 cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGroup* groups, int n_groups, const float4* fb_in_rowmajor,
-                          float4* out_tiles, cudaStream_t stream, cudaEvent_t fork_event, int* launches_out)
+                          float4* out_tiles, cudaStream_t stream, cudaEvent_t fork_event, int* launches_out, double* kernel_times4)
 {
     if (!g_wf_sm_count)
     {
@@ -681,7 +681,9 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, trace_kernel, tb, 0);
     if (per_sm <= 0) per_sm = 1;
     const int trace_grid = g_wf_sm_count * per_sm;
-    static const bool timing = getenv("B200RT_WF_TIMING") != nullptr;      // diagnostics: per-kernel times on stderr (serialises the groups)
+    static const bool timing_env = getenv("B200RT_WF_TIMING") != nullptr;  // diagnostics: per-kernel times on stderr (serialises the groups)
+    const bool timing = timing_env || (P.flags & B200RT_FLAG_TIME_KERNELS);
+    int n_trace = 0, n_shade = 0;
     cudaError_t e;
 
     // fork: every group stream starts after the work already queued on the caller's stream
@@ -749,8 +751,8 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
                 cudaEventElapsedTime(&a, tev[0], tev[1]); cudaEventElapsedTime(&b, tev[1], tev[2]);
                 unsigned int nq[8];
                 cudaMemcpy(nq, G.buf.counters, sizeof(nq), cudaMemcpyDeviceToHost);
-                t_trace += a; t_shade += b;
-                fprintf(stderr, "wf g%d it %lld: trace %.3f ms  shade %.3f ms  active px %u  next queue %u\n", g, R.it, a, b, nq[2], nq[3 + R.parity]);
+                t_trace += a; t_shade += b; n_trace++; n_shade++;
+                if (timing_env) fprintf(stderr, "wf g%d it %lld: trace %.3f ms  shade %.3f ms  active px %u  next queue %u\n", g, R.it, a, b, nq[2], nq[3 + R.parity]);
             }
             R.it++;
             if (!R.poll_pending && ((R.it & 3) == 0 || R.it >= max_iters))
@@ -772,7 +774,8 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
     }
     if (timing)
     {
-        fprintf(stderr, "wf total: trace %.3f ms  shade %.3f ms  launches %d\n", t_trace, t_shade, launches);
+        if (timing_env) fprintf(stderr, "wf total: trace %.3f ms  shade %.3f ms  launches %d\n", t_trace, t_shade, launches);
+        if (kernel_times4) { kernel_times4[0] = t_trace; kernel_times4[1] = t_shade; kernel_times4[2] = n_trace; kernel_times4[3] = n_shade; }
         for (int i = 0; i < 3; i++) cudaEventDestroy(tev[i]);
     }
     if (launches_out) *launches_out = launches;

@@ -140,6 +140,10 @@ def test_render_matches_reference_framebuffer(rt, golden_scenes, golden_cameras,
     assert abs(s["mean_gpu"] - s["mean_ref"]) <= 0.005 * max(s["mean_ref"], 1e-6), s
     assert s["nan_gpu"] == s["nan_ref"], "the reference's own NaN pixels (quirk 6) must reproduce"
     assert st["rays"] > 0 and st["gpu_launches"] >= 2
+    # both traversal layouts: identical frames, NaN pixels included
+    for flags in (rt.FLAG_BVH8, rt.FLAG_BVH2):
+        other, st2 = sc.render(cam(rt, golden_cameras, CAM_OF[key]), w, h, spp, b, flags=flags)
+        assert np.array_equal(bits(img), bits(other)) and st2["rays"] == st["rays"], flags
 
 
 def test_render_c3_small_matches_reference(rt, golden_cameras):
@@ -187,12 +191,14 @@ def test_flags_do_not_change_the_image(rt, golden_scenes, golden_cameras):
     assert np.array_equal(bits(base), bits(skip))
     assert st1["rays"] == st0["rays"], "cornell has emissive materials: nothing is dead"
     # every traversal layout / trace kernel finds the same exact closest hits -> the same image and the same ray count
-    for name, flags in (("binary BVH", rt.FLAG_BVH2), ("8-ary BVH, one ray per lane", rt.FLAG_SIMPLE_TRACE),
-                        ("binary BVH, one ray per lane", rt.FLAG_BVH2 | rt.FLAG_SIMPLE_TRACE)):
+    for name, flags in (("binary BVH", rt.FLAG_BVH2), ("8-ary BVH, cooperative kernel", rt.FLAG_BVH8),
+                        ("8-ary BVH, one ray per lane", rt.FLAG_BVH8 | rt.FLAG_SIMPLE_TRACE),
+                        ("binary BVH, one ray per lane", rt.FLAG_BVH2 | rt.FLAG_SIMPLE_TRACE),
+                        ("per-kernel timing mode", rt.FLAG_TIME_KERNELS)):
         img, st = sc.render(c, 96, 80, 4, 5, flags=flags)
         assert np.array_equal(bits(base), bits(img)), name
         assert st["rays"] == st0["rays"], name
-    for name, flags in (("binary", rt.FLAG_BVH2), ("8-ary", 0)):
+    for name, flags in (("binary", rt.FLAG_BVH2), ("8-ary", rt.FLAG_BVH8)):
         mega, stm = sc.render(c, 96, 80, 4, 5, integrator=rt.INTEGRATOR_MEGAKERNEL, flags=flags)
         assert np.array_equal(bits(base), bits(mega)) and stm["rays"] == st0["rays"], name
 
@@ -291,6 +297,10 @@ def test_wavefront_equals_megakernel_bit_for_bit(rt, golden_scenes, golden_camer
     wave, st_w = sc.render(c, w, h, spp, b, integrator=rt.INTEGRATOR_WAVEFRONT)
     assert np.array_equal(bits(mega), bits(wave)), f"{(bits(mega) != bits(wave)).sum()} differing words"
     assert st_m["rays"] == st_w["rays"] and st_w["gpu_launches"] > 3
+    # the binary layout's phase-vote kernel and the 8-ary cooperative kernel (named explicitly), spheres included
+    for flags in (rt.FLAG_BVH8, rt.FLAG_BVH2):
+        wave8, st_8 = sc.render(c, w, h, spp, b, integrator=rt.INTEGRATOR_WAVEFRONT, flags=flags)
+        assert np.array_equal(bits(mega), bits(wave8)) and st_8["rays"] == st_m["rays"], flags
     s = image_stats(wave, g["image"])
     assert s["frac_close"] >= 0.99 and s["rmse"] <= 5.0e-3, s
 
