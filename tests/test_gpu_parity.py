@@ -426,3 +426,74 @@ def test_quantise_rgba8_matches_reference_png(rt):
     for flip in (1, 0):
         out = rt.quantise_rgba8(g["image"], flip_y=bool(flip))
         assert out.dtype == np.uint8 and np.array_equal(out, g[f"rgba8_flip{flip}"]), flip
+
+
+def _brute_force_closest(tri, rays):
+    """numpy Moller-Trumbore over every triangle (triangle.h:16-60 in float32, strict '<' with ties to the lower index)."""
+    f32 = np.float32
+    a = tri[:, 0:3]; e1 = (tri[:, 3:6] - a).astype(f32); e2 = (tri[:, 6:9] - a).astype(f32)
+    best_t = np.full(len(rays), -1.0, f32); best_p = np.full(len(rays), -1, np.int32)
+    for r, (o, d) in enumerate(zip(rays[:, :3], rays[:, 3:])):
+        h = np.stack([d[1] * e2[:, 2] - d[2] * e2[:, 1], d[2] * e2[:, 0] - d[0] * e2[:, 2], d[0] * e2[:, 1] - d[1] * e2[:, 0]], 1).astype(f32)
+        det = ((e1[:, 0] * h[:, 0]).astype(f32) + (e1[:, 1] * h[:, 1]).astype(f32) + (e1[:, 2] * h[:, 2]).astype(f32)).astype(f32)
+        ok = ~((det > -1e-7) & (det < 1e-7))
+        with np.errstate(divide="ignore", invalid="ignore"):
+            f = (f32(1.0) / det).astype(f32)
+            s_ = (o - a).astype(f32)
+            u = (f * ((s_[:, 0] * h[:, 0]).astype(f32) + (s_[:, 1] * h[:, 1]).astype(f32) + (s_[:, 2] * h[:, 2]).astype(f32)).astype(f32)).astype(f32)
+            ok &= ~((u < 0) | (u > 1))
+            q = np.stack([s_[:, 1] * e1[:, 2] - s_[:, 2] * e1[:, 1], s_[:, 2] * e1[:, 0] - s_[:, 0] * e1[:, 2], s_[:, 0] * e1[:, 1] - s_[:, 1] * e1[:, 0]], 1).astype(f32)
+            v = (f * ((d[0] * q[:, 0]).astype(f32) + (d[1] * q[:, 1]).astype(f32) + (d[2] * q[:, 2]).astype(f32)).astype(f32)).astype(f32)
+            ok &= ~((v < 0) | ((u + v).astype(f32) > 1))
+            t = (f * ((e2[:, 0] * q[:, 0]).astype(f32) + (e2[:, 1] * q[:, 1]).astype(f32) + (e2[:, 2] * q[:, 2]).astype(f32)).astype(f32)).astype(f32)
+        ok &= t > 1e-7
+        if ok.any():
+            tt = np.where(ok, t, np.inf)
+            i = int(np.argmin(tt))            # first (= lowest index) of the minima
+            best_t[r] = tt[i]; best_p[r] = i
+    return best_p, best_t
+
+
+@pytest.mark.parametrize("on_device", [False, True])
+def test_degenerate_and_awkward_inputs_closest_hit(rt, on_device):
+    """Triangle soups that stress both builders and both layouts — duplicates, zero-area and needle triangles, huge next to
+    tiny, all centroids equal, axis-parallel rays through shared vertices — against a numpy brute force of the reference's
+    triangle test. Hit / miss and the primitive index must agree exactly; t bit for bit where numpy's float32 evaluation
+    order matches (it does: same operations, no fused multiply-adds on either side)."""
+    rng = np.random.default_rng(17)
+    mats = np.array([[1, 0, 1, 1, 0, 0, 0, 1, 0, 1], [0, 0, 0, 1, .8, .8, .8, 1, 0, 1]], np.float32)
+    soups = {
+        "random_soup": rng.random((3000, 9)).astype(np.float32) * 4 - 2,
+        "duplicates": np.repeat(rng.random((7, 9)).astype(np.float32) * 2 - 1, 40, axis=0),
+        "degenerate_mix": np.concatenate([rng.random((500, 9)).astype(np.float32) * 2 - 1,
+                                          np.repeat(rng.random((100, 3)).astype(np.float32), 3, axis=1).reshape(100, 9),        # zero-area (a = b = c)
+                                          np.concatenate([rng.random((100, 6)), rng.random((100, 3)) * 1e-6], 1).astype(np.float32)]),
+        "huge_and_tiny": np.concatenate([rng.random((200, 9)).astype(np.float32) * 2000 - 1000, rng.random((800, 9)).astype(np.float32) * 0.02 - 0.01]),
+        "grid_axis_aligned": np.array([[x, y, 0, x + 1, y, 0, x, y + 1, 0] for x in range(-8, 8) for y in range(-8, 8)]
+                                      + [[x + 1, y, 0, x + 1, y + 1, 0, x, y + 1, 0] for x in range(-8, 8) for y in range(-8, 8)], np.float32),
+    }
+    for name, tri in soups.items():
+        if on_device and len(tri) <= 3:
+            continue
+        bvh = rt.BVH(tri, on_device=on_device)
+        bvh.check()
+        sc = rt.Scene(tri, np.ones(len(tri), np.int32), mats, np.zeros(0, np.int32), bvh=bvh)
+        n = 600
+        o = (rng.random((n, 3)).astype(np.float32) * 6 - 3)
+        d = rng.normal(size=(n, 3)).astype(np.float32)
+        d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+        rays = np.concatenate([o, d], 1).astype(np.float32)
+        # axis-parallel rays, some exactly through grid vertices / shared edges
+        extra = np.array([[0, 0, 5, 0, 0, -1], [1, 1, 5, 0, 0, -1], [0.5, 0.5, 5, 0, 0, -1], [-3, 2, -4, 0, 0, 1], [0.25, -7.75, 1, 0, 0, -1],
+                          [5, 0.5, 0, -1, 0, 0], [0, 0, 0, 1, 0, 0]], np.float32)
+        rays = np.concatenate([rays, extra])
+        bp, bt = _brute_force_closest(tri, rays)
+        for flags in (0, rt.FLAG_BVH2):
+            prim, t, _ = sc.trace_rays(rays, flags=flags)
+            assert np.array_equal(prim >= 0, bp >= 0), (name, flags, "hit/miss")
+            assert np.array_equal(bits(np.where(prim >= 0, t, 0)), bits(np.where(bp >= 0, bt, 0))), (name, flags, "t")
+            same = prim == bp
+            # exact-t ties between different triangles (duplicates, shared edges): the lowest index wins, as in the brute force
+            assert same.all(), (name, flags, int((~same).sum()))
+        any_p, _, _ = sc.trace_rays(rays, any_hit=True)
+        assert np.array_equal(any_p == 1, bp >= 0), (name, "any-hit")
