@@ -1,0 +1,14 @@
+"""Emulates one rank of an N-GPU frame on a single GPU (development tool): rank 0's interleaved tiles of a world of
+WORLD (default 8), C3 at SPP (default 64). The per-rank kernel time is what bounds the N-GPU frame."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import sycl_ray_tracing_b200 as rt
+from sycl_ray_tracing_b200 import scenes
+world = int(os.environ.get("WORLD", "8")); spp = int(os.environ.get("SPP", "64"))
+c3 = scenes.c3_scene()
+sc = rt.Scene(c3["tri9"], c3["mat_idx"], c3["mats10"], c3["emissive"], skysphere=c3["env"])
+fb = rt.Image(1920, 1080).pixels
+sc.render(c3["camera"], 1920, 1080, 1, 8, framebuffer=fb, rank=0, world=world)
+for rep in range(3):
+    img, st = sc.render(c3["camera"], 1920, 1080, spp, 8, framebuffer=fb, rank=0, world=world)
+    print("world", world, "spp", spp, "kernel_ms %.2f" % st["kernel_ms"], "launches", st["gpu_launches"], "rays", st["rays"], file=sys.stderr)
