@@ -102,6 +102,7 @@ enum TraceMode { TRACE_CLOSEST = 0, TRACE_ANY = 1, TRACE_SHADOW = 2 };
 struct RaySlabs
 {
     float ix, iy, iz;        // clamped reciprocals of the direction
+    float ox, oy, oz;        // origin * reciprocal: slab distance = fma(plane, i, -o) (one FFMA; conservative within the builder's pad)
     float rc[4], na[4], nb[4];
 };
 
@@ -113,6 +114,7 @@ __device__ __forceinline__ float safe_rcp(float d)
 __device__ __forceinline__ void setup_slabs(v3 o, v3 d, bool use_diag, RaySlabs& rs)
 {
     rs.ix = safe_rcp(d.x); rs.iy = safe_rcp(d.y); rs.iz = safe_rcp(d.z);
+    rs.ox = o.x * rs.ix; rs.oy = o.y * rs.iy; rs.oz = o.z * rs.iz;
     if (use_diag)
     {
         // diagonal planes (+-1, +-1, 1) (the reference's PLANE_NORMALS[3..6] without the common sqrt(3)/3, bvh.cpp:8-16)
@@ -217,14 +219,16 @@ __device__ __forceinline__ void trav_inner(const SceneDev& S, Trav& T, TravStack
         const float4* an = S.axis + 4 * (size_t)T.cur;
         const float4 n0 = __ldg(an + 0), n1 = __ldg(an + 1), n2 = __ldg(an + 2), n3 = __ldg(an + 3);
         // L: lo = (n0.x n0.y n0.z) hi = (n0.w n1.x n1.y); R: lo = (n1.z n1.w n2.x) hi = (n2.y n2.z n2.w)
-        float a0 = (n0.x - o.x) * rs.ix, a1 = (n0.w - o.x) * rs.ix;
-        float b0 = (n0.y - o.y) * rs.iy, b1 = (n1.x - o.y) * rs.iy;
-        float c0 = (n0.z - o.z) * rs.iz, c1 = (n1.y - o.z) * rs.iz;
+        // The slab distances only have to be conservative (the exact test is Moller-Trumbore): one fused multiply-add each.
+        // Rounding moves a plane by at most ~2^-23 |o| along its axis, inside the pad the builder put around every volume.
+        float a0 = fmaf(n0.x, rs.ix, -rs.ox), a1 = fmaf(n0.w, rs.ix, -rs.ox);
+        float b0 = fmaf(n0.y, rs.iy, -rs.oy), b1 = fmaf(n1.x, rs.iy, -rs.oy);
+        float c0 = fmaf(n0.z, rs.iz, -rs.oz), c1 = fmaf(n1.y, rs.iz, -rs.oz);
         float tnL = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), 0.0f));
         float tfL = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), tbest));
-        a0 = (n1.z - o.x) * rs.ix; a1 = (n2.y - o.x) * rs.ix;
-        b0 = (n1.w - o.y) * rs.iy; b1 = (n2.z - o.y) * rs.iy;
-        c0 = (n2.x - o.z) * rs.iz; c1 = (n2.w - o.z) * rs.iz;
+        a0 = fmaf(n1.z, rs.ix, -rs.ox); a1 = fmaf(n2.y, rs.ix, -rs.ox);
+        b0 = fmaf(n1.w, rs.iy, -rs.oy); b1 = fmaf(n2.z, rs.iy, -rs.oy);
+        c0 = fmaf(n2.x, rs.iz, -rs.oz); c1 = fmaf(n2.w, rs.iz, -rs.oz);
         float tnR = fmaxf(fmaxf(fminf(a0, a1), fminf(b0, b1)), fmaxf(fminf(c0, c1), 0.0f));
         float tfR = fminf(fminf(fmaxf(a0, a1), fmaxf(b0, b1)), fminf(fmaxf(c0, c1), tbest));
         // distance-proportional widening keeps the float slab test conservative (Ize, "Robust BVH ray traversal")
