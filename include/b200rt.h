@@ -123,8 +123,8 @@ size_t b200rt_scene_device_bytes(const b200rt_scene* scene);
 
 #define B200RT_FLAG_BVH8 64              /* b200rt_trace_primary: use the 8-ary layout too (coherent camera rays default to the binary one, which is
                                             faster for them; every other entry point already defaults to the 8-ary layout) */
-#define B200RT_FLAG_TIME_KERNELS 128     /* wavefront: bracket every trace and shade launch with CUDA events and report the sums in b200rt_stats
-                                            (the tile groups then run one after the other: a measurement mode, slower than the default) */
+#define B200RT_FLAG_TIME_KERNELS 128     /* wavefront: bracket every trace and shade launch with CUDA events and report the sums in the stats
+                                            struct; the tile groups then run one after the other: a measurement mode, slower than the default */
 #define B200RT_FLAG_ENV_ALIAS 32         /* sample_environment_map's texel pick (render_kernel.cpp:532-567, two dependent binary searches over the float
                                             running-sum CDF, ~21 dependent loads) is replaced by one alias-table lookup with the same single RNG draw.
                                             Same per-texel probability lum/total in exact arithmetic, different draw -> texel map: the image agrees

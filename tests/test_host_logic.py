@@ -25,7 +25,8 @@ def test_library_exports_every_declared_symbol(rt):
 
 def test_header_cites_reference_interfaces():
     header = open(os.path.join(ROOT, "include", "b200rt.h")).read()
-    for cite in ("render_kernel.h:24-46", "render_kernel.cpp:189-211", "flattened_bvh.h:25-39", "bvh.cpp:62-65", "utils.cpp:126-142"):
+    for cite in ("render_kernel.h:24-46", "render_kernel.cpp:189-211", "flattened_bvh.h:25-39", "bvh.cpp:62-65", "utils.cpp:126-142",
+                 "image_io.cpp:165-182", "bvh.cpp:19-60", "render_kernel.cpp:532-567"):
         assert cite in header
 
 
@@ -34,6 +35,11 @@ def test_compute_fails_loudly_without_a_gpu(rt, golden_scenes):
     a = scene_arrays(golden_scenes, "cornell")
     with pytest.raises(rt.B200RTError, match="no CUDA device"):
         rt.Scene(a["tri9"], a["mat_idx"], a["mats10"], a["emissive"])
+    # the stages either side of the path have no CPU fallback either
+    with pytest.raises(rt.B200RTError, match="no CUDA device"):
+        rt.BVH(a["tri9"], on_device=True)
+    with pytest.raises(rt.B200RTError, match="no CUDA device"):
+        rt.quantise_rgba8(np.zeros((4, 4, 4), np.float32))
 
 
 @pytest.mark.parametrize("key", ["cornell", "mis", "area"])
