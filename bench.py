@@ -424,6 +424,24 @@ def main():
         except Exception as e:          # the baseline is reported context, never a reason to lose the GPU numbers
             cpu_baseline = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
 
+    # roofline of the dominant kernel (contract): algorithmic bytes per launch / its average launch duration, CUDA events on its
+    # launching stream. Path tracing: wf_trace_coop, every launch of one frame timed alone (B200RT_FLAG_TIME_KERNELS: one tile
+    # group at a time, full persistent grid); "frame" is the same arithmetic over the whole overlapped frame (trace + shade).
+    traffic_total = profile_traffic(args.workload)
+    frame_view = {"kernel": kernel_name, "achieved": achieved, "frac": achieved / peak, "kernel_ms": kernel_ms,
+                  "traffic": (traffic_total / world) if traffic_total else None}
+    if dominant:
+        tpr = profile_traffic(args.workload + "_trace_bytes_per_ray")
+        roofline = {"bound": "hbm", "kernel": dominant["kernel"], "achieved": dominant["achieved"], "peak": peak, "unit": "GB/s",
+                    "frac": dominant["frac"], "traffic": (tpr * dominant["rays_per_launch"]) if tpr else None,
+                    "bytes_per_ray": bytes_per_ray, "launches": dominant["launches"], "avg_launch_ms": dominant["avg_launch_ms"],
+                    "rays_per_launch": dominant["rays_per_launch"], "share_of_kernel_time": dominant["share_of_kernel_time"],
+                    "shade_avg_launch_ms": dominant["shade_avg_launch_ms"], "peak_source": peak_src, "frame": frame_view}
+    else:
+        roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                    "traffic": frame_view["traffic"], "bytes_per_ray": bytes_per_ray, "rays_per_launch": rays_per_launch,
+                    "kernel_ms": kernel_ms, "peak_source": peak_src}
+
     if rank == 0:
         info = scene.bvh_info()
         line = {
@@ -443,9 +461,7 @@ def main():
             "clocks": sampler.result(),
             "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps,
-            "roofline": {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": (profile_traffic(args.workload) / world) if profile_traffic(args.workload) else None, "bytes_per_ray": bytes_per_ray, "rays_per_launch": rays_per_launch,
-                         "kernel_ms": kernel_ms, "peak_source": peak_src, "dominant_kernel": dominant},
+            "roofline": roofline,
             "cpu_baseline": cpu_baseline,
         }
         print(json.dumps(line), flush=True)

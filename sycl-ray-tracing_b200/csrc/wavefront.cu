@@ -685,7 +685,8 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
     // default 58): the rest of every SM stays free for the other groups' trace / shade kernels, which then overlap with the
     // whole pass instead of only with its tail (C3, 32 spp: 2 179 vs 2 108 Mrays/s; 72 %: 2 157, 43 %: 2 112).
     static const int grid_pct_env = []() { const char* e = getenv("B200RT_TRACE_GRID_PCT"); int v = e ? atoi(e) : 0; return v > 100 ? 100 : v; }();
-    const int grid_pct = grid_pct_env >= 10 ? grid_pct_env : (n_groups > 1 ? 58 : 100);
+    const bool timing_mode = getenv("B200RT_WF_TIMING") != nullptr || (P.flags & B200RT_FLAG_TIME_KERNELS);      // kernels run one at a time: full grid
+    const int grid_pct = grid_pct_env >= 10 ? grid_pct_env : ((n_groups > 1 && !timing_mode) ? 58 : 100);
     const int trace_grid = g_wf_sm_count * std::max(1, (per_sm * grid_pct + 50) / 100);
     static const bool timing_env = getenv("B200RT_WF_TIMING") != nullptr;  // diagnostics: per-kernel times on stderr (serialises the groups)
     const bool timing = timing_env || (P.flags & B200RT_FLAG_TIME_KERNELS);
