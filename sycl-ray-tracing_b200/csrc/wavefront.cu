@@ -577,11 +577,18 @@ __global__ void __launch_bounds__(32 * kCoopMaxWarps, WF_COOP_MIN_BLOCKS) wf_tra
             continue;
         }
         // (2) one node step for every lane that has one
-        if (active && !T.done) trav8_node(S, T, K);
+        if (active && !T.done)
+        {
+            trav8_node(S, T, K);
+            // the next node group can be fetched from the stack right away (its load overlaps the queue housekeeping below);
+            // the pending triangle group lives in T.tg / T.tvalid, which the pop does not touch
+            if (!T.done && !(T.ng.y & 0xff000000u)) trav8_pop(T, K);
+        }
         // (3) hit triangles -> the warp's pair queue (draining first when it would overflow); the lane moves on
         for (;;)
         {
             const unsigned int cnt = (active ? __popc(T.tg.y) : 0u);
+            if (!__any_sync(FULL, cnt != 0u)) break;            // node steps near the root hit no leaf child at all: no scan needed
             unsigned int incl = cnt;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1)
@@ -611,7 +618,6 @@ __global__ void __launch_bounds__(32 * kCoopMaxWarps, WF_COOP_MIN_BLOCKS) wf_tra
             if (total <= room) break;
             coop_drain(S, W, lane, qcount, false, pending);
         }
-        if (active && !T.done && !(T.ng.y & 0xff000000u)) trav8_pop(T, K);
         // (4) test queued pairs: whole batches of 32; everything when no lane has node work left or enough lanes wait
         const unsigned int m_node = __ballot_sync(FULL, active && !T.done);
         const unsigned int m_wait = __ballot_sync(FULL, active && T.done && pending);
