@@ -79,6 +79,9 @@ int b200rt_bvh_build_device(const float* tri_xyz9, int n_tri, int device, b200rt
 int b200rt_bvh_get_info(const b200rt_bvh* bvh, b200rt_bvh_info* out);
 /* borrowed pointers into the host arrays described above; valid until b200rt_bvh_destroy  (FlattenedBVH::get_nodes, flattened_bvh.h:43-44) */
 int b200rt_bvh_get_arrays(const b200rt_bvh* bvh, const float** axis16, const float** diag16, const float** tris12);
+/* the 8-ary layout: *nodes80 = n_nodes records of 80 bytes (layout: csrc/bvh_build.h WideNode, decoding: csrc/pt_device.cuh);
+ * borrowed, valid until b200rt_bvh_destroy; n_nodes = 0 when the BVH has none (max_leaf_size > 3) */
+int b200rt_bvh_get_wide_nodes(const b200rt_bvh* bvh, const void** nodes80, int* n_nodes);
 /* structural self-check (every triangle in exactly one leaf, every child volume contains its triangles): 0 = sound */
 int b200rt_bvh_check(const b200rt_bvh* bvh, const float* tri_xyz9, int n_tri);
 void b200rt_bvh_destroy(b200rt_bvh* bvh);

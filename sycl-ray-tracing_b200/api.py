@@ -177,6 +177,11 @@ def quantise_rgba8(image, flip_y: bool = True) -> np.ndarray:
     return out
 
 
+WIDE_NODE_DTYPE = np.dtype([("p", "<f4", 3), ("e", "u1", 3), ("imask", "u1"), ("child_base", "<u4"), ("tri_base", "<u4"), ("valid24", "<u4"),
+                            ("spare", "<u4"), ("lox", "u1", 8), ("loy", "u1", 8), ("loz", "u1", 8), ("hix", "u1", 8), ("hiy", "u1", 8), ("hiz", "u1", 8)])
+assert WIDE_NODE_DTYPE.itemsize == 80
+
+
 # ---- BVH / FlattenedBVH ---------------------------------------------------------------------------------------------------
 class BVH:
     """BVH(std::vector<Triangle>*) (bvh.cpp:19-37). Holds the host-side flattened tree built by the C library."""
@@ -229,6 +234,11 @@ class FlattenedBVH:
         self.axis = np.ctypeslib.as_array(a, shape=(n, 16))
         self.diag = np.ctypeslib.as_array(d, shape=(n, 16))
         self.tris = np.ctypeslib.as_array(t, shape=(max(info["n_triangles"], 0), 12)) if info["n_triangles"] else np.zeros((0, 12), np.float32)
+        # the 8-ary layout as a structured array (80-byte records, csrc/bvh_build.h WideNode)
+        wp, wn = C.c_void_p(), C.c_int()
+        B.check(L.b200rt_bvh_get_wide_nodes(bvh._h, C.byref(wp), C.byref(wn)))
+        self.wide = (np.ctypeslib.as_array(C.cast(wp, C.POINTER(C.c_ubyte)), shape=(wn.value * 80,)).view(WIDE_NODE_DTYPE)
+                     if wn.value else np.zeros(0, WIDE_NODE_DTYPE))
 
     def get_nodes(self):
         return self.axis, self.diag

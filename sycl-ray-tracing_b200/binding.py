@@ -59,7 +59,7 @@ class Stats(C.Structure):
 
 # every symbol include/b200rt.h declares (tests check the library exports each of them)
 EXPORTS = [
-    "b200rt_bvh_default_options", "b200rt_bvh_build", "b200rt_bvh_build_device", "b200rt_bvh_get_info", "b200rt_bvh_get_arrays", "b200rt_bvh_check",
+    "b200rt_bvh_default_options", "b200rt_bvh_build", "b200rt_bvh_build_device", "b200rt_bvh_get_info", "b200rt_bvh_get_arrays", "b200rt_bvh_get_wide_nodes", "b200rt_bvh_check",
     "b200rt_bvh_destroy", "b200rt_scene_create", "b200rt_scene_destroy", "b200rt_scene_set_materials", "b200rt_scene_build_env_alias",
     "b200rt_scene_get_bvh_info", "b200rt_scene_device_bytes", "b200rt_default_render_options", "b200rt_render",
     "b200rt_trace_primary", "b200rt_trace_rays", "b200rt_tiles_for_rank", "b200rt_render_tiles_device",
@@ -86,6 +86,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     L.b200rt_bvh_build_device.argtypes = [FP, I, I, C.POINTER(VP)]
     L.b200rt_bvh_get_info.argtypes = [VP, C.POINTER(BvhInfo)]
     L.b200rt_bvh_get_arrays.argtypes = [VP, C.POINTER(FP), C.POINTER(FP), C.POINTER(FP)]
+    L.b200rt_bvh_get_wide_nodes.argtypes = [VP, C.POINTER(VP), C.POINTER(I)]
     L.b200rt_bvh_check.argtypes = [VP, FP, I]
     L.b200rt_bvh_destroy.argtypes = [VP]
     L.b200rt_bvh_destroy.restype = None

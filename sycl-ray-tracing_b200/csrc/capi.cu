@@ -364,6 +364,14 @@ int b200rt_bvh_get_arrays(const b200rt_bvh* bvh, const float** axis16, const flo
     return B200RT_OK;
 }
 
+int b200rt_bvh_get_wide_nodes(const b200rt_bvh* bvh, const void** nodes80, int* n_nodes)
+{
+    if (!bvh || !nodes80 || !n_nodes) return fail(B200RT_ERR_ARG, "NULL argument");
+    *nodes80 = bvh->flat.wide.data();
+    *n_nodes = (int)bvh->flat.wide.size();
+    return B200RT_OK;
+}
+
 int b200rt_bvh_check(const b200rt_bvh* bvh, const float* tri_xyz9, int n_tri)
 {
     if (!bvh) return fail(B200RT_ERR_ARG, "NULL bvh");

@@ -160,3 +160,126 @@ def test_c2_known_answer_through_the_oracle():
     ps = PortOracle().scene_from_arrays(c2["tri9"], c2["mat_idx"], c2["mats10"], c2["emissive"])
     prim, t, _ = ps.primary(c2["camera"].as_array17(), 1920, 1080, mode=0)
     assert int((prim >= 0).sum()) == 502161
+
+
+# ---- the 8-ary quantised layout, decoded and traversed on the CPU (numpy) -----------------------------------------------------------
+def _wide_grid(q):
+    """plane byte -> grid value: the float whose bits are 0x43000000 | q << 16 (csrc/pt_device.cuh B200RT_Q)."""
+    return (np.uint32(0x43000000) | (np.asarray(q, np.uint32) << np.uint32(16))).view(np.float32)
+
+
+def _wide_closest(flat, ray):
+    """Independent restatement of trav8_node / trav8_tris for ONE ray on the host arrays: boxes decoded in float64
+    (plane = p + 2^(e-127) * v(q)), children visited in slot ^ (7 - octant) order through an explicit stack of node groups,
+    exact triangle tests on the leaf-ordered stream (a, e1, e2 as stored), ties to the lower original index."""
+    wide, tris = flat.wide, flat.tris
+    o = ray[:3].astype(np.float64); d = ray[3:].astype(np.float64)
+    inv = 1.0 / np.where(np.abs(d) < 1e-20, np.copysign(1e-20, d), d)
+    octant = 7 - (int(inv[0] < 0) | (int(inv[1] < 0) << 1) | (int(inv[2] < 0) << 2))
+    best_t, best_p, visited = np.inf, -1, 0
+    stack = [0]
+    f32 = np.float32
+    o32, d32 = ray[:3].astype(f32), ray[3:].astype(f32)
+    while stack:
+        n = wide[stack.pop()]
+        visited += 1
+        cell = np.ldexp(1.0, n["e"].astype(np.int64) - 127)
+        lo = np.stack([n["p"][a] + cell[a] * _wide_grid(n[k]).astype(np.float64) for a, k in enumerate(("lox", "loy", "loz"))], 1)   # [slot, axis]
+        hi = np.stack([n["p"][a] + cell[a] * _wide_grid(n[k]).astype(np.float64) for a, k in enumerate(("hix", "hiy", "hiz"))], 1)
+        t0 = (lo - o) * inv; t1 = (hi - o) * inv
+        tn = np.maximum(np.minimum(t0, t1).max(1), 0.0); tf = np.minimum(np.maximum(t0, t1).min(1), best_t)
+        hit = tn <= tf * (1 + 1e-6)
+        imask, valid = int(n["imask"]), int(n["valid24"])
+        inner = [s for s in range(8) if hit[s] and (imask >> s) & 1]
+        # triangles first (as the device does), then the inner children front to back: push in reverse priority
+        for s in range(8):
+            if not hit[s] or (imask >> s) & 1:
+                continue
+            for i in range(3):
+                b = 3 * s + i
+                if not (valid >> b) & 1:
+                    continue
+                slot = int(n["tri_base"]) + bin(valid & ((1 << b) - 1)).count("1")
+                a_, prim = tris[slot, 0:3], int(tris[slot, 3:4].view(np.int32)[0])
+                e1, e2 = tris[slot, 4:7], tris[slot, 8:11]
+                # triangle.h:16-60 with vec.h's left-to-right dot and cross, every operation rounded to float32
+                dot = lambda p_, q_: f32(f32(f32(p_[0] * q_[0]) + f32(p_[1] * q_[1])) + f32(p_[2] * q_[2]))
+                cross = lambda p_, q_: np.array([f32(f32(p_[1] * q_[2]) - f32(p_[2] * q_[1])), f32(f32(p_[2] * q_[0]) - f32(p_[0] * q_[2])),
+                                                 f32(f32(p_[0] * q_[1]) - f32(p_[1] * q_[0]))], f32)
+                h = cross(d32, e2); det = dot(e1, h)
+                if -1e-7 < det < 1e-7:
+                    continue
+                f = f32(f32(1.0) / det); s_ = (o32 - a_).astype(f32); u = f32(f * dot(s_, h))
+                if u < 0 or u > 1:
+                    continue
+                q = cross(s_, e1); v = f32(f * dot(d32, q))
+                if v < 0 or f32(u + v) > 1:
+                    continue
+                t = f32(f * dot(e2, q))
+                if t > 1e-7 and (t < best_t or (t == best_t and prim < best_p)):
+                    best_t, best_p = float(t), prim
+        for s in sorted(inner, key=lambda s: s ^ octant):           # lowest priority first onto the stack
+            rank = bin(imask & ((1 << s) - 1)).count("1")
+            stack.append(int(n["child_base"]) + rank)
+    return best_p, (np.float32(best_t) if best_p >= 0 else np.float32(-1.0)), visited
+
+
+@pytest.mark.parametrize("key", ["cornell", "area", "soup"])
+def test_wide_layout_decodes_and_traverses_on_the_cpu(rt, golden_scenes, key):
+    """The 80-byte node format is a contract between the builders and the kernels: decode it independently (numpy) and find
+    the same closest hits as a brute force over all triangles. Also pins that traversal prunes (visits far fewer nodes than exist)."""
+    from conftest import brute_force_closest
+    rng = np.random.default_rng(23)
+    tri = (rng.random((400, 9)).astype(np.float32) * 4 - 2) if key == "soup" else scene_arrays(golden_scenes, key)["tri9"]
+    flat = rt.BVH(tri).flatten()
+    assert flat.wide.dtype.itemsize == 80 and len(flat.wide) == flat.bvh.info()["n_wide_nodes"] >= 1
+    lo, hi = tri.reshape(-1, 3).min(0), tri.reshape(-1, 3).max(0)
+    n = 60
+    o = (lo + (hi - lo) * rng.random((n, 3))).astype(np.float32)
+    d = rng.normal(size=(n, 3)).astype(np.float32); d /= np.linalg.norm(d, axis=1, keepdims=True).astype(np.float32)
+    rays = np.concatenate([o, d], 1).astype(np.float32)
+    rays = np.concatenate([rays, np.array([[0, 1, 3.5, 0, 0, -1], [0, 1, 3.5, 1, 0, 0], [5, 5, 5, 0, 1, 0]], np.float32)])     # axis-parallel, and one that misses
+    bp, bt = brute_force_closest(tri, rays)
+    visited = 0
+    for r in range(len(rays)):
+        p, t, v = _wide_closest(flat, rays[r])
+        visited += v
+        assert p == bp[r], (key, r, p, bp[r])
+        assert np.float32(t).view(np.uint32) == np.float32(bt[r]).view(np.uint32), (key, r)
+    if len(flat.wide) > 40:
+        assert visited / len(rays) < 0.5 * len(flat.wide)
+
+
+def test_c_abi_compiles_and_links_as_plain_c(rt, tmp_path):
+    """include/b200rt.h is a C header: a C99 translation unit (-pedantic -Werror) includes it, links libb200rt.so, builds and
+    checks a BVH on the host through the C ABI and reads the 8-ary nodes back; the compute call fails loudly without a GPU."""
+    import subprocess
+    src = tmp_path / "abi.c"
+    src.write_text(r"""
+#include <stdio.h>
+#include <string.h>
+#include "b200rt.h"
+int main(void)
+{
+    float tri[4 * 9] = { 0,0,0, 1,0,0, 0,1,0,   0,0,1, 1,0,1, 0,1,1,   2,0,0, 3,0,0, 2,1,0,   0,2,0, 1,2,0, 0,3,0 };
+    b200rt_bvh* bvh = NULL;
+    b200rt_bvh_options o;
+    b200rt_bvh_info info;
+    const void* nodes = NULL;
+    int n_nodes = -1;
+    b200rt_bvh_default_options(&o);
+    if (b200rt_bvh_build(tri, 4, &o, &bvh) != B200RT_OK) { printf("build: %s\n", b200rt_last_error()); return 1; }
+    if (b200rt_bvh_check(bvh, tri, 4) != B200RT_OK) { printf("check: %s\n", b200rt_last_error()); return 2; }
+    if (b200rt_bvh_get_info(bvh, &info) != B200RT_OK || info.n_triangles != 4) return 3;
+    if (b200rt_bvh_get_wide_nodes(bvh, &nodes, &n_nodes) != B200RT_OK || n_nodes < 1 || !nodes) return 4;
+    printf("%s nodes=%d depth=%d\n", b200rt_version(), n_nodes, info.wide_max_depth);
+    b200rt_bvh_destroy(bvh);
+    return 0;
+}
+""")
+    exe = tmp_path / "abi"
+    libdir = os.path.join(ROOT, "sycl-ray-tracing_b200")
+    subprocess.run(["gcc", "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe),
+                    "-L", libdir, "-lb200rt", f"-Wl,-rpath,{libdir}"], check=True)
+    out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
+    assert "sm_100a" in out and "nodes=1" in out
