@@ -107,6 +107,9 @@ int b200rt_scene_set_materials(b200rt_scene* scene, const float* materials10, in
  * B200RT_FLAG_ENV_ALIAS samples from. Replaces Utils::compute_env_map_cdf (utils.cpp:126-142) + env_map_cdf_search
  * (render_kernel.cpp:532-567) for callers that opt in. */
 int b200rt_scene_build_env_alias(b200rt_scene* scene);
+/* the same table on the host, for callers / tests that want to look at it: env_w*env_h acceptance probabilities and alias
+ * texels; *total_out (may be NULL) = the exact luminance sum the probabilities are normalised with. Host-only, no GPU needed. */
+int b200rt_env_alias_table(const float* env_rgba, int env_w, int env_h, float* prob_out, int* alias_out, double* total_out);
 int b200rt_scene_get_bvh_info(const b200rt_scene* scene, b200rt_bvh_info* out);
 size_t b200rt_scene_device_bytes(const b200rt_scene* scene);
 

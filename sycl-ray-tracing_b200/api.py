@@ -168,6 +168,15 @@ def compute_env_map_cdf(skysphere: "Image | np.ndarray") -> np.ndarray:
     return np.cumsum(lum, dtype=np.float32)          # add.accumulate in float32 == the reference's serial loop
 
 
+def env_alias_table(skysphere):
+    """Alias table of an env map's luminance, built by the library on the host (b200rt_env_alias_table): (prob, alias, total)."""
+    env = _f32(skysphere.pixels if isinstance(skysphere, Image) else skysphere)
+    h, w = env.shape[:2]
+    prob = np.empty(h * w, np.float32); alias = np.empty(h * w, np.int32); total = C.c_double()
+    B.check(B.load_library().b200rt_env_alias_table(B.fptr(env), w, h, B.fptr(prob), alias.ctypes.data_as(C.POINTER(C.c_int)), C.byref(total)))
+    return prob, alias, total.value
+
+
 def quantise_rgba8(image, flip_y: bool = True) -> np.ndarray:
     """write_image_png's quantisation (image_io.cpp:165-182) on the GPU: (h, w, 4) float32 -> (h, w, 4) uint8."""
     img = _f32(image)

@@ -60,7 +60,7 @@ class Stats(C.Structure):
 # every symbol include/b200rt.h declares (tests check the library exports each of them)
 EXPORTS = [
     "b200rt_bvh_default_options", "b200rt_bvh_build", "b200rt_bvh_build_device", "b200rt_bvh_get_info", "b200rt_bvh_get_arrays", "b200rt_bvh_get_wide_nodes", "b200rt_bvh_check",
-    "b200rt_bvh_destroy", "b200rt_scene_create", "b200rt_scene_destroy", "b200rt_scene_set_materials", "b200rt_scene_build_env_alias",
+    "b200rt_bvh_destroy", "b200rt_scene_create", "b200rt_scene_destroy", "b200rt_scene_set_materials", "b200rt_scene_build_env_alias", "b200rt_env_alias_table",
     "b200rt_scene_get_bvh_info", "b200rt_scene_device_bytes", "b200rt_default_render_options", "b200rt_render",
     "b200rt_trace_primary", "b200rt_trace_rays", "b200rt_tiles_for_rank", "b200rt_render_tiles_device",
     "b200rt_untile_device", "b200rt_trace_primary_device", "b200rt_trace_rays_device", "b200rt_quantise_rgba8", "b200rt_quantise_rgba8_device", "b200rt_last_error", "b200rt_version",
@@ -95,6 +95,7 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     L.b200rt_scene_destroy.restype = None
     L.b200rt_scene_set_materials.argtypes = [VP, FP, I]
     L.b200rt_scene_build_env_alias.argtypes = [VP]
+    L.b200rt_env_alias_table.argtypes = [FP, I, I, FP, C.POINTER(C.c_int), C.POINTER(C.c_double)]
     L.b200rt_quantise_rgba8.argtypes = [FP, I, I, I, C.POINTER(C.c_ubyte)]
     L.b200rt_quantise_rgba8_device.argtypes = [VP, I, I, I, VP, VP]
     L.b200rt_scene_get_bvh_info.argtypes = [VP, C.POINTER(BvhInfo)]

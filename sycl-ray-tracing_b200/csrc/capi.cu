@@ -503,23 +503,18 @@ int b200rt_scene_create(const float* tri_xyz9, int n_tri, const int* tri_materia
     return B200RT_OK;
 }
 
-int b200rt_scene_build_env_alias(b200rt_scene* s)
+// Vose's alias method in double over per-texel luminances: texel i is accepted with probability prob[i], otherwise alias[i] is taken
+static int build_alias_table(const float* lum, size_t n, std::vector<float>& prob, std::vector<int>& alias_out, double* total_out)
 {
-    if (!s) return fail(B200RT_ERR_ARG, "NULL scene");
-    if (s->d_alias) return B200RT_OK;
-    CU(cudaSetDevice(s->device));
-    const size_t n = s->env_lum.size();
-    if (!n) return fail(B200RT_ERR_ARG, "scene has no environment map");
-    // Vose's alias method in double: texel i is accepted with probability q[i], otherwise its alias is taken
     double total = 0.0;
-    for (float l : s->env_lum) total += l > 0.0f ? (double)l : 0.0;
+    for (size_t i = 0; i < n; i++) total += lum[i] > 0.0f ? (double)lum[i] : 0.0;
     if (!(total > 0.0)) return fail(B200RT_ERR_ARG, "environment map has no luminance to sample");
     std::vector<double> q(n);
     std::vector<unsigned int> alias(n), small, large;
     small.reserve(n); large.reserve(n);
     for (size_t i = 0; i < n; i++)
     {
-        q[i] = (s->env_lum[i] > 0.0f ? (double)s->env_lum[i] : 0.0) / total * (double)n;
+        q[i] = (lum[i] > 0.0f ? (double)lum[i] : 0.0) / total * (double)n;
         alias[i] = (unsigned int)i;
         (q[i] < 1.0 ? small : large).push_back((unsigned int)i);
     }
@@ -533,12 +528,46 @@ int b200rt_scene_build_env_alias(b200rt_scene* s)
     }
     for (unsigned int i : large) q[i] = 1.0;
     for (unsigned int i : small) q[i] = 1.0;          // numerical leftovers
+    prob.resize(n); alias_out.resize(n);
+    for (size_t i = 0; i < n; i++) { prob[i] = (float)q[i]; alias_out[i] = (int)alias[i]; }
+    *total_out = total;
+    return B200RT_OK;
+}
+
+int b200rt_env_alias_table(const float* env_rgba, int env_w, int env_h, float* prob_out, int* alias_out, double* total_out)
+{
+    if (!env_rgba || env_w <= 0 || env_h <= 0 || !prob_out || !alias_out) return fail(B200RT_ERR_ARG, "bad alias table arguments");
+    const size_t n = (size_t)env_w * env_h;
+    std::vector<float> lum(n);
+    for (size_t i = 0; i < n; i++)
+    {
+        const float* p = env_rgba + 4 * i;
+        lum[i] = (float)(0.3086 * p[0] + 0.6094 * p[1] + 0.0820 * p[2]);      // Image::luminance_of_pixel, image.h:80-85
+    }
+    std::vector<float> prob; std::vector<int> alias; double total = 0.0;
+    int rc = build_alias_table(lum.data(), n, prob, alias, &total);
+    if (rc) return rc;
+    std::memcpy(prob_out, prob.data(), n * sizeof(float));
+    std::memcpy(alias_out, alias.data(), n * sizeof(int));
+    if (total_out) *total_out = total;
+    return B200RT_OK;
+}
+
+int b200rt_scene_build_env_alias(b200rt_scene* s)
+{
+    if (!s) return fail(B200RT_ERR_ARG, "NULL scene");
+    if (s->d_alias) return B200RT_OK;
+    CU(cudaSetDevice(s->device));
+    const size_t n = s->env_lum.size();
+    if (!n) return fail(B200RT_ERR_ARG, "scene has no environment map");
+    std::vector<float> prob; std::vector<int> alias; double total = 0.0;
+    int rc = build_alias_table(s->env_lum.data(), n, prob, alias, &total);
+    if (rc) return rc;
     std::vector<float2> table(n);
     for (size_t i = 0; i < n; i++)
     {
-        table[i].x = (float)q[i];
-        int a = (int)alias[i];
-        std::memcpy(&table[i].y, &a, sizeof(int));
+        table[i].x = prob[i];
+        std::memcpy(&table[i].y, &alias[i], sizeof(int));
     }
     CU(cudaMalloc(&s->d_alias, n * sizeof(float2)));
     s->bytes += n * sizeof(float2);

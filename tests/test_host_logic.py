@@ -283,3 +283,24 @@ int main(void)
                     "-L", libdir, "-lb200rt", f"-Wl,-rpath,{libdir}"], check=True)
     out = subprocess.run([str(exe)], check=True, capture_output=True, text=True).stdout
     assert "sm_100a" in out and "nodes=1" in out
+
+
+def test_env_alias_table_encodes_luminance_over_total(rt):
+    """The alias table B200RT_FLAG_ENV_ALIAS samples from: the distribution it implies (accept texel i with prob[i], else take
+    alias[i], i uniform) must be each texel's luminance over the exact total — to 1e-6 relative (prob is stored as float)."""
+    from sycl_ray_tracing_b200 import scenes
+    rng = np.random.default_rng(9)
+    for env in (rng.random((16, 32, 4)).astype(np.float32) * np.array([1, 1, 1, 0], np.float32),
+                scenes.procedural_sky(128, 64),                                                   # sun 5e4 next to sky 0.3: the float running-sum CDF stagnates here
+                np.concatenate([np.zeros((4, 8, 4), np.float32), np.ones((4, 8, 4), np.float32)])):      # zero-luminance texels are never picked
+        prob, alias, total = rt.env_alias_table(env)
+        n = prob.size
+        e64 = env.astype(np.float64)
+        lum = (0.3086 * e64[..., 0] + 0.6094 * e64[..., 1] + 0.0820 * e64[..., 2]).astype(np.float32).astype(np.float64).ravel()    # image.h:80-85
+        assert abs(total - lum.sum()) <= 1e-9 * lum.sum()
+        assert ((prob >= 0) & (prob <= 1)).all() and ((alias >= 0) & (alias < n)).all()
+        implied = prob.astype(np.float64) / n
+        np.add.at(implied, alias, (1.0 - prob.astype(np.float64)) / n)
+        want = lum / lum.sum()
+        assert np.abs(implied - want).max() <= 1e-6 * want.max() + 1e-12
+        assert (implied[lum == 0] == 0).all()
