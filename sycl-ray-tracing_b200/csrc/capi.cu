@@ -148,22 +148,18 @@ cudaError_t wf_alloc(b200rt_scene* s, T** p, size_t n)
     return e;
 }
 
-int wavefront_group_count()
+// tile groups (independent iteration chains on their own streams). 3 for a full 1080p frame; a rank that holds a fraction of it
+// (multi-GPU) is latency-bound per pass and gains a little from a fourth chain (one rank of 8 emulated: 115.9 -> 112.2 ms)
+int wavefront_group_count(const RenderParams& P)
 {
-    static int n = -1;
-    if (n < 0)
-    {
-        const char* e = getenv("B200RT_WF_GROUPS");
-        n = e ? atoi(e) : 3;
-        if (n < 1) n = 1;
-        if (n > kMaxWfGroups) n = kMaxWfGroups;
-    }
-    return n;
+    static const int env_n = []() { const char* e = getenv("B200RT_WF_GROUPS"); int v = e ? atoi(e) : 0; return v > kMaxWfGroups ? kMaxWfGroups : v; }();
+    if (env_n >= 1) return env_n;
+    return (long long)P.n_rank_tiles * kTilePixels < 700000 ? 4 : 3;
 }
 
 int ensure_wavefront(b200rt_scene* s, const RenderParams& P)
 {
-    const int G = wavefront_group_count();
+    const int G = wavefront_group_count(P);
     if (!s->h_active)
     {
         CU(cudaMallocHost(&s->h_active, kMaxWfGroups * sizeof(unsigned int)));
