@@ -365,7 +365,25 @@ struct Trav8
     unsigned int tvalid;       // valid24 of the node the triangle group belongs to
     Hit hit;
 };
-struct TravStack8 { uint2 e[kStackSize]; };
+// Stack of node groups. TravStack8: per-lane local memory (lane-interleaved 4-byte words: lanes at different depths touch a
+// different 32-byte sector each, 2.5 useful bytes per sector in ncu, local-load L1 hit rate 54 % in wf_trace_coop).
+// TravStack8Shared: the first kSharedStackDepth entries (a C3 tree is 9 levels deep, the 20 M-triangle tree 12) in shared
+// memory, one 8-byte column per thread, the rest in local memory.
+struct TravStack8
+{
+    uint2 e[kStackSize];
+    __device__ __forceinline__ void push(int sp, uint2 v) { e[sp] = v; }
+    __device__ __forceinline__ uint2 pop(int sp) const { return e[sp]; }
+};
+constexpr int kSharedStackDepth = 10;
+struct TravStack8Shared
+{
+    uint2* sh;          // this thread's column: entry i at sh[i * blockDim.x]
+    int stride;
+    uint2 ovf[kStackSize - kSharedStackDepth];
+    __device__ __forceinline__ void push(int sp, uint2 v) { if (sp < kSharedStackDepth) sh[sp * stride] = v; else ovf[sp - kSharedStackDepth] = v; }
+    __device__ __forceinline__ uint2 pop(int sp) const { return sp < kSharedStackDepth ? sh[sp * stride] : ovf[sp - kSharedStackDepth]; }
+};
 
 __device__ __forceinline__ float safe_rcp8(float d)
 {
@@ -387,10 +405,11 @@ __device__ __forceinline__ void trav8_init(Trav8& T, v3 o, v3 d, float tmax, con
 
 __device__ __forceinline__ bool trav8_has_node(const Trav8& T) { return T.tg.y == 0u; }     // else: triangles pending
 
-__device__ __forceinline__ void trav8_pop(Trav8& T, TravStack8& K)
+template <typename Stack>
+__device__ __forceinline__ void trav8_pop(Trav8& T, Stack& K)
 {
     if (T.sp == 0) { T.done = true; return; }
-    T.ng = K.e[--T.sp];
+    T.ng = K.pop(--T.sp);
 }
 
 // slot of the triangle behind bit b of a triangle group
@@ -425,12 +444,13 @@ __device__ __forceinline__ unsigned int wide_test4(unsigned int acc, unsigned in
 
 // pre: trav8_has_node(T) and the node group holds at least one hit. Takes the front-most child node of the group, tests
 // its 8 children, leaves the hit inner children in T.ng and the hit triangles in T.tg.
-__device__ __forceinline__ void trav8_node(const SceneDev& S, Trav8& T, TravStack8& K)
+template <typename Stack>
+__device__ __forceinline__ void trav8_node(const SceneDev& S, Trav8& T, Stack& K)
 {
     const unsigned int hits = T.ng.y;
     const int bit = 31 - __clz((int)hits);
     T.ng.y = hits & ~(1u << bit);
-    if (T.ng.y & 0xff000000u) K.e[T.sp++] = T.ng;          // the group's remaining members wait on the stack
+    if (T.ng.y & 0xff000000u) K.push(T.sp++, T.ng);        // the group's remaining members wait on the stack
     const unsigned int slot = (unsigned int)(bit - 24) ^ T.oct;
     const unsigned int rel = __popc(hits & 0xffu & ~(0xffffffffu << slot));
     const float4* np = S.wide + 5 * (size_t)(T.ng.x + rel);
@@ -477,7 +497,8 @@ __device__ __forceinline__ void trav8_node(const SceneDev& S, Trav8& T, TravStac
 }
 
 // pre: !trav8_has_node(T). Exact triangle tests of the pending triangle group, then the next node group.
-__device__ __forceinline__ void trav8_tris(const SceneDev& S, Trav8& T, TravStack8& K)
+template <typename Stack>
+__device__ __forceinline__ void trav8_tris(const SceneDev& S, Trav8& T, Stack& K)
 {
     const v3 o = T.o, d = T.d;
     unsigned int bits = T.tg.y;

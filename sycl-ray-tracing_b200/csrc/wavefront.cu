@@ -526,7 +526,13 @@ __global__ void __launch_bounds__(32 * kCoopMaxWarps, WF_COOP_MIN_BLOCKS) wf_tra
     const unsigned int warp_block = min((unsigned int)kWarpBlock, max(32u, (n_rays / total_warps) & ~31u));
 
     Trav8 T;
+#ifdef WF_COOP_LOCAL_STACK
     TravStack8 K;
+#else
+    __shared__ uint2 s_stack[kSharedStackDepth * 32 * kCoopMaxWarps];
+    TravStack8Shared K;
+    K.sh = s_stack + threadIdx.x; K.stride = 32 * kCoopMaxWarps;
+#endif
     T.done = true; T.tg = make_uint2(0u, 0u);
     bool active = false, pending = false;
     size_t r = 0;
