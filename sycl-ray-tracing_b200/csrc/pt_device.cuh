@@ -375,7 +375,10 @@ struct TravStack8
     __device__ __forceinline__ void push(int sp, uint2 v) { e[sp] = v; }
     __device__ __forceinline__ uint2 pop(int sp) const { return e[sp]; }
 };
-constexpr int kSharedStackDepth = 10;
+#ifndef B200RT_SHARED_STACK_DEPTH
+#define B200RT_SHARED_STACK_DEPTH 10
+#endif
+constexpr int kSharedStackDepth = B200RT_SHARED_STACK_DEPTH;     // (a build with 2 runs the whole GPU test suite through the local-memory overflow)
 struct TravStack8Shared
 {
     uint2* sh;          // this thread's column: entry i at sh[i * blockDim.x]
