@@ -456,7 +456,11 @@ __global__ void WF_TRACE_BOUNDS wf_trace(SceneDev S, WfBuffers B, int parity)
 // (t bits << 32 | primitive index) with a shared-memory atomicMin — which is exactly the closest-hit rule of the other
 // kernels (smaller t, ties to the lower original index). Owners pick up their new t_best after each drain. A ray is
 // finished when it has no node work and no pair left in the queue.
-constexpr int kCoopQueue = 160;         // pairs per warp; an append that does not fit drains first
+#ifndef WF_COOP_QUEUE
+#define WF_COOP_QUEUE 160
+#endif
+constexpr int kCoopQueue = WF_COOP_QUEUE;   // pairs per warp (> 32); an append that does not fit drains first (a build with 40 runs the GPU
+                                            // test suite through that path all the time)
 constexpr int kCoopMaxWarps = 4;         // the kernel is launched with 128-thread CTAs
 constexpr unsigned long long kNoHit = 0xffffffffffffffffull;
 
