@@ -201,6 +201,46 @@ LeafTriangle make_leaf_triangle(const float* tri9, int id)
 // exact Moller-Trumbore test accepts
 inline float box_pad(float lo, float hi, float abs_pad) { return 1e-5f * std::max(std::fabs(lo), std::fabs(hi)) + abs_pad; }
 
+// One axis of a wide node: frame origin p, cell size 2^(e-127) and the 8 x 2 plane bytes from the (already padded) child boxes
+// of the used slots. Cell size: 376 cells span the extent (the grid has 382; the rest absorbs the roundings below), and a
+// cell is never finer than the float spacing of the coordinates. lo planes round down, hi planes up, on the grid
+// v(q) = 128 + q (q < 128), 2q (q >= 128).
+void quantise_slots(WideNode& w, int a, const float* klo, const float* khi, const bool* used, bool& overflow)
+{
+    float lo = kInf, hi = -kInf;
+    for (int s = 0; s < 8; s++)
+        if (used[s]) { lo = std::min(lo, klo[s]); hi = std::max(hi, khi[s]); }
+    if (!(lo <= hi)) { lo = 0.0f; hi = 0.0f; }
+    const double extent = (double)hi - (double)lo;
+    int e = -100;
+    if (extent > 0.0) { int ex; std::frexp(extent / 376.0, &ex); e = ex; }      // 2^ex > extent / 376
+    const double amax = std::max(std::fabs((double)lo), std::fabs((double)hi));
+    if (amax > 0.0) e = std::max(e, std::ilogb(amax) - 23);
+    e = std::min(126, std::max(-100, e));
+    const double cell = std::ldexp(1.0, e);
+    const double pd = (double)lo - 128.0 * cell;
+    float pf = (float)pd;
+    if ((double)pf > pd) pf = std::nextafter(pf, -kInf);
+    w.p[a] = pf;
+    w.e[a] = (uint8_t)(e + 127);
+    uint8_t* qlo = a == 0 ? w.lox : (a == 1 ? w.loy : w.loz);
+    uint8_t* qhi = a == 0 ? w.hix : (a == 1 ? w.hiy : w.hiz);
+    for (int s = 0; s < 8; s++)
+    {
+        qlo[s] = 255; qhi[s] = 0;                                                 // empty slots: inverted, never hit
+        if (!used[s]) continue;
+        long vl = (long)std::floor(((double)klo[s] - (double)pf) / cell);
+        long vh = (long)std::ceil(((double)khi[s] - (double)pf) / cell);
+        if (vl < 128 || vh > 510) overflow = true;
+        vl = std::min(510L, std::max(128L, vl)); vh = std::min(510L, std::max(128L, vh));
+        if (vl >= 256) vl &= ~1L;
+        if (vh >= 256 && (vh & 1)) vh++;
+        if (vh > 510) { overflow = true; vh = 510; }
+        qlo[s] = (uint8_t)(vl < 256 ? vl - 128 : vl / 2);
+        qhi[s] = (uint8_t)(vh < 256 ? vh - 128 : vh / 2);
+    }
+}
+
 // Collapses the binary tree into the 8-ary quantised layout (WideNode) and fixes the order of the triangle stream:
 // the triangles of a node's leaf children are contiguous, in slot order.
 struct WideBuilder
@@ -220,47 +260,15 @@ struct WideBuilder
 
     void quantise_axis(WideNode& w, int a, const int* kids, const int* slot_of, int nk)
     {
-        float lo = kInf, hi = -kInf;
-        float klo[8], khi[8];
+        float klo[8], khi[8]; bool used[8] = {};
         for (int k = 0; k < nk; k++)
         {
             const Box& bx = b.nodes[kids[k]].box;
-            if (!(bx.lo[a] <= bx.hi[a])) { klo[k] = kInf; khi[k] = -kInf; continue; }      // empty leaf
+            if (!(bx.lo[a] <= bx.hi[a])) continue;                                           // empty leaf
             const float pad = box_pad(bx.lo[a], bx.hi[a], abs_pad);
-            klo[k] = bx.lo[a] - pad; khi[k] = bx.hi[a] + pad;
-            lo = std::min(lo, klo[k]); hi = std::max(hi, khi[k]);
+            klo[slot_of[k]] = bx.lo[a] - pad; khi[slot_of[k]] = bx.hi[a] + pad; used[slot_of[k]] = true;
         }
-        if (!(lo <= hi)) { lo = 0.0f; hi = 0.0f; }
-        // cell size 2^e: 376 cells span the extent (the grid has 382; the rest absorbs the roundings below), and a cell is
-        // never finer than the float spacing of the coordinates
-        const double extent = (double)hi - (double)lo;
-        int e = -100;
-        if (extent > 0.0) { int ex; std::frexp(extent / 376.0, &ex); e = ex; }      // 2^ex > extent / 376
-        const double amax = std::max(std::fabs((double)lo), std::fabs((double)hi));
-        if (amax > 0.0) e = std::max(e, std::ilogb(amax) - 23);
-        e = std::min(126, std::max(-100, e));
-        const double cell = std::ldexp(1.0, e);
-        const double pd = (double)lo - 128.0 * cell;
-        float pf = (float)pd;
-        if ((double)pf > pd) pf = std::nextafter(pf, -kInf);
-        w.p[a] = pf;
-        w.e[a] = (uint8_t)(e + 127);
-        uint8_t* qlo = a == 0 ? w.lox : (a == 1 ? w.loy : w.loz);
-        uint8_t* qhi = a == 0 ? w.hix : (a == 1 ? w.hiy : w.hiz);
-        for (int s = 0; s < 8; s++) { qlo[s] = 255; qhi[s] = 0; }               // empty slots: inverted, never hit
-        for (int k = 0; k < nk; k++)
-        {
-            if (!(klo[k] <= khi[k])) continue;
-            long vl = (long)std::floor(((double)klo[k] - (double)pf) / cell);
-            long vh = (long)std::ceil(((double)khi[k] - (double)pf) / cell);
-            if (vl < 128 || vh > 510) overflow = true;
-            vl = std::min(510L, std::max(128L, vl)); vh = std::min(510L, std::max(128L, vh));
-            if (vl >= 256) vl &= ~1L;
-            if (vh >= 256 && (vh & 1)) vh++;
-            if (vh > 510) { overflow = true; vh = 510; }
-            qlo[slot_of[k]] = (uint8_t)(vl < 256 ? vl - 128 : vl / 2);
-            qhi[slot_of[k]] = (uint8_t)(vh < 256 ? vh - 128 : vh / 2);
-        }
+        quantise_slots(w, a, klo, khi, used, overflow);
     }
 
     // fills wide node `me` from binary inner node `bn`
@@ -528,6 +536,123 @@ void build_flat_bvh(const float* tri9, int n_tri, const b200rt_bvh_options& opts
     out.info.sah_cost = sah;
     out.info.n_wide_nodes = (int)out.wide.size();
     out.info.wide_max_depth = wide_depth;
+}
+
+// Hangs triangles that were kept out of the tree (the device builder's outsized ones) in front of both layouts' roots: the old
+// root record moves to the end of its array, record 0 becomes a top-level node whose one inner child is the old root (or the
+// next top-level node) and whose other children are leaves holding the extra triangles (8-ary: 7 leaves x 3 triangles per
+// node; binary: one leaf of up to 15 per record). The extra triangles go to the end of the triangle stream.
+void append_top_level(FlatBVH& b, const float* tri9, const std::vector<int>& ids, float abs_pad)
+{
+    if (ids.empty() || b.wide.empty() || b.axis.empty()) return;
+    const int n_extra = (int)ids.size();
+    const size_t first_slot = b.tris.size();
+    std::vector<Box> tbox((size_t)n_extra);
+    for (int i = 0; i < n_extra; i++)
+    {
+        b.tris.push_back(make_leaf_triangle(tri9, ids[i]));
+        const float* p = tri9 + 9 * (size_t)ids[i];
+        tbox[i].grow(p); tbox[i].grow(p + 3); tbox[i].grow(p + 6);
+        for (int a = 0; a < 3; a++) { const float pad = box_pad(tbox[i].lo[a], tbox[i].hi[a], abs_pad); tbox[i].lo[a] -= pad; tbox[i].hi[a] += pad; }
+    }
+    // ---- 8-ary layout
+    {
+        Box root;                                                   // the old root's extent: union of its decoded child boxes
+        const WideNode w0 = b.wide[0];
+        const uint8_t* ql[3] = { w0.lox, w0.loy, w0.loz };
+        const uint8_t* qh[3] = { w0.hix, w0.hiy, w0.hiz };
+        for (int s = 0; s < 8; s++)
+        {
+            if (!((w0.imask >> s) & 1) && !((w0.valid24 >> (3 * s)) & 7u)) continue;
+            float lo[3], hi[3];
+            for (int a = 0; a < 3; a++)
+            {
+                const double cell = std::ldexp(1.0, (int)w0.e[a] - 127);
+                const double dl = (double)w0.p[a] + cell * wide_grid_value(ql[a][s]), dh = (double)w0.p[a] + cell * wide_grid_value(qh[a][s]);
+                lo[a] = (float)dl; if ((double)lo[a] > dl) lo[a] = std::nextafter(lo[a], -kInf);
+                hi[a] = (float)dh; if ((double)hi[a] < dh) hi[a] = std::nextafter(hi[a], kInf);
+            }
+            root.grow(lo); root.grow(hi);
+        }
+        const int per_node = 7 * kWideMaxLeaf;
+        const int n_top = (n_extra + per_node - 1) / per_node;
+        const size_t moved = b.wide.size();
+        b.wide.push_back(w0);
+        b.wide.resize(moved + (size_t)n_top);                      // top node k lives at index 0 (k = 0) or moved + k
+        std::vector<Box> below((size_t)n_top + 1);                 // extent of everything under top node k's inner child
+        below[(size_t)n_top] = root;
+        for (int k = n_top - 1; k >= 0; k--)
+        {
+            below[(size_t)k] = below[(size_t)k + 1];
+            for (int i = k * per_node; i < std::min(n_extra, (k + 1) * per_node); i++) below[(size_t)k].grow(tbox[i]);
+        }
+        bool overflow = false;
+        for (int k = 0; k < n_top; k++)
+        {
+            WideNode w;
+            std::memset(&w, 0, sizeof(w));
+            float klo[3][8], khi[3][8]; bool used[8] = {};
+            w.imask = 1;                                            // slot 0: the rest of the structure
+            w.child_base = (uint32_t)(k + 1 < n_top ? moved + (size_t)k + 1 : moved);
+            w.tri_base = (uint32_t)(first_slot + (size_t)k * per_node);
+            used[0] = true;
+            for (int a = 0; a < 3; a++) { klo[a][0] = below[(size_t)k + 1].lo[a]; khi[a][0] = below[(size_t)k + 1].hi[a]; }
+            for (int s = 1; s < 8; s++)
+            {
+                const int i0 = k * per_node + (s - 1) * kWideMaxLeaf, cnt = std::min(kWideMaxLeaf, n_extra - i0);
+                if (cnt <= 0) break;
+                Box lb;
+                for (int i = i0; i < i0 + cnt; i++) lb.grow(tbox[i]);
+                used[s] = true;
+                for (int a = 0; a < 3; a++) { klo[a][s] = lb.lo[a]; khi[a][s] = lb.hi[a]; }
+                w.valid24 |= ((1u << cnt) - 1u) << (3 * s);
+            }
+            for (int a = 0; a < 3; a++) quantise_slots(w, a, klo[a], khi[a], used, overflow);
+            b.wide[k == 0 ? 0 : moved + (size_t)k] = w;
+        }
+        if (overflow) throw std::runtime_error("wide BVH quantisation overflow (top level)");
+        b.info.n_wide_nodes = (int)b.wide.size();
+        b.info.wide_max_depth += n_top;
+    }
+    // ---- binary layout
+    {
+        const AxisNode a0 = b.axis[0];
+        Box root;
+        root.grow(a0.l_lo); root.grow(a0.l_hi);
+        if (a0.r_lo[0] <= a0.r_hi[0]) { root.grow(a0.r_lo); root.grow(a0.r_hi); }
+        const int per_rec = 15;
+        const int n_top = (n_extra + per_rec - 1) / per_rec;
+        const size_t moved = b.axis.size();
+        b.axis.push_back(a0);
+        b.axis.resize(moved + (size_t)n_top);
+        if (!b.diag.empty()) { b.diag.push_back(b.diag[0]); b.diag.resize(b.axis.size()); }
+        std::vector<Box> below((size_t)n_top + 1);
+        below[(size_t)n_top] = root;
+        for (int k = n_top - 1; k >= 0; k--)
+        {
+            below[(size_t)k] = below[(size_t)k + 1];
+            for (int i = k * per_rec; i < std::min(n_extra, (k + 1) * per_rec); i++) below[(size_t)k].grow(tbox[i]);
+        }
+        for (int k = 0; k < n_top; k++)
+        {
+            AxisNode an;
+            const int i0 = k * per_rec, cnt = std::min(per_rec, n_extra - i0);
+            Box lb;
+            for (int i = i0; i < i0 + cnt; i++) lb.grow(tbox[i]);
+            for (int a = 0; a < 3; a++)
+            {
+                an.l_lo[a] = below[(size_t)k + 1].lo[a]; an.l_hi[a] = below[(size_t)k + 1].hi[a];
+                an.r_lo[a] = lb.lo[a]; an.r_hi[a] = lb.hi[a];
+            }
+            an.l_ref = (int)(k + 1 < n_top ? moved + (size_t)k + 1 : moved); an.l_count = 0;
+            an.r_ref = leaf_ref((int)(first_slot + (size_t)i0), cnt); an.r_count = cnt;
+            b.axis[k == 0 ? 0 : moved + (size_t)k] = an;
+        }
+        b.info.n_inner_nodes = (int)b.axis.size();
+        b.info.n_leaves += n_top;
+        b.info.max_depth += n_top;
+        b.info.max_leaf_size = std::max(b.info.max_leaf_size, std::min(per_rec, n_extra));
+    }
 }
 
 // 8-ary layout: every triangle slot referenced exactly once, every decoded child box contains all vertices below it

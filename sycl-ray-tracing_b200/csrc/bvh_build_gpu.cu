@@ -9,8 +9,12 @@
 //   5. subtrees of <= 3 triangles become leaves; level-by-level collapse into the 8-ary layout: every wide node opens its
 //      largest children until it has 8, assigns them to octant slots     (lw_expand, lw_link; prefix sums give child_base / tri_base)
 //   6. emit: quantised 80-byte wide nodes + the leaf-ordered triangle stream (lw_emit), binary two-children records (lb_emit)
+// Outsized triangles (box diagonal > 1/4 of the scene's: a ground quad under a mesh) would drag every ancestor box of their
+// Morton leaf out to the whole scene; up to 45 of them are kept out of the tree and hung, as leaf children, under one to
+// three extra top-level nodes in front of the tree's root (append_top_level, on the host after the download).
 // Output is the same FlatBVH the host builder produces (b200rt_bvh_check validates either), except that it carries no
 // diagonal slabs (has_diag_slabs = 0: the 7-plane ablation needs the host builder).
+#include <algorithm>
 #include <cfloat>
 #include <chrono>
 #include <cstdint>
@@ -38,7 +42,8 @@ struct DevArrays
     int *left, *right, *first, *last, *parent_node, *parent_leaf;
     float4 *nlo, *nhi;                       // per internal node box
     unsigned int* visits;
-    int* scene;                              // 7 ordered ints: centre-bounds min xyz, max xyz, max |coord|
+    int* scene;                              // ordered ints: [0..5] centre-bounds min xyz / max xyz, [6] max |coord|, [8..13] scene box min / max; [14] = outsized count
+    int segregate;                           // 1: outsized triangles get the largest sort key and stay out of the tree
     int n;
 };
 
@@ -71,6 +76,12 @@ __global__ void lb_bounds(DevArrays A)
     }
     for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(0xffffffffu, am, o));
     if ((threadIdx.x & 31) == 0) atomicMax(&A.scene[6], f2ord(am));
+    for (int a = 0; a < 3; a++)
+    {
+        float mn = live ? lo[a] : FLT_MAX, mx = live ? hi[a] : -FLT_MAX;
+        for (int o = 16; o > 0; o >>= 1) { mn = fminf(mn, __shfl_xor_sync(0xffffffffu, mn, o)); mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o)); }
+        if ((threadIdx.x & 31) == 0 && mn <= mx) { atomicMin(&A.scene[8 + a], f2ord(mn)); atomicMax(&A.scene[11 + a], f2ord(mx)); }
+    }
 }
 
 __device__ __forceinline__ unsigned long long spread3(unsigned long long x)       // 21 bits -> every third bit
@@ -90,6 +101,23 @@ __global__ void lb_morton(DevArrays A)
     if (i >= A.n) return;
     const float4 lo = A.plo[i], hi = A.phi[i];
     const float c[3] = { 0.5f * (lo.x + hi.x), 0.5f * (lo.y + hi.y), 0.5f * (lo.z + hi.z) };
+    if (A.segregate)
+    {
+        double d2 = 0.0, s2 = 0.0;
+        const float ext[3] = { hi.x - lo.x, hi.y - lo.y, hi.z - lo.z };
+        for (int a = 0; a < 3; a++)
+        {
+            const double se = (double)ord2f(A.scene[11 + a]) - (double)ord2f(A.scene[8 + a]);
+            d2 += (double)ext[a] * ext[a]; s2 += se * se;
+        }
+        if (d2 > 0.0625 * s2)          // box diagonal > 1/4 of the scene's
+        {
+            A.keys[i] = ~0ull;
+            A.vals[i] = i;
+            atomicAdd(&A.scene[14], 1);
+            return;
+        }
+    }
     unsigned long long code = 0;
     for (int a = 0; a < 3; a++)
     {
@@ -432,28 +460,48 @@ int build_flat_bvh_device(const float* tri9_host, int n_tri, int device, FlatBVH
     GCU(pool.get(&A.left, n)); GCU(pool.get(&A.right, n)); GCU(pool.get(&A.first, n)); GCU(pool.get(&A.last, n));
     GCU(pool.get(&A.parent_node, n)); GCU(pool.get(&A.parent_leaf, n));
     GCU(pool.get(&A.nlo, n)); GCU(pool.get(&A.nhi, n)); GCU(pool.get(&A.visits, n));
-    GCU(pool.get(&A.scene, 8));
+    GCU(pool.get(&A.scene, 16));
     int* d_misc = nullptr;                   // [0] max depth, [1] overflow flag
     GCU(pool.get(&d_misc, 4));
     GCU(cudaMemset(d_misc, 0, 4 * sizeof(int)));
     GCU(cudaMemset(A.visits, 0, n * sizeof(unsigned int)));
     {
-        const int init[8] = { INT32_MAX, INT32_MAX, INT32_MAX, INT32_MIN, INT32_MIN, INT32_MIN, INT32_MIN, 0 };
+        const int init[16] = { INT32_MAX, INT32_MAX, INT32_MAX, INT32_MIN, INT32_MIN, INT32_MIN, INT32_MIN, 0,
+                               INT32_MAX, INT32_MAX, INT32_MAX, INT32_MIN, INT32_MIN, INT32_MIN, 0, 0 };
         GCU(cudaMemcpy(A.scene, init, sizeof(init), cudaMemcpyHostToDevice));
     }
-    const int tb = 256, grid_n = (n_tri + tb - 1) / tb;
+    const int tb = 256;
+    int grid_n = (n_tri + tb - 1) / tb;
     lb_bounds<<<grid_n, tb>>>(A);
-    lb_morton<<<grid_n, tb>>>(A);
+    size_t sort_bytes = 0;
     {
         cub::DoubleBuffer<unsigned long long> dk(A.keys, A.keys_alt);
         cub::DoubleBuffer<int> dv(A.vals, A.vals_alt);
-        size_t tmp_bytes = 0;
-        GCU(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, dk, dv, n_tri, 0, 63));
-        char* tmp = nullptr;
-        GCU(pool.get(&tmp, tmp_bytes));
-        GCU(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, dk, dv, n_tri, 0, 63));
-        A.keys = dk.Current(); A.vals = dv.Current();
+        GCU(cub::DeviceRadixSort::SortPairs(nullptr, sort_bytes, dk, dv, n_tri, 0, 64));
     }
+    char* sort_tmp = nullptr;
+    GCU(pool.get(&sort_tmp, sort_bytes));
+    int n_large = 0;
+    for (int attempt = 0; attempt < 2; attempt++)
+    {
+        // first with the outsized triangles given the largest key (they sort to the end and stay out of the tree); if there are
+        // too many of them for a few top-level nodes, or too few others for a tree, once more with everything in the tree
+        A.segregate = attempt == 0 ? 1 : 0;
+        lb_morton<<<grid_n, tb>>>(A);
+        cub::DoubleBuffer<unsigned long long> dk(A.keys, A.keys_alt);
+        cub::DoubleBuffer<int> dv(A.vals, A.vals_alt);
+        GCU(cub::DeviceRadixSort::SortPairs(sort_tmp, sort_bytes, dk, dv, n_tri, 0, 64));
+        A.keys = dk.Current(); A.keys_alt = dk.Alternate(); A.vals = dv.Current(); A.vals_alt = dv.Alternate();
+        n_large = 0;
+        if (attempt == 0) GCU(cudaMemcpy(&n_large, A.scene + 14, sizeof(int), cudaMemcpyDeviceToHost));
+        if (n_large <= 45 && n_tri - n_large > kWideMaxLeaf) break;
+    }
+    std::vector<int> large_ids((size_t)n_large);
+    if (n_large) GCU(cudaMemcpy(large_ids.data(), A.vals + (n_tri - n_large), (size_t)n_large * sizeof(int), cudaMemcpyDeviceToHost));
+    const int n_all = n_tri;
+    n_tri -= n_large;                         // the tree is built over the first n_tri sorted triangles
+    A.n = n_tri;
+    grid_n = (n_tri + tb - 1) / tb;
     lb_tree<<<grid_n, tb>>>(A);
     lb_fit<<<grid_n, tb>>>(A, d_misc);
     int scene_h[8];
@@ -518,22 +566,31 @@ int build_flat_bvh_device(const float* tri9_host, int n_tri, int device, FlatBVH
     GCU(cudaGetLastError());
     if (misc_h[1]) { err = "wide BVH quantisation overflow"; return 1; }
 
-    out.wide.resize((size_t)n_wide); out.tris.resize(n); out.axis.resize((size_t)n_axis); out.diag.clear();
+    // room for the top level append_top_level may add: growing these vectors afterwards would copy gigabytes at 20 M triangles
+    out.wide.clear(); out.tris.clear(); out.axis.clear(); out.diag.clear();
+    out.wide.reserve((size_t)n_wide + 8); out.tris.reserve((size_t)n_all); out.axis.reserve((size_t)n_axis + 8);
+    out.wide.resize((size_t)n_wide); out.tris.resize((size_t)n_tri); out.axis.resize((size_t)n_axis);
     GCU(cudaMemcpy(out.wide.data(), d_wide, (size_t)n_wide * sizeof(WideNode), cudaMemcpyDeviceToHost));
-    GCU(cudaMemcpy(out.tris.data(), d_tris, n * sizeof(LeafTriangle), cudaMemcpyDeviceToHost));
+    GCU(cudaMemcpy(out.tris.data(), d_tris, (size_t)n_tri * sizeof(LeafTriangle), cudaMemcpyDeviceToHost));
     GCU(cudaMemcpy(out.axis.data(), d_axis, (size_t)n_axis * sizeof(AxisNode), cudaMemcpyDeviceToHost));
-    const auto t1 = std::chrono::high_resolution_clock::now();
     memset(&out.info, 0, sizeof(out.info));
-    out.info.n_triangles = n_tri;
+    out.info.n_triangles = n_all;
     out.info.n_inner_nodes = n_axis;
     out.info.n_leaves = n_axis + 1;
     out.info.max_leaf_size = kWideMaxLeaf;
     out.info.max_depth = misc_h[0];
     out.info.has_diag_slabs = 0;
-    out.info.build_seconds = std::chrono::duration<double>(t1 - t0).count();
     out.info.sah_cost = 0.0;
     out.info.n_wide_nodes = n_wide;
     out.info.wide_max_depth = wide_depth;
+    if (n_large)
+    {
+        std::sort(large_ids.begin(), large_ids.end());
+        try { append_top_level(out, tri9_host, large_ids, abs_pad); }
+        catch (const std::exception& e) { err = e.what(); return 1; }
+        if (out.info.max_depth > kMaxTraversalDepth || out.info.wide_max_depth > kMaxTraversalDepth) { err = "tree deeper than the traversal stack"; return 2; }
+    }
+    out.info.build_seconds = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
     return 0;
 }
 

@@ -212,7 +212,7 @@ __device__ __forceinline__ void trav_pop(Trav& T, TravStack& K)
 template <bool use_diag>
 __device__ __forceinline__ void trav_inner(const SceneDev& S, Trav& T, TravStack& K)
 {
-    const v3 o = T.o;
+
     const RaySlabs& rs = T.rs;
     const float tbest = T.tbest;
     {
