@@ -25,7 +25,7 @@ def timeit(fn, n=5):
     return min(ms), sum(ms) / len(ms)
 
 res = {}
-for flags, name in ((0, "7plane"), (4, "3plane")):
+for flags, name in ((4, "7plane binary"), (16, "3plane binary"), (64, "8-ary")):
     best, avg = timeit(lambda: sc.trace_primary_device(cam, w, h, prim.data_ptr(), t.data_ptr(), flags=flags, want_stats=True))
     res[f"c3_primary_{name}"] = dict(ms=best, mrays=w * h / best / 1e3)
 # secondary-like rays: from primary hit points, uniform random directions in the upper hemisphere of +y-ish / any direction
@@ -53,7 +53,7 @@ for name, gen in (("incoherent_sphere", lambda n: rng.normal(size=(n, 3))), ("up
         dr = torch.from_numpy(np.ascontiguousarray(rr)).to(dev)
         n = len(rr)
         dp = torch.empty(n, dtype=torch.int32, device=dev); dt = torch.empty(n, dtype=torch.float32, device=dev)
-        for flags, fname in ((0, "7plane"), (4, "3plane")):
+        for flags, fname in ((4, "7plane binary"), (16, "3plane binary"), (0, "8-ary")):
             for any_hit in (False, True):
                 best, avg = timeit(lambda: sc.trace_rays_device(dr.data_ptr(), n, dp.data_ptr(), dt.data_ptr(), any_hit=any_hit, flags=flags, want_stats=True))
                 res[f"c3_{name}_{order}_{fname}_{'any' if any_hit else 'closest'}"] = dict(ms=best, mrays=n / best / 1e3, n=n, hit_frac=float((dp >= (1 if any_hit else 0)).float().mean()))
