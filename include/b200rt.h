@@ -90,8 +90,10 @@ void b200rt_bvh_destroy(b200rt_bvh* bvh);
  * Replaces the 13-argument RenderKernel constructor's borrowed buffers (include/render_kernel.h:24-46,
  * source/main.cpp:95-106): everything is copied to HBM once and stays resident across renders.
  * tri_material has n_material_indices >= n_tri entries (analytic spheres index past the triangles, main.cpp:19-31).
- * env_cdf may be NULL: it is then computed exactly as Utils::compute_env_map_cdf does (utils.cpp:126-142).
- * bvh may be NULL: one is built with default options. device < 0 = the calling thread's current CUDA device. */
+ * env_cdf may be NULL: it is then computed on the device exactly as Utils::compute_env_map_cdf does (utils.cpp:126-142: the
+ * same serial float additions, bit for bit).
+ * bvh may be NULL: one is built with default options (host SAH builder; from 5 M triangles on, the device builder).
+ * device < 0 = the calling thread's current CUDA device. The calling thread's current device is left unchanged by every call. */
 int b200rt_scene_create(const float* tri_xyz9, int n_tri,
                         const int* tri_material, int n_material_indices,
                         const float* materials10, int n_materials,
@@ -100,13 +102,35 @@ int b200rt_scene_create(const float* tri_xyz9, int n_tri,
                         const float* env_rgba, int env_w, int env_h, const float* env_cdf_or_null,
                         const b200rt_bvh* bvh_or_null, int device,
                         b200rt_scene** out);
+/* Multi-GPU behind the boundary: the same scene replicated on n_devices GPUs of this process (devices_or_null ==
+ * NULL: devices 0 .. n_devices-1). b200rt_render / b200rt_render_rgba8 on such a scene cut the frame into interleaved 16x16
+ * tiles (tile_id % n_devices), render every share on its own device from its own host thread, gather the per-rank tile
+ * buffers on devices[0] with one peer copy per rank (NVLink) and do `framebuffer += final; tone map`
+ * (render_kernel.cpp:169-180) there — the incoming framebuffer is honoured and the result equals the 1-GPU frame bit for bit.
+ * The BVH is built once. A device may be listed more than once (several ranks then share it: how a one-GPU box exercises
+ * this path). env_channels: 4 = RGBA (Image), 3 = the RGB triplets stbi_loadf returns, expanded to RGBA with
+ * alpha 0 on the device (Utils::read_image_float, utils.cpp:113-121). */
+int b200rt_scene_create_multi(const float* tri_xyz9, int n_tri,
+                              const int* tri_material, int n_material_indices,
+                              const float* materials10, int n_materials,
+                              const int* emissive_tri, int n_emissive,
+                              const void* spheres20, int n_spheres,
+                              const float* env_pixels, int env_channels, int env_w, int env_h, const float* env_cdf_or_null,
+                              const b200rt_bvh* bvh_or_null, const int* devices_or_null, int n_devices,
+                              b200rt_scene** out);
+int b200rt_scene_device_count(const b200rt_scene* scene);
 void b200rt_scene_destroy(b200rt_scene* scene);
 /* replace the materials in place (C4 roughness/metalness sweeps re-use the resident geometry) */
 int b200rt_scene_set_materials(b200rt_scene* scene, const float* materials10, int n_materials);
-/* Builds the alias table of the environment map's luminance (Vose, in double; 8 bytes per texel on the device) that
- * B200RT_FLAG_ENV_ALIAS samples from. Replaces Utils::compute_env_map_cdf (utils.cpp:126-142) + env_map_cdf_search
- * (render_kernel.cpp:532-567) for callers that opt in. */
+/* Builds, ON THE DEVICE (csrc/env_tables.cu: three prefix sums and two binary searches per texel, in double), the alias table
+ * of the environment map's luminance that B200RT_FLAG_ENV_ALIAS samples from (8 bytes per texel). Replaces
+ * Utils::compute_env_map_cdf (utils.cpp:126-142) + env_map_cdf_search (render_kernel.cpp:532-567) for callers that opt in. */
 int b200rt_scene_build_env_alias(b200rt_scene* scene);
+/* the device-built table, downloaded: env_w*env_h acceptance probabilities and alias texels, *total_out = the luminance sum */
+int b200rt_scene_get_env_alias(b200rt_scene* scene, float* prob_out, int* alias_out, double* total_out_or_null);
+/* the running-sum CDF the integrator searches (the caller's, or — env_cdf_or_null == NULL at creation — the one the device
+ * computed in the reference's serial float order, Utils::compute_env_map_cdf, utils.cpp:126-142): env_w*env_h floats */
+int b200rt_scene_get_env_cdf(b200rt_scene* scene, float* cdf_out);
 /* the same table on the host, for callers / tests that want to look at it: env_w*env_h acceptance probabilities and alias
  * texels; *total_out (may be NULL) = the exact luminance sum the probabilities are normalised with. Host-only, no GPU needed. */
 int b200rt_env_alias_table(const float* env_rgba, int env_w, int env_h, float* prob_out, int* alias_out, double* total_out);
@@ -136,6 +160,11 @@ size_t b200rt_scene_device_bytes(const b200rt_scene* scene);
                                             Same per-texel probability lum/total in exact arithmetic, different draw -> texel map: the image agrees
                                             with the default statistically, not bit for bit. Needs b200rt_scene_build_env_alias(). */
 
+#define B200RT_FLAG_LINEAR_TILES 256     /* b200rt_render_tiles_device: the tile buffer receives each pixel's mean radiance (`final_color / spp`,
+                                            render_kernel.cpp:167) instead of the tone-mapped value; b200rt_untile_accumulate_device then does
+                                            `framebuffer += final; tone map` (:169-180) on the gathering device, so the incoming framebuffer is
+                                            honoured on the multi-GPU path without shipping it to every rank */
+
 typedef struct b200rt_render_options
 {
     int integrator;       /* B200RT_INTEGRATOR_* */
@@ -164,6 +193,32 @@ void b200rt_default_render_options(b200rt_render_options* opts);
 int b200rt_render(b200rt_scene* scene, const float* camera17, int width, int height, int spp, int max_bounces,
                   float* framebuffer_rgba_inout, const b200rt_render_options* opts_or_null, b200rt_stats* stats_or_null);
 
+/* Same as b200rt_render, but the frame leaves the GPU as RGBA8 — the bytes write_image_png would put into the PNG
+ * (source/image_io.cpp:165-182: x255, clamp, truncate; flip_y != 0 writes the bottom row last): 4 B/pixel over PCIe instead of
+ * 16. framebuffer_rgba_in_or_null is the incoming Image (NULL = Color::Black()); it is read, never written. */
+int b200rt_render_rgba8(b200rt_scene* scene, const float* camera17, int width, int height, int spp, int max_bounces,
+                        const float* framebuffer_rgba_in_or_null, int flip_y, unsigned char* out_rgba8,
+                        const b200rt_render_options* opts_or_null, b200rt_stats* stats_or_null);
+
+/* Replaces RenderKernel::ray_trace_pixel(x, y) (include/render_kernel.h:56, source/render_kernel.cpp:75-181) and the
+ * DEBUG_PIXEL single-pixel mode (:186-197) for a rectangle of pixels [x0, x1) x [y0, y1) of the width x height frame: the
+ * pixels keep the frame's coordinates, hence its camera rays and RNG seeds (31 + x*y*spp), so a crop equals the same
+ * pixels of the full render bit for bit. out_rgba: (y1-y0)*(x1-x0)*4 floats, row-major, row 0 = y0; the value each pixel
+ * would hold after render() on a Color::Black() framebuffer. One pixel: x1 = x0 + 1, y1 = y0 + 1. */
+int b200rt_render_region(b200rt_scene* scene, const float* camera17, int width, int height, int spp, int max_bounces,
+                         int x0, int y0, int x1, int y1, float* out_rgba, const b200rt_render_options* opts_or_null,
+                         b200rt_stats* stats_or_null);
+
+/* Parity hook for xorshift32_generator (include/xorshift.h:10-31) as ray_trace_pixel seeds it (render_kernel.cpp:77-82):
+ * *state_out = the generator state of pixel (x, y) after the 10 warm-up draws (seed 31 + x*y*spp in wrapping int arithmetic),
+ * floats_out[0..n) = the next n floats. Runs on the calling thread's current device. */
+int b200rt_rng_stream(int x, int y, int spp, int n, uint32_t* state_out, float* floats_out);
+
+/* Page-locked host memory for framebuffers / result arrays: copies from and to such buffers run at the full PCIe rate and are
+ * not staged. Pageable buffers are accepted everywhere too (staged through the library's own pinned chunks). */
+int b200rt_host_alloc(size_t bytes, void** out);
+void b200rt_host_free(void* p);
+
 /* Parity hook = RenderKernel::get_camera_ray + INTERSECT_SCENE for every pixel (render_kernel.cpp:56-73, :504-511).
  * sample < 0: un-jittered rays through (float)x,(float)y; sample >= 0: the jittered ray of that sample index of the
  * pixel's RNG stream ONLY IF sample == 0 (later samples depend on the path lengths before them).
@@ -189,6 +244,10 @@ int b200rt_render_tiles_device(b200rt_scene* scene, const float* camera17, int w
  * all-gather leaves them) -> row-major bottom-up RGBA image on the device */
 int b200rt_untile_device(b200rt_scene* scene, const void* dev_gathered_tiles, int tiles_per_rank_padded, int world,
                          int width, int height, void* dev_image_rgba, void* cuda_stream);
+/* As b200rt_untile_device, but for B200RT_FLAG_LINEAR_TILES tile buffers: dev_framebuffer_rgba_inout holds the incoming
+ * framebuffer and receives `fb += final; fb = tone_map(fb)` (render_kernel.cpp:169-180) in place. */
+int b200rt_untile_accumulate_device(b200rt_scene* scene, const void* dev_gathered_tiles, int tiles_per_rank_padded, int world,
+                                    int width, int height, void* dev_framebuffer_rgba_inout, void* cuda_stream);
 int b200rt_trace_primary_device(b200rt_scene* scene, const float* camera17, int width, int height, int sample, int spp_for_seed,
                                 void* dev_prim, void* dev_t, const b200rt_render_options* opts_or_null, void* cuda_stream,
                                 b200rt_stats* stats_or_null);

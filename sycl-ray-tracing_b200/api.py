@@ -114,18 +114,63 @@ for _name, _vals in _PRESETS.items():
     setattr(Camera, _name, Camera.from_array17(_hexrow(_vals)))
 
 
+class _PinnedOwner:
+    def __init__(self):
+        self._pinned = None
+
+    def __del__(self):
+        try:
+            if self._pinned:
+                B.load_library().b200rt_host_free(self._pinned)
+                self._pinned = None
+        except Exception:
+            pass
+
+
+def pinned_array(shape, dtype=np.float32, owner=None) -> np.ndarray:
+    """numpy array over page-locked host memory (b200rt_host_alloc). The memory lives as long as `owner` (default: an owner
+    object attached to the returned array's base)."""
+    n = int(np.prod(shape)) * np.dtype(dtype).itemsize
+    p = C.c_void_p()
+    B.check(B.load_library().b200rt_host_alloc(max(n, 1), C.byref(p)))
+    own = owner if owner is not None else _PinnedOwner()
+    own._pinned = p
+    buf = (C.c_ubyte * max(n, 1)).from_address(p.value)
+    buf._owner = own                      # keeps the allocation alive with the array
+    return np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+
+
+def rng_stream(x: int, y: int, spp: int, n: int = 16):
+    """The RNG stream of pixel (x, y) as ray_trace_pixel seeds it (render_kernel.cpp:77-82), computed on the GPU:
+    (state after the 10 warm-up draws, the next n floats)."""
+    st = C.c_uint32()
+    fl = np.zeros(n, np.float32)
+    B.check(B.load_library().b200rt_rng_stream(x, y, spp, n, C.byref(st), B.fptr(fl)))
+    return int(st.value), fl
+
+
 # ---- Image (image.h:25-178) ----------------------------------------------------------------------------------------------
 class Image:
     """RGBA float32, row-major, row 0 = bottom. Image(w, h) starts as Color::Black() = (0, 0, 0, 1)."""
 
-    def __init__(self, w: int = 0, h: int = 0, color=(0.0, 0.0, 0.0, 1.0), data=None):
+    def __init__(self, w: int = 0, h: int = 0, color=(0.0, 0.0, 0.0, 1.0), data=None, pinned: bool = False):
+        """pinned=True puts the pixels in page-locked memory (b200rt_host_alloc): renders then copy at the full PCIe rate."""
+        self._pinned = None
         if data is not None:
             d = _f32(data)
             assert d.ndim == 3 and d.shape[2] == 4
             self.pixels = d
         else:
-            self.pixels = np.empty((h, w, 4), np.float32)
+            self.pixels = pinned_array((h, w, 4), np.float32, self) if pinned else np.empty((h, w, 4), np.float32)
             self.pixels[...] = np.asarray(color, np.float32)
+
+    def __del__(self):
+        try:
+            if getattr(self, "_pinned", None):
+                B.load_library().b200rt_host_free(self._pinned)
+                self._pinned = None
+        except Exception:
+            pass
 
     def width(self):
         return self.pixels.shape[1]
@@ -274,7 +319,10 @@ def constant_env(value: float = 1.0e-20, w: int = 4, h: int = 2) -> np.ndarray:
 
 class Scene:
     def __init__(self, triangles, materials_indices, materials, emissive_triangle_indices, spheres=None, skysphere=None,
-                 env_map_cdf=None, bvh: BVH | None = None, device: int = -1):
+                 env_map_cdf=None, bvh: BVH | None = None, device: int = -1, devices=None):
+        """devices: a list of CUDA device ids (or an int N = devices 0..N-1) replicates the scene on several GPUs of this
+        process (b200rt_scene_create_multi); render() / render_rgba8() then partition every frame over them.
+        skysphere may be (h, w, 3): stb's RGB triplets, expanded to RGBA on the device (multi-device entry point only)."""
         L = B.load_library()
         self.tri = _f32(triangles).reshape(-1, 9)
         self.mat_idx = np.ascontiguousarray(materials_indices, np.int32)
@@ -289,15 +337,25 @@ class Scene:
             sph = rec.view(np.uint8)
             n_sph = len(spheres)
         env = constant_env() if skysphere is None else (skysphere.pixels if isinstance(skysphere, Image) else _f32(skysphere))
-        assert env.ndim == 3 and env.shape[2] == 4
+        assert env.ndim == 3 and env.shape[2] in (3, 4)
         self.env = np.ascontiguousarray(env)
         cdf = None if env_map_cdf is None else _f32(env_map_cdf)
         h = C.c_void_p()
-        B.check(L.b200rt_scene_create(
-            B.fptr(self.tri), len(self.tri), B.iptr(self.mat_idx), len(self.mat_idx), B.fptr(self.mats), len(self.mats),
-            B.iptr(self.emissive), len(self.emissive), sph.ctypes.data_as(C.c_void_p) if n_sph else None, n_sph,
-            B.fptr(self.env), self.env.shape[1], self.env.shape[0], B.fptr(cdf), bvh._h if bvh is not None else None,
-            device, C.byref(h)))
+        if devices is None and self.env.shape[2] == 4:
+            B.check(L.b200rt_scene_create(
+                B.fptr(self.tri), len(self.tri), B.iptr(self.mat_idx), len(self.mat_idx), B.fptr(self.mats), len(self.mats),
+                B.iptr(self.emissive), len(self.emissive), sph.ctypes.data_as(C.c_void_p) if n_sph else None, n_sph,
+                B.fptr(self.env), self.env.shape[1], self.env.shape[0], B.fptr(cdf), bvh._h if bvh is not None else None,
+                device, C.byref(h)))
+        else:
+            if devices is None:
+                devices = [device]
+            devs = np.arange(devices, dtype=np.int32) if isinstance(devices, int) else np.ascontiguousarray(devices, np.int32)
+            B.check(L.b200rt_scene_create_multi(
+                B.fptr(self.tri), len(self.tri), B.iptr(self.mat_idx), len(self.mat_idx), B.fptr(self.mats), len(self.mats),
+                B.iptr(self.emissive), len(self.emissive), sph.ctypes.data_as(C.c_void_p) if n_sph else None, n_sph,
+                B.fptr(self.env), self.env.shape[2], self.env.shape[1], self.env.shape[0], B.fptr(cdf),
+                bvh._h if bvh is not None else None, B.iptr(devs), len(devs), C.byref(h)))
         self._h = h
 
     def __del__(self):
@@ -315,6 +373,22 @@ class Scene:
 
     def device_bytes(self) -> int:
         return int(B.load_library().b200rt_scene_device_bytes(self._h))
+
+    def device_count(self) -> int:
+        return int(B.load_library().b200rt_scene_device_count(self._h))
+
+    def env_alias(self):
+        """The device-built alias table (b200rt_scene_get_env_alias): (prob, alias, total)."""
+        n = self.env.shape[0] * self.env.shape[1]
+        prob = np.empty(n, np.float32); alias = np.empty(n, np.int32); total = C.c_double()
+        B.check(B.load_library().b200rt_scene_get_env_alias(self._h, B.fptr(prob), B.iptr(alias), C.byref(total)))
+        return prob, alias, total.value
+
+    def env_cdf(self) -> np.ndarray:
+        """The CDF the integrator searches (device-computed when none was passed in)."""
+        out = np.empty(self.env.shape[0] * self.env.shape[1], np.float32)
+        B.check(B.load_library().b200rt_scene_get_env_cdf(self._h, B.fptr(out)))
+        return out
 
     def build_env_alias(self) -> None:
         """Alias table of the env map's luminance for FLAG_ENV_ALIAS renders (b200rt_scene_build_env_alias)."""
@@ -340,6 +414,33 @@ class Scene:
         B.check(B.load_library().b200rt_render(self._h, B.fptr(camera.as_array17()), w, h, spp, max_bounces,
                                                B.fptr(framebuffer), C.byref(o), C.byref(st)))
         return framebuffer, st.as_dict()
+
+    def render_rgba8(self, camera: Camera, w: int, h: int, spp: int, max_bounces: int, framebuffer: np.ndarray | None = None,
+                     flip_y: bool = True, out: np.ndarray | None = None, integrator: int = B.INTEGRATOR_WAVEFRONT, flags: int = 0):
+        """render() + write_image_png's quantisation on the device: returns ((h, w, 4) uint8, stats)."""
+        if out is None:
+            out = np.empty((h, w, 4), np.uint8)
+        assert out.dtype == np.uint8 and out.shape == (h, w, 4) and out.flags["C_CONTIGUOUS"]
+        if framebuffer is not None:
+            assert framebuffer.dtype == np.float32 and framebuffer.shape == (h, w, 4) and framebuffer.flags["C_CONTIGUOUS"]
+        st = B.Stats()
+        o = self._opts(integrator, flags, 0, 1)
+        B.check(B.load_library().b200rt_render_rgba8(self._h, B.fptr(camera.as_array17()), w, h, spp, max_bounces, B.fptr(framebuffer),
+                                                     1 if flip_y else 0, out.ctypes.data_as(C.POINTER(C.c_ubyte)), C.byref(o), C.byref(st)))
+        return out, st.as_dict()
+
+    def render_region(self, camera: Camera, w: int, h: int, spp: int, max_bounces: int, x0: int, y0: int, x1: int, y1: int, flags: int = 0):
+        """ray_trace_pixel(x, y) for every pixel of [x0, x1) x [y0, y1) of the w x h frame (b200rt_render_region)."""
+        out = np.empty((y1 - y0, x1 - x0, 4), np.float32)
+        st = B.Stats()
+        o = self._opts(B.INTEGRATOR_MEGAKERNEL, flags, 0, 1)
+        B.check(B.load_library().b200rt_render_region(self._h, B.fptr(camera.as_array17()), w, h, spp, max_bounces, x0, y0, x1, y1,
+                                                      B.fptr(out), C.byref(o), C.byref(st)))
+        return out, st.as_dict()
+
+    def ray_trace_pixel(self, camera: Camera, w: int, h: int, spp: int, max_bounces: int, x: int, y: int):
+        """RenderKernel::ray_trace_pixel(x, y) on a black framebuffer: the pixel's RGBA."""
+        return self.render_region(camera, w, h, spp, max_bounces, x, y, x + 1, y + 1)[0][0, 0]
 
     def trace_primary(self, camera: Camera, w: int, h: int, sample: int = -1, spp_for_seed: int = 1, flags: int = 0,
                       rank: int = 0, world: int = 1):
@@ -371,6 +472,11 @@ class Scene:
                                                             C.c_void_p(dev_tiles_ptr), C.byref(o), C.c_void_p(stream_ptr),
                                                             C.byref(st) if want_stats else None))
         return st.as_dict() if want_stats else None
+
+    def untile_accumulate_device(self, dev_gathered_ptr: int, tiles_per_rank_padded: int, world: int, w: int, h: int, dev_fb_inout_ptr: int,
+                                 stream_ptr: int = 0):
+        B.check(B.load_library().b200rt_untile_accumulate_device(self._h, C.c_void_p(dev_gathered_ptr), tiles_per_rank_padded, world, w, h,
+                                                                 C.c_void_p(dev_fb_inout_ptr), C.c_void_p(stream_ptr)))
 
     def untile_device(self, dev_gathered_ptr: int, tiles_per_rank_padded: int, world: int, w: int, h: int, dev_image_ptr: int,
                       stream_ptr: int = 0):
@@ -405,14 +511,14 @@ class RenderKernel:
 
     def __init__(self, width, height, render_samples, max_bounces, image_buffer: Image, triangle_buffer, materials_buffer,
                  emissive_triangle_indices, materials_indices, analytic_spheres=None, bvh: BVH | None = None,
-                 skysphere: Image | None = None, env_map_cdf=None, integrator: int = B.INTEGRATOR_WAVEFRONT, flags: int = 0):
+                 skysphere: Image | None = None, env_map_cdf=None, integrator: int = B.INTEGRATOR_WAVEFRONT, flags: int = 0, devices=None):
         self.m_width, self.m_height = int(width), int(height)
         self.m_render_samples, self.m_max_bounces = int(render_samples), int(max_bounces)
         self.m_frame_buffer = image_buffer
         self._args = (triangle_buffer, materials_indices, materials_buffer, emissive_triangle_indices, analytic_spheres, skysphere,
                       env_map_cdf, bvh)
         self.m_camera = Camera()
-        self.integrator, self.flags = integrator, flags
+        self.integrator, self.flags, self.devices = integrator, flags, devices
         self._scene = None
         self.last_stats = None
 
@@ -422,8 +528,14 @@ class RenderKernel:
     def scene(self) -> Scene:
         if self._scene is None:
             tri, mi, mats, em, sph, sky, cdf, bvh = self._args
-            self._scene = Scene(tri, mi, mats, em, spheres=sph, skysphere=sky, env_map_cdf=cdf, bvh=bvh)
+            self._scene = Scene(tri, mi, mats, em, spheres=sph, skysphere=sky, env_map_cdf=cdf, bvh=bvh, devices=self.devices)
         return self._scene
+
+    def ray_trace_pixel(self, x: int, y: int):
+        """render_kernel.h:56 / the DEBUG_PIXEL mode (render_kernel.cpp:186-197): renders one pixel into the framebuffer in place."""
+        px = self.scene().ray_trace_pixel(self.m_camera, self.m_width, self.m_height, self.m_render_samples, self.m_max_bounces, x, y)
+        self.m_frame_buffer.pixels[y, x] = px
+        return px
 
     def render(self):
         # the reference iterates the framebuffer's own size (render_kernel.cpp:199-201)

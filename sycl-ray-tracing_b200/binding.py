@@ -23,6 +23,7 @@ FLAG_BVH2 = 16
 FLAG_ENV_ALIAS = 32
 FLAG_BVH8 = 64
 FLAG_TIME_KERNELS = 128
+FLAG_LINEAR_TILES = 256
 TILE_DIM = 16
 TILE_PIXELS = 256
 
@@ -63,6 +64,8 @@ EXPORTS = [
     "b200rt_bvh_destroy", "b200rt_scene_create", "b200rt_scene_destroy", "b200rt_scene_set_materials", "b200rt_scene_build_env_alias", "b200rt_env_alias_table",
     "b200rt_scene_get_bvh_info", "b200rt_scene_device_bytes", "b200rt_default_render_options", "b200rt_render",
     "b200rt_trace_primary", "b200rt_trace_rays", "b200rt_tiles_for_rank", "b200rt_render_tiles_device",
+    "b200rt_scene_create_multi", "b200rt_scene_device_count", "b200rt_scene_get_env_alias", "b200rt_scene_get_env_cdf",
+    "b200rt_render_rgba8", "b200rt_render_region", "b200rt_rng_stream", "b200rt_host_alloc", "b200rt_host_free", "b200rt_untile_accumulate_device",
     "b200rt_untile_device", "b200rt_trace_primary_device", "b200rt_trace_rays_device", "b200rt_quantise_rgba8", "b200rt_quantise_rgba8_device", "b200rt_last_error", "b200rt_version",
 ]
 
@@ -91,6 +94,17 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     L.b200rt_bvh_destroy.argtypes = [VP]
     L.b200rt_bvh_destroy.restype = None
     L.b200rt_scene_create.argtypes = [FP, I, IP, I, FP, I, IP, I, VP, I, FP, I, I, FP, VP, I, C.POINTER(VP)]
+    L.b200rt_scene_create_multi.argtypes = [FP, I, IP, I, FP, I, IP, I, VP, I, FP, I, I, I, FP, VP, IP, I, C.POINTER(VP)]
+    L.b200rt_scene_device_count.argtypes = [VP]
+    L.b200rt_scene_get_env_alias.argtypes = [VP, FP, IP, C.POINTER(C.c_double)]
+    L.b200rt_scene_get_env_cdf.argtypes = [VP, FP]
+    L.b200rt_render_rgba8.argtypes = [VP, FP, I, I, I, I, FP, I, C.POINTER(C.c_ubyte), C.POINTER(RenderOptions), C.POINTER(Stats)]
+    L.b200rt_render_region.argtypes = [VP, FP, I, I, I, I, I, I, I, I, FP, C.POINTER(RenderOptions), C.POINTER(Stats)]
+    L.b200rt_rng_stream.argtypes = [I, I, I, I, C.POINTER(C.c_uint32), FP]
+    L.b200rt_host_alloc.argtypes = [C.c_size_t, C.POINTER(VP)]
+    L.b200rt_host_free.argtypes = [VP]
+    L.b200rt_host_free.restype = None
+    L.b200rt_untile_accumulate_device.argtypes = [VP, VP, I, I, I, I, VP, VP]
     L.b200rt_scene_destroy.argtypes = [VP]
     L.b200rt_scene_destroy.restype = None
     L.b200rt_scene_set_materials.argtypes = [VP, FP, I]

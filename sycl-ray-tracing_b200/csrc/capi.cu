@@ -7,6 +7,7 @@
 #include <cstring>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include <cuda_runtime.h>
@@ -29,6 +30,7 @@ struct b200rt_scene
     std::vector<void*> allocs;
     MaterialDev* d_mats = nullptr; int mats_cap = 0;
     std::vector<char> mat_used;           // material slots some primitive references (slot 0 of parse_obj is emissive but normally unused)
+    int max_mat_index = -1;               // highest material index any primitive references: every later material set must cover it
     // per-scene scratch, grown on demand and kept across calls
     unsigned int* d_work = nullptr;
     unsigned long long* d_rays = nullptr;
@@ -40,11 +42,18 @@ struct b200rt_scene
     WfGroup wf[kMaxWfGroups]{}; int wf_groups = 0; std::vector<void*> wf_allocs; int wf_cap[kMaxWfGroups] = {};   // slots allocated per group
     unsigned int* h_active = nullptr;     // pinned, one word per group
     cudaEvent_t fork_event = nullptr;
-    std::vector<float> env_lum;           // per-texel luminance as the integrator computes it (image.h:80-85), kept for the alias table
+    float* d_env_lum = nullptr;           // per-texel luminance as the integrator computes it (image.h:80-85), kept for the alias table
     float2* d_alias = nullptr; float alias_total = 0.0f;
     void* bvh_window = nullptr; size_t bvh_window_bytes = 0;   // 8-ary nodes + triangles, kept resident in L2 (see pin_bvh_in_l2)
     bool l2_pinned = false, l2_window_set = false;
     double kernel_times[4] = {};          // B200RT_FLAG_TIME_KERNELS: trace ms, shade ms, trace launches, shade launches of the last render
+    // multi-GPU scenes (b200rt_scene_create_multi): this scene is rank 0; replicas[i] is rank i + 1 on another device, owned here
+    std::vector<b200rt_scene*> replicas;
+    float4* d_gather = nullptr; size_t gather_cap = 0;      // rank 0: world per-rank tile buffers, rank-major (the peer copies' destination)
+    cudaStream_t mg_stream = nullptr;                       // per device: the stream a multi-GPU frame runs on
+    unsigned char* d_rgba8 = nullptr; size_t rgba8_cap = 0; // output stage scratch (b200rt_render_rgba8)
+    // pinned staging for copies from / to pageable caller memory: two chunks, ping-pong
+    void* h_stage[2] = { nullptr, nullptr }; cudaEvent_t stage_ev[2] = { nullptr, nullptr };
 };
 
 namespace {
@@ -68,6 +77,26 @@ int fail(int code, const char* fmt, ...)
         if (e__ != cudaSuccess) return fail(B200RT_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__)); \
     } while (0)
 
+// Makes `device` current for the lifetime of the guard and restores the caller's device afterwards: the library must not
+// change the calling thread's current device behind its back (torch and other CUDA users share the thread).
+struct DeviceScope
+{
+    int prev = -1;
+    cudaError_t err = cudaSuccess;
+    explicit DeviceScope(int device)
+    {
+        err = cudaGetDevice(&prev);
+        if (err == cudaSuccess && prev != device) err = cudaSetDevice(device);
+        else if (err == cudaSuccess) prev = -1;          // nothing to restore
+    }
+    ~DeviceScope() { if (prev >= 0) cudaSetDevice(prev); }
+    DeviceScope(const DeviceScope&) = delete;
+    DeviceScope& operator=(const DeviceScope&) = delete;
+};
+#define ON_DEVICE(dev)                                                                                          \
+    DeviceScope device_scope__(dev);                                                                             \
+    if (device_scope__.err != cudaSuccess) return fail(B200RT_ERR_CUDA, "cudaSetDevice(%d) failed: %s", (dev), cudaGetErrorString(device_scope__.err))
+
 template <typename T>
 int upload(b200rt_scene* s, const T* host, size_t n, const T** dev_out)
 {
@@ -78,6 +107,18 @@ int upload(b200rt_scene* s, const T* host, size_t n, const T** dev_out)
     s->bytes += bytes;
     if (n) CU(cudaMemcpy(d, host, n * sizeof(T), cudaMemcpyHostToDevice));
     *dev_out = d;
+    return B200RT_OK;
+}
+
+template <typename T>
+int device_alloc(b200rt_scene* s, T** out, size_t n)
+{
+    T* d = nullptr;
+    const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    CU(cudaMalloc(&d, bytes));
+    s->allocs.push_back(d);
+    s->bytes += bytes;
+    *out = d;
     return B200RT_OK;
 }
 
@@ -101,6 +142,7 @@ int make_params(const b200rt_scene* s, const float* camera17, int w, int h, int 
     P.tiles_y = (h + kTileDim - 1) / kTileDim;
     P.n_rank_tiles = b200rt_tiles_for_rank(w, h, d.rank, d.world);
     P.flags = d.flags;
+    P.rx0 = P.ry0 = P.rw = P.rh = 0;
     return B200RT_OK;
 }
 
@@ -135,6 +177,96 @@ int ensure_scratch(b200rt_scene* s, size_t tile_px, size_t image_px, size_t prim
         CU(cudaMalloc(&s->d_prim, prim_px * sizeof(int)));
         CU(cudaMalloc(&s->d_t, prim_px * sizeof(float)));
         s->prim_cap = prim_px;
+    }
+    return B200RT_OK;
+}
+
+
+// ---- host <-> device copies -----------------------------------------------------------------------------------------------------
+// Caller buffers may be pageable (std::vector, numpy) or page-locked (b200rt_host_alloc, cudaHostRegister). Page-locked memory
+// is copied directly at the PCIe rate. Pageable memory goes through two pinned chunks owned by the scene: the DMA of one
+// chunk overlaps the host memcpy of the other (a plain cudaMemcpy on pageable memory does the same inside the driver, one
+// thread and smaller chunks).
+constexpr size_t kStageChunk = 8u << 20;
+
+bool host_pointer_is_pinned(const void* p)
+{
+    cudaPointerAttributes a;
+    if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+    return a.type == cudaMemoryTypeHost || a.type == cudaMemoryTypeManaged;
+}
+
+void host_memcpy(void* dst, const void* src, size_t bytes)
+{
+    constexpr size_t kBlock = 1u << 20;
+    const long long n_blocks = (long long)((bytes + kBlock - 1) / kBlock);
+    if (n_blocks < 4) { std::memcpy(dst, src, bytes); return; }
+#pragma omp parallel for schedule(static)
+    for (long long b = 0; b < n_blocks; b++)
+    {
+        const size_t off = (size_t)b * kBlock;
+        std::memcpy((char*)dst + off, (const char*)src + off, std::min(kBlock, bytes - off));
+    }
+}
+
+int ensure_stage(b200rt_scene* s)
+{
+    if (s->h_stage[0]) return B200RT_OK;
+    for (int i = 0; i < 2; i++)
+    {
+        CU(cudaMallocHost(&s->h_stage[i], kStageChunk));
+        CU(cudaEventCreateWithFlags(&s->stage_ev[i], cudaEventDisableTiming));
+    }
+    return B200RT_OK;
+}
+
+// asynchronous with respect to the host only for pinned sources; in both cases `src` may be reused when the call returns
+// only after the stream has been synchronised (pinned) or immediately (pageable: it has been copied out)
+int copy_to_device(b200rt_scene* s, void* dst_dev, const void* src_host, size_t bytes, cudaStream_t st)
+{
+    if (!bytes) return B200RT_OK;
+    if (host_pointer_is_pinned(src_host)) { CU(cudaMemcpyAsync(dst_dev, src_host, bytes, cudaMemcpyHostToDevice, st)); return B200RT_OK; }
+    int rc = ensure_stage(s);
+    if (rc) return rc;
+    size_t off = 0;
+    for (int i = 0; off < bytes; i++, off += kStageChunk)
+    {
+        const int b = i & 1;
+        const size_t n = std::min(kStageChunk, bytes - off);
+        if (i >= 2) CU(cudaEventSynchronize(s->stage_ev[b]));            // the DMA that last read this chunk has finished
+        host_memcpy(s->h_stage[b], (const char*)src_host + off, n);
+        CU(cudaMemcpyAsync((char*)dst_dev + off, s->h_stage[b], n, cudaMemcpyHostToDevice, st));
+        CU(cudaEventRecord(s->stage_ev[b], st));
+    }
+    return B200RT_OK;
+}
+
+// blocking: returns when dst_host holds the data
+int copy_to_host(b200rt_scene* s, void* dst_host, const void* src_dev, size_t bytes, cudaStream_t st)
+{
+    if (!bytes) { CU(cudaStreamSynchronize(st)); return B200RT_OK; }
+    if (host_pointer_is_pinned(dst_host))
+    {
+        CU(cudaMemcpyAsync(dst_host, src_dev, bytes, cudaMemcpyDeviceToHost, st));
+        CU(cudaStreamSynchronize(st));
+        return B200RT_OK;
+    }
+    int rc = ensure_stage(s);
+    if (rc) return rc;
+    const size_t n_chunks = (bytes + kStageChunk - 1) / kStageChunk;
+    auto issue = [&](size_t i) -> cudaError_t {
+        const size_t off = i * kStageChunk, n = std::min(kStageChunk, bytes - off);
+        cudaError_t e = cudaMemcpyAsync(s->h_stage[i & 1], (const char*)src_dev + off, n, cudaMemcpyDeviceToHost, st);
+        return e != cudaSuccess ? e : cudaEventRecord(s->stage_ev[i & 1], st);
+    };
+    CU(issue(0));
+    if (n_chunks > 1) CU(issue(1));
+    for (size_t i = 0; i < n_chunks; i++)
+    {
+        const size_t off = i * kStageChunk, n = std::min(kStageChunk, bytes - off);
+        CU(cudaEventSynchronize(s->stage_ev[i & 1]));
+        host_memcpy((char*)dst_host + off, s->h_stage[i & 1], n);
+        if (i + 2 < n_chunks) CU(issue(i + 2));
     }
     return B200RT_OK;
 }
@@ -258,7 +390,9 @@ int run_integrator(b200rt_scene* s, const RenderParams& P, int integrator, const
         int rc = ensure_wavefront(s, P);
         if (rc) return rc;
         if (!s->l2_window_set) { if ((rc = pin_bvh_in_l2(s, nullptr))) return rc; s->l2_window_set = true; }
-        CU(run_wavefront(dev, P, s->wf, s->wf_groups, fb_in, out_tiles, st, s->fork_event, launches, s->kernel_times));
+        unsigned int unfinished = 0;
+        CU(run_wavefront(dev, P, s->wf, s->wf_groups, fb_in, out_tiles, st, s->fork_event, launches, s->kernel_times, &unfinished));
+        if (unfinished) return fail(B200RT_ERR_CUDA, "wavefront integrator: %u pixels unfinished after spp * (max_bounces + 1) iterations", unfinished);
         CU(wavefront_sum_rays(s->wf, s->wf_groups, s->d_rays, st));
         *launches += 1;
         return B200RT_OK;
@@ -333,13 +467,15 @@ int b200rt_bvh_build_device(const float* tri_xyz9, int n_tri, int device, b200rt
     if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) return fail(B200RT_ERR_CUDA, "no CUDA device: b200rt_bvh_build_device has no CPU fallback");
     if (device < 0) CU(cudaGetDevice(&device));
     if (device >= n_dev) return fail(B200RT_ERR_ARG, "device %d of %d", device, n_dev);
+    ON_DEVICE(device);
     b200rt_bvh* b = new (std::nothrow) b200rt_bvh;
     if (!b) return fail(B200RT_ERR_ALLOC, "out of host memory");
     std::string err;
     int rc = 1;
     try { rc = build_flat_bvh_device(tri_xyz9, n_tri, device, b->flat, err); }
     catch (const std::exception& e) { err = e.what(); rc = 1; }
-    if (rc) { delete b; return fail(rc == 2 ? B200RT_ERR_ARG : B200RT_ERR_CUDA, "device BVH build: %s", err.c_str()); }
+    if (rc == 2) { delete b; return b200rt_bvh_build(tri_xyz9, n_tri, nullptr, out); }     // radix tree deeper than the traversal stack: host SAH builder
+    if (rc) { delete b; return fail(B200RT_ERR_CUDA, "device BVH build: %s", err.c_str()); }
     *out = b;
     return B200RT_OK;
 }
@@ -378,126 +514,225 @@ int b200rt_bvh_check(const b200rt_bvh* bvh, const float* tri_xyz9, int n_tri)
 
 void b200rt_bvh_destroy(b200rt_bvh* bvh) { delete bvh; }
 
+} // extern "C"
+
+namespace {
+
+struct SceneArgs
+{
+    const float* tri_xyz9; int n_tri;
+    const int* tri_material; int n_material_indices;
+    const float* materials10; int n_materials;
+    const int* emissive_tri; int n_emissive;
+    const void* spheres20; int n_spheres;
+    const float* env_rgba; int env_w, env_h; const float* env_cdf_or_null;
+    int env_channels;       // 4 = Image (RGBA); 3 = stbi_loadf's RGB triplets, expanded on the device (utils.cpp:113-121)
+};
+
+int validate_scene_args(const SceneArgs& a)
+{
+    if (a.n_tri < 0 || (a.n_tri > 0 && !a.tri_xyz9)) return fail(B200RT_ERR_ARG, "bad triangle buffer");
+    if (a.n_material_indices < a.n_tri || (a.n_material_indices > 0 && !a.tri_material)) return fail(B200RT_ERR_ARG, "need one material index per triangle");
+    if (a.n_materials <= 0 || !a.materials10) return fail(B200RT_ERR_ARG, "need at least one material");
+    if (a.n_emissive < 0 || (a.n_emissive > 0 && !a.emissive_tri)) return fail(B200RT_ERR_ARG, "bad emissive triangle list");
+    if (a.n_spheres < 0 || (a.n_spheres > 0 && !a.spheres20)) return fail(B200RT_ERR_ARG, "bad sphere buffer");
+    if (a.env_channels != 3 && a.env_channels != 4) return fail(B200RT_ERR_ARG, "env_channels must be 3 (RGB) or 4 (RGBA)");
+    if (!a.env_rgba || a.env_w <= 0 || a.env_h <= 0)
+        return fail(B200RT_ERR_ARG, "an environment map is required (the reference samples it unconditionally, render_kernel.cpp:114)");
+    for (int i = 0; i < a.n_material_indices; i++)
+        if (a.tri_material[i] < 0 || a.tri_material[i] >= a.n_materials) return fail(B200RT_ERR_ARG, "material index %d of primitive %d out of range", a.tri_material[i], i);
+    for (int i = 0; i < a.n_emissive; i++)
+        if (a.emissive_tri[i] < 0 || a.emissive_tri[i] >= a.n_tri) return fail(B200RT_ERR_ARG, "emissive triangle index out of range");
+    return B200RT_OK;
+}
+
+// host-side products shared by every device replica of a scene (computed once)
+struct SceneHostData
+{
+    std::vector<float4> bvh_and_tris; size_t n_wide4 = 0;
+    std::vector<unsigned char> oct_lut;
+    std::vector<int> slot_of_prim;
+    std::vector<SphereDev> spheres;
+};
+
+void prepare_host_data(const SceneArgs& a, const FlatBVH& f, SceneHostData& h)
+{
+    // the 8-ary nodes and the triangle stream share one allocation: one L2 access-policy window covers everything a ray fetches
+    const size_t nw = f.wide.size() * 5, nt = f.tris.size() * 3;
+    h.bvh_and_tris.resize(std::max<size_t>(nw + nt, 1));
+    if (nw) std::memcpy(h.bvh_and_tris.data(), f.wide.data(), nw * sizeof(float4));
+    if (nt) std::memcpy(h.bvh_and_tris.data() + nw, f.tris.data(), nt * sizeof(float4));
+    h.n_wide4 = nw;
+    h.oct_lut.resize(8 * 256);
+    for (int o = 0; o < 8; o++)
+        for (int m = 0; m < 256; m++)
+        {
+            unsigned r = 0;
+            for (int b = 0; b < 8; b++) if (m & (1 << b)) r |= 1u << (b ^ o);
+            h.oct_lut[(size_t)o * 256 + m] = (unsigned char)r;
+        }
+    h.slot_of_prim.assign((size_t)std::max(a.n_tri, 1), 0);
+    for (size_t i = 0; i < f.tris.size(); i++) h.slot_of_prim[f.tris[i].prim] = (int)i;
+    h.spheres.resize((size_t)std::max(a.n_spheres, 1));
+    for (int i = 0; i < a.n_spheres; i++) std::memcpy(&h.spheres[i], (const char*)a.spheres20 + 20 * (size_t)i, 20);
+}
+
+// uploads one replica of the scene to `device`
+int create_on_device(const SceneArgs& a, const FlatBVH& f, const SceneHostData& h, int device, b200rt_scene** out)
+{
+    *out = nullptr;
+    ON_DEVICE(device);
+    b200rt_scene* s = new (std::nothrow) b200rt_scene;
+    if (!s) return fail(B200RT_ERR_ALLOC, "out of host memory");
+    s->device = device;
+    s->info = f.info;
+    s->mat_used.assign((size_t)a.n_materials, 0);
+    for (int i = 0; i < a.n_material_indices; i++) { s->mat_used[a.tri_material[i]] = 1; s->max_mat_index = std::max(s->max_mat_index, a.tri_material[i]); }
+    int rc = B200RT_OK;
+    do
+    {
+        const size_t nt = f.tris.size() * 3;
+        if ((rc = upload(s, h.bvh_and_tris.data(), h.n_wide4 + nt, &s->dev.wide))) break;
+        s->dev.tris = s->dev.wide + h.n_wide4;
+        s->bvh_window = const_cast<float4*>(s->dev.wide);
+        s->bvh_window_bytes = (h.n_wide4 + nt) * sizeof(float4);
+        s->dev.has_wide = f.wide.empty() ? 0 : 1;
+        s->dev.qmagic = 0x43000000u;
+        if ((rc = upload(s, h.oct_lut.data(), h.oct_lut.size(), &s->dev.oct_lut))) break;
+        if ((rc = upload(s, reinterpret_cast<const float4*>(f.axis.data()), f.axis.size() * 4, &s->dev.axis))) break;
+        if ((rc = upload(s, reinterpret_cast<const float4*>(f.diag.data()), f.diag.size() * 4, &s->dev.diag))) break;
+        if ((rc = upload(s, h.slot_of_prim.data(), (size_t)a.n_tri, &s->dev.slot_of_prim))) break;
+        if ((rc = upload(s, a.tri_material, (size_t)a.n_material_indices, &s->dev.mat_idx))) break;
+        if ((rc = upload(s, a.emissive_tri, (size_t)a.n_emissive, &s->dev.emissive))) break;
+        if ((rc = upload(s, h.spheres.data(), (size_t)a.n_spheres, &s->dev.spheres))) break;
+        const size_t n_texels = (size_t)a.env_w * a.env_h;
+        if (a.env_channels == 3)
+        {
+            float4* d_env = nullptr;
+            if ((rc = device_alloc(s, &d_env, n_texels))) break;
+            float* tmp = nullptr;
+            cudaError_t ce = cudaMalloc(&tmp, n_texels * 3 * sizeof(float));
+            if (ce == cudaSuccess) ce = cudaMemcpy(tmp, a.env_rgba, n_texels * 3 * sizeof(float), cudaMemcpyHostToDevice);
+            if (ce == cudaSuccess) ce = launch_env_expand_rgb(tmp, n_texels, d_env, 0);
+            if (ce == cudaSuccess) ce = cudaDeviceSynchronize();
+            cudaFree(tmp);
+            if (ce != cudaSuccess) { rc = fail(B200RT_ERR_CUDA, "env RGB -> RGBA: %s", cudaGetErrorString(ce)); break; }
+            s->dev.env = d_env;
+        }
+        else if ((rc = upload(s, reinterpret_cast<const float4*>(a.env_rgba), n_texels, &s->dev.env))) break;
+        s->dev.n_tri = a.n_tri; s->dev.n_emissive = a.n_emissive; s->dev.n_spheres = a.n_spheres;
+        s->dev.env_w = a.env_w; s->dev.env_h = a.env_h;
+        s->dev.has_diag = f.info.has_diag_slabs;
+        // env tables (K5, env_tables.cu): per-texel luminance, the running-sum CDF in the reference's serial float order
+        // (Utils::compute_env_map_cdf, utils.cpp:126-142) unless the caller brings its own, and the last-column copy the row search probes
+        float* d_lum = nullptr; float* d_cdf = nullptr; float* d_row = nullptr;
+        if ((rc = device_alloc(s, &d_lum, n_texels)) || (rc = device_alloc(s, &d_cdf, n_texels)) || (rc = device_alloc(s, &d_row, (size_t)a.env_h))) break;
+        cudaError_t ce = launch_env_luminance(s->dev.env, n_texels, d_lum, 0);
+        if (ce == cudaSuccess)
+        {
+            if (a.env_cdf_or_null) ce = cudaMemcpy(d_cdf, a.env_cdf_or_null, n_texels * sizeof(float), cudaMemcpyHostToDevice);
+            else ce = launch_env_cdf_serial(d_lum, n_texels, d_cdf, 0);
+        }
+        if (ce == cudaSuccess) ce = launch_env_row_cdf(d_cdf, a.env_w, a.env_h, d_row, 0);
+        if (ce == cudaSuccess) ce = cudaMemcpy(&s->dev.cdf_total, d_cdf + n_texels - 1, sizeof(float), cudaMemcpyDeviceToHost);
+        if (ce != cudaSuccess) { rc = fail(B200RT_ERR_CUDA, "env tables: %s", cudaGetErrorString(ce)); break; }
+        s->dev.cdf = d_cdf; s->dev.row_cdf = d_row; s->d_env_lum = d_lum;
+    } while (0);
+    if (rc) { b200rt_scene_destroy(s); return rc; }
+    rc = b200rt_scene_set_materials(s, a.materials10, a.n_materials);
+    if (rc) { b200rt_scene_destroy(s); return rc; }
+    *out = s;
+    return B200RT_OK;
+}
+
+int create_scene(const SceneArgs& a, const b200rt_bvh* bvh_or_null, const int* devices, int n_devices, b200rt_scene** out)
+{
+    if (!out) return fail(B200RT_ERR_ARG, "out must not be NULL");
+    *out = nullptr;
+    int rc = validate_scene_args(a);
+    if (rc) return rc;
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0)
+        return fail(B200RT_ERR_CUDA, "no CUDA device: b200rt has no CPU fallback");
+    if (n_devices <= 0 || n_devices > 64) return fail(B200RT_ERR_ARG, "bad device count %d", n_devices);
+    std::vector<int> devs((size_t)n_devices);
+    for (int i = 0; i < n_devices; i++)
+    {
+        int d = devices ? devices[i] : -1;
+        if (d < 0) { if (n_devices > 1) d = i; else CU(cudaGetDevice(&d)); }
+        if (d >= n_dev) return fail(B200RT_ERR_ARG, "device %d of %d", d, n_dev);
+        devs[i] = d;
+    }
+
+    b200rt_bvh* own = nullptr;
+    const b200rt_bvh* bvh = bvh_or_null;
+    if (!bvh)
+    {
+        // above ~5 M triangles the host SAH build dominates the whole job (12.5 s at 20 M): build on the GPU instead
+        static const int device_build_threshold = []() { const char* e = getenv("B200RT_DEVICE_BUILD_MIN_TRIS"); return e ? atoi(e) : 5000000; }();
+        rc = a.n_tri >= device_build_threshold ? b200rt_bvh_build_device(a.tri_xyz9, a.n_tri, devs[0], &own) : b200rt_bvh_build(a.tri_xyz9, a.n_tri, nullptr, &own);
+        if (rc) return rc;
+        bvh = own;
+    }
+    if (bvh->flat.info.n_triangles != a.n_tri) { delete own; return fail(B200RT_ERR_ARG, "BVH was built for %d triangles, scene has %d", bvh->flat.info.n_triangles, a.n_tri); }
+
+    SceneHostData h;
+    prepare_host_data(a, bvh->flat, h);
+    b200rt_scene* first = nullptr;
+    rc = create_on_device(a, bvh->flat, h, devs[0], &first);
+    for (int i = 1; i < n_devices && !rc; i++)
+    {
+        b200rt_scene* r = nullptr;
+        rc = create_on_device(a, bvh->flat, h, devs[i], &r);
+        if (!rc) first->replicas.push_back(r);
+    }
+    delete own;
+    if (rc) { if (first) b200rt_scene_destroy(first); return rc; }
+    if (n_devices > 1)
+    {
+        // peer access towards rank 0's device: the per-rank tile buffers are copied GPU to GPU (NVLink) at the end of a frame
+        for (b200rt_scene* r : first->replicas)
+        {
+            DeviceScope scope(r->device);
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, r->device, first->device) == cudaSuccess && can)
+            {
+                const cudaError_t pe = cudaDeviceEnablePeerAccess(first->device, 0);
+                if (pe != cudaSuccess) cudaGetLastError();      // already enabled (or unsupported: the copy is then staged by the driver)
+            }
+        }
+    }
+    *out = first;
+    return B200RT_OK;
+}
+
+} // namespace
+
+extern "C" {
+
 int b200rt_scene_create(const float* tri_xyz9, int n_tri, const int* tri_material, int n_material_indices,
                         const float* materials10, int n_materials, const int* emissive_tri, int n_emissive,
                         const void* spheres20, int n_spheres,
                         const float* env_rgba, int env_w, int env_h, const float* env_cdf_or_null,
                         const b200rt_bvh* bvh_or_null, int device, b200rt_scene** out)
 {
-    if (!out) return fail(B200RT_ERR_ARG, "out must not be NULL");
-    *out = nullptr;
-    if (n_tri < 0 || (n_tri > 0 && !tri_xyz9)) return fail(B200RT_ERR_ARG, "bad triangle buffer");
-    if (n_material_indices < n_tri || (n_material_indices > 0 && !tri_material)) return fail(B200RT_ERR_ARG, "need one material index per triangle");
-    if (n_materials <= 0 || !materials10) return fail(B200RT_ERR_ARG, "need at least one material");
-    if (n_emissive < 0 || (n_emissive > 0 && !emissive_tri)) return fail(B200RT_ERR_ARG, "bad emissive triangle list");
-    if (n_spheres < 0 || (n_spheres > 0 && !spheres20)) return fail(B200RT_ERR_ARG, "bad sphere buffer");
-    if (!env_rgba || env_w <= 0 || env_h <= 0)
-        return fail(B200RT_ERR_ARG, "an environment map is required (the reference samples it unconditionally, render_kernel.cpp:114)");
-    for (int i = 0; i < n_material_indices; i++)
-        if (tri_material[i] < 0 || tri_material[i] >= n_materials) return fail(B200RT_ERR_ARG, "material index %d of primitive %d out of range", tri_material[i], i);
-    for (int i = 0; i < n_emissive; i++)
-        if (emissive_tri[i] < 0 || emissive_tri[i] >= n_tri) return fail(B200RT_ERR_ARG, "emissive triangle index out of range");
-
-    int n_dev = 0;
-    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0)
-        return fail(B200RT_ERR_CUDA, "no CUDA device: b200rt has no CPU fallback");
-    if (device < 0) CU(cudaGetDevice(&device));
-    if (device >= n_dev) return fail(B200RT_ERR_ARG, "device %d of %d", device, n_dev);
-    CU(cudaSetDevice(device));
-
-    b200rt_bvh* own = nullptr;
-    const b200rt_bvh* bvh = bvh_or_null;
-    if (!bvh)
-    {
-        int r = b200rt_bvh_build(tri_xyz9, n_tri, nullptr, &own);
-        if (r) return r;
-        bvh = own;
-    }
-    if (bvh->flat.info.n_triangles != n_tri) { delete own; return fail(B200RT_ERR_ARG, "BVH was built for %d triangles, scene has %d", bvh->flat.info.n_triangles, n_tri); }
-
-    b200rt_scene* s = new (std::nothrow) b200rt_scene;
-    if (!s) { delete own; return fail(B200RT_ERR_ALLOC, "out of host memory"); }
-    s->device = device;
-    s->info = bvh->flat.info;
-    s->mat_used.assign((size_t)n_materials, 0);
-    for (int i = 0; i < n_material_indices; i++) s->mat_used[tri_material[i]] = 1;
-    int rc = B200RT_OK;
-    do
-    {
-        const FlatBVH& f = bvh->flat;
-        {
-            // the 8-ary nodes and the triangle stream share one allocation: one L2 access-policy window covers everything a ray fetches
-            const size_t nw = f.wide.size() * 5, nt = f.tris.size() * 3;
-            std::vector<float4> both(std::max<size_t>(nw + nt, 1));
-            if (nw) std::memcpy(both.data(), f.wide.data(), nw * sizeof(float4));
-            if (nt) std::memcpy(both.data() + nw, f.tris.data(), nt * sizeof(float4));
-            if ((rc = upload(s, both.data(), nw + nt, &s->dev.wide))) break;
-            s->dev.tris = s->dev.wide + nw;
-            s->bvh_window = const_cast<float4*>(s->dev.wide);
-            s->bvh_window_bytes = (nw + nt) * sizeof(float4);
-        }
-        s->dev.has_wide = f.wide.empty() ? 0 : 1;
-        s->dev.qmagic = 0x43000000u;
-        {
-            std::vector<unsigned char> lut(8 * 256);
-            for (int o = 0; o < 8; o++)
-                for (int m = 0; m < 256; m++)
-                {
-                    unsigned r = 0;
-                    for (int b = 0; b < 8; b++) if (m & (1 << b)) r |= 1u << (b ^ o);
-                    lut[(size_t)o * 256 + m] = (unsigned char)r;
-                }
-            if ((rc = upload(s, lut.data(), lut.size(), &s->dev.oct_lut))) break;
-        }
-        if ((rc = upload(s, reinterpret_cast<const float4*>(f.axis.data()), f.axis.size() * 4, &s->dev.axis))) break;
-        if ((rc = upload(s, reinterpret_cast<const float4*>(f.diag.data()), f.diag.size() * 4, &s->dev.diag))) break;
-        std::vector<int> slot_of_prim((size_t)std::max(n_tri, 1), 0);
-        for (size_t i = 0; i < f.tris.size(); i++) slot_of_prim[f.tris[i].prim] = (int)i;
-        if ((rc = upload(s, slot_of_prim.data(), (size_t)n_tri, &s->dev.slot_of_prim))) break;
-        if ((rc = upload(s, tri_material, (size_t)n_material_indices, &s->dev.mat_idx))) break;
-        if ((rc = upload(s, emissive_tri, (size_t)n_emissive, &s->dev.emissive))) break;
-        std::vector<SphereDev> sph((size_t)std::max(n_spheres, 1));
-        for (int i = 0; i < n_spheres; i++) std::memcpy(&sph[i], (const char*)spheres20 + 20 * (size_t)i, 20);
-        if ((rc = upload(s, sph.data(), (size_t)n_spheres, &s->dev.spheres))) break;
-        if ((rc = upload(s, reinterpret_cast<const float4*>(env_rgba), (size_t)env_w * env_h, &s->dev.env))) break;
-        std::vector<float> cdf;
-        const float* cdf_host = env_cdf_or_null;
-        if (!cdf_host)
-        {
-            // Utils::compute_env_map_cdf (utils.cpp:126-142) with Image::luminance_of_pixel's double constants (image.h:84)
-            cdf.resize((size_t)env_w * env_h);
-            float run = 0.0f;
-            for (size_t i = 0; i < cdf.size(); i++)
-            {
-                const float* p = env_rgba + 4 * i;
-                float lum = (float)(0.3086 * p[0] + 0.6094 * p[1] + 0.0820 * p[2]);
-                run = run + lum;
-                cdf[i] = run;
-            }
-            cdf_host = cdf.data();
-        }
-        s->env_lum.resize((size_t)env_w * env_h);
-        for (size_t i = 0; i < s->env_lum.size(); i++)
-        {
-            const float* p = env_rgba + 4 * i;
-            s->env_lum[i] = (float)(0.3086 * p[0] + 0.6094 * p[1] + 0.0820 * p[2]);
-        }
-        if ((rc = upload(s, cdf_host, (size_t)env_w * env_h, &s->dev.cdf))) break;
-        std::vector<float> row_cdf((size_t)env_h);
-        for (int y = 0; y < env_h; y++) row_cdf[y] = cdf_host[(size_t)y * env_w + env_w - 1];
-        if ((rc = upload(s, row_cdf.data(), (size_t)env_h, &s->dev.row_cdf))) break;
-        s->dev.cdf_total = cdf_host[(size_t)env_w * env_h - 1];
-        s->dev.n_tri = n_tri; s->dev.n_emissive = n_emissive; s->dev.n_spheres = n_spheres;
-        s->dev.env_w = env_w; s->dev.env_h = env_h;
-        s->dev.has_diag = f.info.has_diag_slabs;
-    } while (0);
-    delete own;
-    if (rc) { b200rt_scene_destroy(s); return rc; }
-    rc = b200rt_scene_set_materials(s, materials10, n_materials);
-    if (rc) { b200rt_scene_destroy(s); return rc; }
-    *out = s;
-    return B200RT_OK;
+    const SceneArgs a = { tri_xyz9, n_tri, tri_material, n_material_indices, materials10, n_materials, emissive_tri, n_emissive,
+                          spheres20, n_spheres, env_rgba, env_w, env_h, env_cdf_or_null, 4 };
+    return create_scene(a, bvh_or_null, &device, 1, out);
 }
+
+int b200rt_scene_create_multi(const float* tri_xyz9, int n_tri, const int* tri_material, int n_material_indices,
+                              const float* materials10, int n_materials, const int* emissive_tri, int n_emissive,
+                              const void* spheres20, int n_spheres,
+                              const float* env_pixels, int env_channels, int env_w, int env_h, const float* env_cdf_or_null,
+                              const b200rt_bvh* bvh_or_null, const int* devices_or_null, int n_devices, b200rt_scene** out)
+{
+    const SceneArgs a = { tri_xyz9, n_tri, tri_material, n_material_indices, materials10, n_materials, emissive_tri, n_emissive,
+                          spheres20, n_spheres, env_pixels, env_w, env_h, env_cdf_or_null, env_channels };
+    return create_scene(a, bvh_or_null, devices_or_null, n_devices, out);
+}
+
+int b200rt_scene_device_count(const b200rt_scene* s) { return s ? 1 + (int)s->replicas.size() : 0; }
 
 // Vose's alias method in double over per-texel luminances: texel i is accepted with probability prob[i], otherwise alias[i] is taken
 static int build_alias_table(const float* lum, size_t n, std::vector<float>& prob, std::vector<int>& alias_out, double* total_out)
@@ -552,31 +787,57 @@ int b200rt_env_alias_table(const float* env_rgba, int env_w, int env_h, float* p
 int b200rt_scene_build_env_alias(b200rt_scene* s)
 {
     if (!s) return fail(B200RT_ERR_ARG, "NULL scene");
+    for (b200rt_scene* r : s->replicas) { const int rc = b200rt_scene_build_env_alias(r); if (rc) return rc; }
     if (s->d_alias) return B200RT_OK;
-    CU(cudaSetDevice(s->device));
-    const size_t n = s->env_lum.size();
-    if (!n) return fail(B200RT_ERR_ARG, "scene has no environment map");
-    std::vector<float> prob; std::vector<int> alias; double total = 0.0;
-    int rc = build_alias_table(s->env_lum.data(), n, prob, alias, &total);
-    if (rc) return rc;
-    std::vector<float2> table(n);
-    for (size_t i = 0; i < n; i++)
+    ON_DEVICE(s->device);
+    const size_t n = (size_t)s->dev.env_w * s->dev.env_h;
+    if (!n || !s->d_env_lum) return fail(B200RT_ERR_ARG, "scene has no environment map");
+    float2* d = nullptr;
+    CU(cudaMalloc(&d, n * sizeof(float2)));
+    double total = 0.0;
+    const cudaError_t ce = build_env_alias_device(s->d_env_lum, n, d, &total, 0);
+    if (ce != cudaSuccess)
     {
-        table[i].x = prob[i];
-        std::memcpy(&table[i].y, &alias[i], sizeof(int));
+        cudaFree(d);
+        if (ce == cudaErrorInvalidValue) { cudaGetLastError(); return fail(B200RT_ERR_ARG, "environment map has no luminance to sample"); }
+        return fail(B200RT_ERR_CUDA, "alias table build failed: %s", cudaGetErrorString(ce));
     }
-    CU(cudaMalloc(&s->d_alias, n * sizeof(float2)));
+    // published together, only after the build succeeded
+    s->d_alias = d;
     s->bytes += n * sizeof(float2);
-    CU(cudaMemcpy(s->d_alias, table.data(), n * sizeof(float2), cudaMemcpyHostToDevice));
     s->alias_total = (float)total;
-    s->dev.env_alias = s->d_alias;
+    s->dev.env_alias = d;
+    return B200RT_OK;
+}
+
+int b200rt_scene_get_env_alias(b200rt_scene* s, float* prob_out, int* alias_out, double* total_out)
+{
+    if (!s || !prob_out || !alias_out) return fail(B200RT_ERR_ARG, "NULL argument");
+    if (!s->d_alias) return fail(B200RT_ERR_ARG, "no alias table: call b200rt_scene_build_env_alias() first");
+    ON_DEVICE(s->device);
+    const size_t n = (size_t)s->dev.env_w * s->dev.env_h;
+    std::vector<float2> t(n);
+    CU(cudaMemcpy(t.data(), s->d_alias, n * sizeof(float2), cudaMemcpyDeviceToHost));
+    for (size_t i = 0; i < n; i++) { prob_out[i] = t[i].x; std::memcpy(&alias_out[i], &t[i].y, sizeof(int)); }
+    if (total_out) *total_out = (double)s->alias_total;
+    return B200RT_OK;
+}
+
+int b200rt_scene_get_env_cdf(b200rt_scene* s, float* cdf_out)
+{
+    if (!s || !cdf_out) return fail(B200RT_ERR_ARG, "NULL argument");
+    ON_DEVICE(s->device);
+    CU(cudaMemcpy(cdf_out, s->dev.cdf, (size_t)s->dev.env_w * s->dev.env_h * sizeof(float), cudaMemcpyDeviceToHost));
     return B200RT_OK;
 }
 
 int b200rt_scene_set_materials(b200rt_scene* s, const float* materials10, int n_materials)
 {
     if (!s || !materials10 || n_materials <= 0) return fail(B200RT_ERR_ARG, "bad materials");
-    CU(cudaSetDevice(s->device));
+    if (n_materials <= s->max_mat_index)
+        return fail(B200RT_ERR_ARG, "%d materials, but the scene's primitives reference material index %d", n_materials, s->max_mat_index);
+    for (b200rt_scene* r : s->replicas) { const int rc = b200rt_scene_set_materials(r, materials10, n_materials); if (rc) return rc; }
+    ON_DEVICE(s->device);
     std::vector<MaterialDev> mats;
     int any = 0;
     convert_materials(materials10, n_materials, s->mat_used, mats, &any);
@@ -596,7 +857,13 @@ int b200rt_scene_set_materials(b200rt_scene* s, const float* materials10, int n_
 void b200rt_scene_destroy(b200rt_scene* s)
 {
     if (!s) return;
-    cudaSetDevice(s->device);
+    for (b200rt_scene* r : s->replicas) b200rt_scene_destroy(r);
+    s->replicas.clear();
+    DeviceScope scope(s->device);
+    if (s->d_gather) cudaFree(s->d_gather);
+    if (s->d_rgba8) cudaFree(s->d_rgba8);
+    if (s->mg_stream) cudaStreamDestroy(s->mg_stream);
+    for (int i = 0; i < 2; i++) { if (s->h_stage[i]) cudaFreeHost(s->h_stage[i]); if (s->stage_ev[i]) cudaEventDestroy(s->stage_ev[i]); }
     for (void* p : s->allocs) cudaFree(p);
     if (s->d_mats) cudaFree(s->d_mats);
     if (s->d_alias) cudaFree(s->d_alias);
@@ -630,7 +897,13 @@ int b200rt_scene_get_bvh_info(const b200rt_scene* s, b200rt_bvh_info* out)
     return B200RT_OK;
 }
 
-size_t b200rt_scene_device_bytes(const b200rt_scene* s) { return s ? s->bytes : 0; }
+size_t b200rt_scene_device_bytes(const b200rt_scene* s)
+{
+    if (!s) return 0;
+    size_t b = s->bytes;
+    for (const b200rt_scene* r : s->replicas) b += r->bytes;
+    return b;
+}
 
 int b200rt_tiles_for_rank(int width, int height, int rank, int world)
 {
@@ -648,7 +921,7 @@ int b200rt_render_tiles_device(b200rt_scene* s, const float* camera17, int w, in
     if (!dev_tiles) return fail(B200RT_ERR_ARG, "dev_tiles must not be NULL");
     if (opts && opts->integrator != B200RT_INTEGRATOR_MEGAKERNEL && opts->integrator != B200RT_INTEGRATOR_WAVEFRONT)
         return fail(B200RT_ERR_ARG, "unknown integrator %d", opts->integrator);
-    CU(cudaSetDevice(s->device));
+    ON_DEVICE(s->device);
     if ((rc = ensure_scratch(s, 0, 0, 0))) return rc;
     cudaStream_t st = (cudaStream_t)cuda_stream;
     const int integrator = opts ? opts->integrator : B200RT_INTEGRATOR_WAVEFRONT;
@@ -684,58 +957,276 @@ int b200rt_untile_device(b200rt_scene* s, const void* dev_gathered, int tiles_pe
 {
     if (!s || !dev_gathered || !dev_image || world <= 0 || w <= 0 || h <= 0) return fail(B200RT_ERR_ARG, "bad untile arguments");
     if (tiles_per_rank_padded < b200rt_tiles_for_rank(w, h, 0, world)) return fail(B200RT_ERR_ARG, "tiles_per_rank_padded too small");
-    CU(cudaSetDevice(s->device));
+    ON_DEVICE(s->device);
     CU(launch_untile((const float4*)dev_gathered, tiles_per_rank_padded, world, -1, w, h, (float4*)dev_image, (cudaStream_t)cuda_stream));
     return B200RT_OK;
 }
 
-int b200rt_render(b200rt_scene* s, const float* camera17, int w, int h, int spp, int bounces, float* fb,
-                  const b200rt_render_options* opts, b200rt_stats* stats)
+} // extern "C"
+
+namespace {
+
+unsigned long long pixels_of_rank(const RenderParams& P, int w, int h)
+{
+    unsigned long long px = 0;
+    for (int k = 0; k < P.n_rank_tiles; k++)
+    {
+        const int tile = P.rank + k * P.world, tx = tile % P.tiles_x, ty = tile / P.tiles_x;
+        px += (unsigned long long)std::min(kTileDim, w - tx * kTileDim) * std::min(kTileDim, h - ty * kTileDim);
+    }
+    return px;
+}
+
+// One rank of a multi-GPU frame, run by its own host thread: render this device's interleaved tiles as mean radiance
+// (B200RT_FLAG_LINEAR_TILES) and push them into rank 0's gather buffer with ONE device-to-device copy (NVLink peer copy).
+struct RankResult { int rc = B200RT_OK; std::string error; unsigned long long rays = 0; float ms = 0.0f; int launches = 0; };
+
+void render_rank(b200rt_scene* r, b200rt_scene* root, RenderParams P, int integrator, size_t tiles_padded, RankResult* out)
+{
+    auto body = [&]() -> int {
+        ON_DEVICE(r->device);
+        int rc = ensure_scratch(r, r == root ? 0 : tiles_padded * kTilePixels, 0, 0);
+        if (rc) return rc;
+        if (!r->mg_stream) CU(cudaStreamCreateWithFlags(&r->mg_stream, cudaStreamNonBlocking));
+        cudaStream_t st = r->mg_stream;
+        float4* dst = root->d_gather + (size_t)P.rank * tiles_padded * kTilePixels;
+        float4* tiles = r == root ? dst : r->d_tiles;          // rank 0 renders straight into its slice of the gather buffer
+        CU(cudaMemsetAsync(r->d_rays, 0, sizeof(unsigned long long), st));
+        CU(cudaEventRecord(r->ev0, st));
+        if ((rc = run_integrator(r, P, integrator, nullptr, tiles, st, &out->launches))) return rc;
+        CU(cudaEventRecord(r->ev1, st));
+        if (r != root)
+            CU(cudaMemcpyPeerAsync(dst, root->device, tiles, r->device, (size_t)P.n_rank_tiles * kTilePixels * sizeof(float4), st));
+        CU(cudaStreamSynchronize(st));
+        CU(cudaEventElapsedTime(&out->ms, r->ev0, r->ev1));
+        CU(cudaMemcpy(&out->rays, r->d_rays, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        return B200RT_OK;
+    };
+    out->rc = body();
+    if (out->rc) out->error = g_error;
+}
+
+// The whole frame: framebuffer in (or Color::Black()), integrator on one or several devices, un-tile, optional RGBA8 output
+// stage, result out. fb_out / rgba8_out: exactly one is non-NULL.
+int render_frame(b200rt_scene* s, const float* camera17, int w, int h, int spp, int bounces, const float* fb_in, float* fb_out,
+                 unsigned char* rgba8_out, int flip_y, const b200rt_render_options* opts, b200rt_stats* stats)
 {
     RenderParams P;
     int rc = make_params(s, camera17, w, h, spp, bounces, opts, P);
     if (rc) return rc;
-    if (!fb) return fail(B200RT_ERR_ARG, "framebuffer must not be NULL");
-    auto t0 = std::chrono::high_resolution_clock::now();
-    CU(cudaSetDevice(s->device));
-    const size_t image_px = (size_t)w * h;
-    if ((rc = ensure_scratch(s, (size_t)std::max(P.n_rank_tiles, 1) * kTilePixels, image_px, 0))) return rc;
-    cudaStream_t st = 0;
-    const bool upload_fb = !(P.flags & B200RT_FLAG_FB_IS_ZERO) || P.world > 1;
-    unsigned long long h2d = 17 * sizeof(float), d2h = 0;
-    if (upload_fb) { CU(cudaMemcpyAsync(s->d_image, fb, image_px * sizeof(float4), cudaMemcpyHostToDevice, st)); h2d += image_px * sizeof(float4); }
-    CU(cudaMemsetAsync(s->d_rays, 0, sizeof(unsigned long long), st));
-    CU(cudaEventRecord(s->ev0, st));
-    const float4* fb_in = (P.flags & B200RT_FLAG_FB_IS_ZERO) ? nullptr : s->d_image;
     const int integrator = opts ? opts->integrator : B200RT_INTEGRATOR_WAVEFRONT;
     if (integrator != B200RT_INTEGRATOR_MEGAKERNEL && integrator != B200RT_INTEGRATOR_WAVEFRONT) return fail(B200RT_ERR_ARG, "unknown integrator %d", integrator);
+    if (P.flags & B200RT_FLAG_LINEAR_TILES) return fail(B200RT_ERR_ARG, "B200RT_FLAG_LINEAR_TILES is for b200rt_render_tiles_device");
+    const int n_dev = 1 + (int)s->replicas.size();
+    if (n_dev > 1 && P.world != 1) return fail(B200RT_ERR_ARG, "a multi-GPU scene partitions the frame itself: rank/world must stay 0/1");
+    auto t0 = std::chrono::high_resolution_clock::now();
+    ON_DEVICE(s->device);
+    const size_t image_px = (size_t)w * h;
+    if ((rc = ensure_scratch(s, (size_t)std::max(P.n_rank_tiles, 1) * kTilePixels, image_px, 0))) return rc;
+    if (rgba8_out && image_px * 4 > s->rgba8_cap)
+    {
+        if (s->d_rgba8) cudaFree(s->d_rgba8);
+        s->d_rgba8 = nullptr; s->rgba8_cap = 0;
+        CU(cudaMalloc(&s->d_rgba8, image_px * 4));
+        s->rgba8_cap = image_px * 4;
+    }
+    cudaStream_t st = 0;
+    unsigned long long h2d = 17 * sizeof(float), d2h = 0, rays = 0;
     int launches = 0;
-    if ((rc = run_integrator(s, P, integrator, fb_in, s->d_tiles, st, &launches))) return rc;
-    CU(launch_untile(s->d_tiles, P.n_rank_tiles, P.world, P.world > 1 ? P.rank : -1, w, h, s->d_image, st));
+    float kernel_ms = 0.0f;
+    const bool fb_zero = !fb_in || (P.flags & B200RT_FLAG_FB_IS_ZERO);
+
+    if (n_dev == 1)
+    {
+        // single device: the integrator tone-maps each finished pixel against the incoming framebuffer itself
+        const bool upload_fb = !fb_zero || (P.world > 1 && fb_in);
+        if (upload_fb) { if ((rc = copy_to_device(s, s->d_image, fb_in, image_px * sizeof(float4), st))) return rc; h2d += image_px * sizeof(float4); }
+        else if (P.world > 1) CU(launch_fill_f4(s->d_image, image_px, make_float4(0.0f, 0.0f, 0.0f, 1.0f), st));
+        CU(cudaMemsetAsync(s->d_rays, 0, sizeof(unsigned long long), st));
+        CU(cudaEventRecord(s->ev0, st));
+        if ((rc = run_integrator(s, P, integrator, fb_zero ? nullptr : s->d_image, s->d_tiles, st, &launches))) return rc;
+        CU(launch_untile(s->d_tiles, P.n_rank_tiles, P.world, P.world > 1 ? P.rank : -1, w, h, s->d_image, st));
+        launches += 1;
+        CU(cudaEventRecord(s->ev1, st));
+    }
+    else
+    {
+        // N devices, one host thread each: interleaved tiles, scene replicated, mean radiance gathered on rank 0's device, where
+        // `framebuffer += final; tone map` (render_kernel.cpp:169-180) happens against the incoming framebuffer
+        const size_t tiles_padded = (size_t)b200rt_tiles_for_rank(w, h, 0, n_dev);
+        const size_t need = tiles_padded * kTilePixels * (size_t)n_dev;
+        if (need > s->gather_cap)
+        {
+            if (s->d_gather) cudaFree(s->d_gather);
+            s->d_gather = nullptr; s->gather_cap = 0;
+            CU(cudaMalloc(&s->d_gather, need * sizeof(float4)));
+            s->gather_cap = need;
+        }
+        if (!fb_zero) { if ((rc = copy_to_device(s, s->d_image, fb_in, image_px * sizeof(float4), st))) return rc; h2d += image_px * sizeof(float4); }
+        else CU(launch_fill_f4(s->d_image, image_px, make_float4(0.0f, 0.0f, 0.0f, 1.0f), st));
+        CU(cudaStreamSynchronize(st));
+        std::vector<RankResult> res((size_t)n_dev);
+        std::vector<std::thread> threads;
+        for (int d = 0; d < n_dev; d++)
+        {
+            RenderParams Pd = P;
+            Pd.rank = d; Pd.world = n_dev;
+            Pd.n_rank_tiles = b200rt_tiles_for_rank(w, h, d, n_dev);
+            Pd.flags |= B200RT_FLAG_LINEAR_TILES;
+            b200rt_scene* r = d == 0 ? s : s->replicas[(size_t)d - 1];
+            if (d == 0) continue;
+            threads.emplace_back(render_rank, r, s, Pd, integrator, tiles_padded, &res[(size_t)d]);
+        }
+        {
+            RenderParams P0 = P;
+            P0.rank = 0; P0.world = n_dev;
+            P0.n_rank_tiles = b200rt_tiles_for_rank(w, h, 0, n_dev);
+            P0.flags |= B200RT_FLAG_LINEAR_TILES;
+            render_rank(s, s, P0, integrator, tiles_padded, &res[0]);
+        }
+        for (std::thread& t : threads) t.join();
+        for (int d = 0; d < n_dev; d++)
+        {
+            if (res[(size_t)d].rc) { g_error = "device rank " + std::to_string(d) + ": " + res[(size_t)d].error; return res[(size_t)d].rc; }
+            rays += res[(size_t)d].rays;
+            launches += res[(size_t)d].launches;
+            kernel_ms = std::max(kernel_ms, res[(size_t)d].ms);
+        }
+        CU(launch_untile_accumulate(s->d_gather, (int)tiles_padded, n_dev, w, h, s->d_image, st));
+        launches += 1;
+    }
+
+    // output stage
+    if (rgba8_out)
+    {
+        CU(launch_quantise_rgba8(s->d_image, w, h, flip_y, s->d_rgba8, st));
+        launches += 1;
+        if ((rc = copy_to_host(s, rgba8_out, s->d_rgba8, image_px * 4, st))) return rc;
+        d2h += image_px * 4;
+    }
+    else
+    {
+        if ((rc = copy_to_host(s, fb_out, s->d_image, image_px * sizeof(float4), st))) return rc;
+        d2h += image_px * sizeof(float4);
+    }
+    if (stats)
+    {
+        std::memset(stats, 0, sizeof(*stats));
+        if (n_dev == 1)
+        {
+            CU(cudaEventElapsedTime(&kernel_ms, s->ev0, s->ev1));
+            CU(cudaMemcpy(&rays, s->d_rays, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+            stats->samples = pixels_of_rank(P, w, h) * (unsigned long long)spp;
+        }
+        else stats->samples = (unsigned long long)image_px * (unsigned long long)spp;
+        stats->rays = rays;
+        stats->kernel_ms = kernel_ms;
+        stats->trace_ms = s->kernel_times[0]; stats->shade_ms = s->kernel_times[1];
+        stats->trace_launches = (int)s->kernel_times[2]; stats->shade_launches = (int)s->kernel_times[3];
+        stats->gpu_launches = launches;
+        stats->h2d_bytes = h2d; stats->d2h_bytes = d2h;
+        stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
+    }
+    return B200RT_OK;
+}
+
+} // namespace
+
+extern "C" {
+
+int b200rt_render(b200rt_scene* s, const float* camera17, int w, int h, int spp, int bounces, float* fb,
+                  const b200rt_render_options* opts, b200rt_stats* stats)
+{
+    if (!fb) return fail(B200RT_ERR_ARG, "framebuffer must not be NULL");
+    return render_frame(s, camera17, w, h, spp, bounces, fb, fb, nullptr, 0, opts, stats);
+}
+
+int b200rt_render_rgba8(b200rt_scene* s, const float* camera17, int w, int h, int spp, int bounces, const float* fb_in_or_null,
+                        int flip_y, unsigned char* out_rgba8, const b200rt_render_options* opts, b200rt_stats* stats)
+{
+    if (!out_rgba8) return fail(B200RT_ERR_ARG, "out_rgba8 must not be NULL");
+    if (opts && opts->world > 1) return fail(B200RT_ERR_ARG, "b200rt_render_rgba8 renders whole frames (rank/world must stay 0/1)");
+    return render_frame(s, camera17, w, h, spp, bounces, fb_in_or_null, nullptr, out_rgba8, flip_y, opts, stats);
+}
+
+int b200rt_render_region(b200rt_scene* s, const float* camera17, int w, int h, int spp, int bounces, int x0, int y0, int x1, int y1,
+                         float* out_rgba, const b200rt_render_options* opts, b200rt_stats* stats)
+{
+    RenderParams P;
+    int rc = make_params(s, camera17, w, h, spp, bounces, opts, P);
+    if (rc) return rc;
+    if (!out_rgba) return fail(B200RT_ERR_ARG, "out_rgba must not be NULL");
+    if (x0 < 0 || y0 < 0 || x1 > w || y1 > h || x0 >= x1 || y0 >= y1) return fail(B200RT_ERR_ARG, "bad region [%d,%d) x [%d,%d) of %dx%d", x0, x1, y0, y1, w, h);
+    if ((long long)(x1 - x0) * (y1 - y0) > (1ll << 30)) return fail(B200RT_ERR_ARG, "region too large");
+    ON_DEVICE(s->device);
+    const size_t px = (size_t)(x1 - x0) * (y1 - y0);
+    if ((rc = ensure_scratch(s, px, 0, 0))) return rc;
+    P.rank = 0; P.world = 1;
+    P.flags &= ~B200RT_FLAG_LINEAR_TILES;
+    P.rx0 = x0; P.ry0 = y0; P.rw = x1 - x0; P.rh = y1 - y0;
+    cudaStream_t st = 0;
+    SceneDev dev = s->dev;
+    if (P.flags & B200RT_FLAG_ENV_ALIAS)
+    {
+        if (!s->d_alias) return fail(B200RT_ERR_ARG, "B200RT_FLAG_ENV_ALIAS needs b200rt_scene_build_env_alias() first");
+        dev.use_alias = 1; dev.cdf_total = s->alias_total;
+    }
+    CU(cudaMemsetAsync(s->d_rays, 0, sizeof(unsigned long long), st));
+    CU(cudaEventRecord(s->ev0, st));
+    // one lane per pixel through the megakernel's state machine (both integrators produce identical pixels)
+    CU(launch_megakernel(dev, P, nullptr, s->d_tiles, s->d_work, s->d_rays, st));
     CU(cudaEventRecord(s->ev1, st));
-    CU(cudaMemcpyAsync(fb, s->d_image, image_px * sizeof(float4), cudaMemcpyDeviceToHost, st));
-    d2h += image_px * sizeof(float4);
-    CU(cudaStreamSynchronize(st));
+    if ((rc = copy_to_host(s, out_rgba, s->d_tiles, px * sizeof(float4), st))) return rc;
     if (stats)
     {
         std::memset(stats, 0, sizeof(*stats));
         float ms = 0.0f;
         CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
         CU(cudaMemcpy(&stats->rays, s->d_rays, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
-        unsigned long long px = 0;
-        for (int k = 0; k < P.n_rank_tiles; k++)
-        {
-            int tile = P.rank + k * P.world, tx = tile % P.tiles_x, ty = tile / P.tiles_x;
-            px += (unsigned long long)std::min(kTileDim, w - tx * kTileDim) * std::min(kTileDim, h - ty * kTileDim);
-        }
-        stats->samples = px * (unsigned long long)spp;
-        stats->kernel_ms = ms;
-        stats->trace_ms = s->kernel_times[0]; stats->shade_ms = s->kernel_times[1];
-        stats->trace_launches = (int)s->kernel_times[2]; stats->shade_launches = (int)s->kernel_times[3];
-        stats->gpu_launches = launches + 1;
-        stats->h2d_bytes = h2d; stats->d2h_bytes = d2h;
-        stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
+        stats->samples = (unsigned long long)px * (unsigned long long)spp;
+        stats->kernel_ms = ms; stats->total_ms = ms; stats->gpu_launches = 1;
+        stats->h2d_bytes = 17 * sizeof(float); stats->d2h_bytes = px * sizeof(float4);
     }
+    return B200RT_OK;
+}
+
+int b200rt_rng_stream(int x, int y, int spp, int n, uint32_t* state_out, float* floats_out)
+{
+    if (n < 0 || !state_out || (n > 0 && !floats_out)) return fail(B200RT_ERR_ARG, "bad rng_stream arguments");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) return fail(B200RT_ERR_CUDA, "no CUDA device: b200rt has no CPU fallback");
+    uint32_t* d_state = nullptr; float* d_f = nullptr;
+    cudaError_t e = cudaSuccess;
+    do
+    {
+        if ((e = cudaMalloc(&d_state, sizeof(uint32_t))) != cudaSuccess) break;
+        if ((e = cudaMalloc(&d_f, sizeof(float) * (size_t)std::max(n, 1))) != cudaSuccess) break;
+        if ((e = launch_rng_stream(x, y, spp, n, d_state, d_f, 0)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(state_out, d_state, sizeof(uint32_t), cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+        if (n && (e = cudaMemcpy(floats_out, d_f, sizeof(float) * (size_t)n, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+    } while (0);
+    cudaFree(d_state); cudaFree(d_f);
+    if (e != cudaSuccess) return fail(B200RT_ERR_CUDA, "rng_stream: %s", cudaGetErrorString(e));
+    return B200RT_OK;
+}
+
+int b200rt_host_alloc(size_t bytes, void** out)
+{
+    if (!out) return fail(B200RT_ERR_ARG, "out must not be NULL");
+    *out = nullptr;
+    CU(cudaMallocHost(out, std::max<size_t>(bytes, 1)));
+    return B200RT_OK;
+}
+
+void b200rt_host_free(void* p) { if (p) cudaFreeHost(p); }
+
+int b200rt_untile_accumulate_device(b200rt_scene* s, const void* dev_gathered, int tiles_per_rank_padded, int world, int w, int h,
+                                    void* dev_fb_inout, void* cuda_stream)
+{
+    if (!s || !dev_gathered || !dev_fb_inout || world <= 0 || w <= 0 || h <= 0) return fail(B200RT_ERR_ARG, "bad untile arguments");
+    if (tiles_per_rank_padded < b200rt_tiles_for_rank(w, h, 0, world)) return fail(B200RT_ERR_ARG, "tiles_per_rank_padded too small");
+    ON_DEVICE(s->device);
+    CU(launch_untile_accumulate((const float4*)dev_gathered, tiles_per_rank_padded, world, w, h, (float4*)dev_fb_inout, (cudaStream_t)cuda_stream));
     return B200RT_OK;
 }
 
@@ -775,7 +1266,7 @@ int b200rt_trace_primary_device(b200rt_scene* s, const float* camera17, int w, i
     if (rc) return rc;
     if (!dev_prim || !dev_t) return fail(B200RT_ERR_ARG, "output buffers must not be NULL");
     if (sample > 0) return fail(B200RT_ERR_ARG, "only sample 0 (or < 0 = un-jittered) has a path-independent camera ray");
-    CU(cudaSetDevice(s->device));
+    ON_DEVICE(s->device);
     if ((rc = ensure_scratch(s, 0, 0, 0))) return rc;
     cudaStream_t st = (cudaStream_t)cuda_stream;
     if (stats) CU(cudaEventRecord(s->ev0, st));
@@ -806,19 +1297,20 @@ int b200rt_trace_primary(b200rt_scene* s, const float* camera17, int w, int h, i
     if (!prim_out || !t_out) return fail(B200RT_ERR_ARG, "output buffers must not be NULL");
     if (w <= 0 || h <= 0) return fail(B200RT_ERR_ARG, "bad frame size");
     auto t0 = std::chrono::high_resolution_clock::now();
-    CU(cudaSetDevice(s->device));
+    ON_DEVICE(s->device);
     const size_t px = (size_t)w * h;
     int rc = ensure_scratch(s, 0, 0, px);
     if (rc) return rc;
-    CU(cudaMemset(s->d_prim, 0xff, px * sizeof(int)));                 // -1: pixels of other ranks read as "miss"
+    if (opts && opts->world > 1)
     {
-        std::vector<float> neg(px, -1.0f);
-        CU(cudaMemcpy(s->d_t, neg.data(), px * sizeof(float), cudaMemcpyHostToDevice));
+        // pixels of other ranks read as "miss"; a whole-frame call writes every pixel itself
+        CU(cudaMemsetAsync(s->d_prim, 0xff, px * sizeof(int), 0));
+        CU(launch_fill_f32(s->d_t, px, -1.0f, 0));
     }
     rc = b200rt_trace_primary_device(s, camera17, w, h, sample, spp_for_seed, s->d_prim, s->d_t, opts, nullptr, stats);
     if (rc) return rc;
-    CU(cudaMemcpy(prim_out, s->d_prim, px * sizeof(int), cudaMemcpyDeviceToHost));
-    CU(cudaMemcpy(t_out, s->d_t, px * sizeof(float), cudaMemcpyDeviceToHost));
+    if ((rc = copy_to_host(s, prim_out, s->d_prim, px * sizeof(int), 0))) return rc;
+    if ((rc = copy_to_host(s, t_out, s->d_t, px * sizeof(float), 0))) return rc;
     if (stats)
     {
         stats->d2h_bytes = px * 8; stats->h2d_bytes = 17 * sizeof(float);
@@ -832,7 +1324,7 @@ int b200rt_trace_rays_device(b200rt_scene* s, const void* dev_rays6, int n, int 
 {
     if (!s) return fail(B200RT_ERR_ARG, "NULL scene");
     if (n < 0 || (n > 0 && (!dev_rays6 || !dev_prim || !dev_t))) return fail(B200RT_ERR_ARG, "bad ray buffers");
-    CU(cudaSetDevice(s->device));
+    ON_DEVICE(s->device);
     int rc = ensure_scratch(s, 0, 0, 0);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)cuda_stream;
@@ -856,7 +1348,7 @@ int b200rt_trace_rays(b200rt_scene* s, const float* rays6, int n, int any_hit, i
     if (!s) return fail(B200RT_ERR_ARG, "NULL scene");
     if (n < 0 || (n > 0 && (!rays6 || !prim_out || !t_out))) return fail(B200RT_ERR_ARG, "bad ray buffers");
     if (n == 0) return B200RT_OK;
-    CU(cudaSetDevice(s->device));
+    ON_DEVICE(s->device);
     float* d_rays6 = nullptr; int* d_prim = nullptr; float* d_t = nullptr; float* d_extra = nullptr;
     int rc = B200RT_OK;
     cudaError_t e = cudaSuccess;

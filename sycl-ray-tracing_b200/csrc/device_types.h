@@ -63,6 +63,9 @@ struct RenderParams
     int tiles_x, tiles_y;
     int n_rank_tiles;          // tiles owned by this rank
     int flags;
+    // region mode (b200rt_render_region, megakernel only): slots are the pixels of the rectangle [rx0, rx0 + rw) x [ry0, ry0 + rh)
+    // of the frame in row-major order instead of this rank's tiles; rw == 0 = off
+    int rx0, ry0, rw, rh;
 };
 
 // wavefront integrator state: one slot per pixel of this rank's tile-major buffer (SoA, HBM resident)

@@ -1,5 +1,7 @@
 // sm_100a kernels of the path: primary closest-hit (K1), megakernel integrator (K2), ray batches, untile (K4).
 // Compiled with -fmad=false (see pt_device.cuh).
+#include <algorithm>
+
 #include "kernels.h"
 #include "pt_device.cuh"
 
@@ -52,6 +54,12 @@ __device__ __forceinline__ void start_sample(const RenderParams& P, LaneState& L
 // slot (tile-major index into this rank's tile buffer) -> pixel; consecutive slots are the lanes of one 8x4 patch
 __device__ __forceinline__ bool slot_pixel(const RenderParams& P, unsigned int slot, int& x, int& y)
 {
+    if (P.rw > 0)
+    {
+        x = P.rx0 + (int)(slot % (unsigned int)P.rw);
+        y = P.ry0 + (int)(slot / (unsigned int)P.rw);
+        return x < P.cam.w && y < P.cam.h;
+    }
     const PixelSlot ps = unit_pixel(P, (int)(slot >> 5), (int)(slot & 31u));
     x = ps.x; y = ps.y;
     return ps.inside;
@@ -64,7 +72,7 @@ __global__ void __launch_bounds__(256) k_pathtrace_mega(SceneDev S, RenderParams
 {
     const unsigned int FULL = 0xffffffffu;
     const int lane = threadIdx.x & 31;
-    const unsigned int n_slots = (unsigned int)P.n_rank_tiles * kTilePixels;
+    const unsigned int n_slots = P.rw > 0 ? (unsigned int)(P.rw * P.rh) : (unsigned int)P.n_rank_tiles * kTilePixels;
     const bool trace_light_brdf = S.any_emissive_material || !(P.flags & B200RT_FLAG_SKIP_DEAD_RAYS);
     const bool no_paths = P.spp <= 0 || P.max_bounces <= 0;
     unsigned long long rays = 0;
@@ -82,9 +90,8 @@ __global__ void __launch_bounds__(256) k_pathtrace_mega(SceneDev S, RenderParams
             if (!slot_pixel(P, slot, x, y)) { out_tiles[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); continue; }
             if (no_paths)
             {
-                const float4 fb = fb_in_rowmajor ? fb_in_rowmajor[(size_t)y * P.cam.w + x] : make_float4(0.0f, 0.0f, 0.0f, 1.0f);
                 const float n = (float)P.spp;
-                out_tiles[slot] = tonemap(fb, CO(0.0f / n, 0.0f / n, 0.0f / n));
+                out_tiles[slot] = pixel_output(P.flags, fb_in_rowmajor, (size_t)y * P.cam.w + x, CO(0.0f / n, 0.0f / n, 0.0f / n));
                 continue;
             }
             L.x = x; L.y = y; L.slot = slot;
@@ -175,8 +182,7 @@ __global__ void __launch_bounds__(256) k_pathtrace_mega(SceneDev S, RenderParams
             {
                 const float n = (float)P.spp;
                 const col mean = CO(L.final_color.r / n, L.final_color.g / n, L.final_color.b / n);   // operator/= divides (color.h:67-74)
-                const float4 fb = fb_in_rowmajor ? fb_in_rowmajor[(size_t)L.y * P.cam.w + L.x] : make_float4(0.0f, 0.0f, 0.0f, 1.0f);
-                out_tiles[L.slot] = tonemap(fb, mean);
+                out_tiles[L.slot] = pixel_output(P.flags, fb_in_rowmajor, (size_t)L.y * P.cam.w + L.x, mean);
                 have_pixel = false;
             }
         }
@@ -254,6 +260,54 @@ __global__ void __launch_bounds__(256) k_untile(const float4* __restrict__ tiles
     image[(size_t)y * w + x] = tiles[src];
 }
 
+// K4 for B200RT_FLAG_LINEAR_TILES buffers: image (the incoming framebuffer) += mean radiance, tone map in place (:169-180)
+__global__ void __launch_bounds__(256) k_untile_accumulate(const float4* __restrict__ tiles, int tiles_per_rank_padded, int world, int w, int h,
+                                                           int tiles_x, float4* __restrict__ image)
+{
+    const int x = blockIdx.x * 16 + (threadIdx.x & 15);
+    const int y = blockIdx.y * 16 + (threadIdx.x >> 4);
+    if (x >= w || y >= h) return;
+    const int tile_id = (y / kTileDim) * tiles_x + (x / kTileDim);
+    const int rank = tile_id % world, k = tile_id / world;
+    const int lx = x % kTileDim, ly = y % kTileDim;
+    const int sub = (ly / kPatchH) * 2 + (lx / kPatchW);
+    const int lane = (ly % kPatchH) * kPatchW + (lx % kPatchW);
+    const float4 m = tiles[((size_t)rank * tiles_per_rank_padded + k) * kTilePixels + sub * 32 + lane];
+    const size_t i = (size_t)y * w + x;
+    image[i] = tonemap(image[i], CO(m.x, m.y, m.z));
+}
+
+cudaError_t launch_untile_accumulate(const float4* tiles, int tiles_per_rank_padded, int world, int w, int h, float4* image, cudaStream_t stream)
+{
+    const int tiles_x = (w + kTileDim - 1) / kTileDim, tiles_y = (h + kTileDim - 1) / kTileDim;
+    dim3 grid(tiles_x, tiles_y);
+    k_untile_accumulate<<<grid, 256, 0, stream>>>(tiles, tiles_per_rank_padded, world, w, h, tiles_x, image);
+    return cudaGetLastError();
+}
+
+// fills a float array with one value (b200rt_trace_primary: "miss" for the pixels of other ranks)
+__global__ void k_fill_f32(float* p, size_t n, float v)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+cudaError_t launch_fill_f32(float* p, size_t n, float v, cudaStream_t stream)
+{
+    if (!n) return cudaSuccess;
+    k_fill_f32<<<(unsigned int)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, stream>>>(p, n, v);
+    return cudaGetLastError();
+}
+
+__global__ void k_fill_f4(float4* p, size_t n, float4 v)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) p[i] = v;
+}
+cudaError_t launch_fill_f4(float4* p, size_t n, float4 v, cudaStream_t stream)
+{
+    if (!n) return cudaSuccess;
+    k_fill_f4<<<(unsigned int)std::min<size_t>((n + 255) / 256, 148 * 8), 256, 0, stream>>>(p, n, v);
+    return cudaGetLastError();
+}
+
 // ---- output stage: the quantisation loop of write_image_png (source/image_io.cpp:165-182), 16 B in -> 4 B out per pixel -----
 // Color pixel = image(i) * 255; tmp = clamp(pixel, 0, 255) -> unsigned char (truncation); flipY puts image row 0 (bottom) last.
 __device__ __forceinline__ unsigned int quantise_channel(float v)
@@ -273,19 +327,37 @@ __global__ void __launch_bounds__(256) k_quantise_rgba8(const float4* __restrict
                                           (unsigned char)quantise_channel(p.z), (unsigned char)quantise_channel(p.w));
 }
 
-// ---- launchers ----------------------------------------------------------------------------------------------------------------
-static int g_sm_count = 0;
-static int sm_count()
+// ---- parity hook: the RNG stream of one pixel (xorshift.h:10-31 seeded and warmed up as render_kernel.cpp:77-82) -----------------
+__global__ void k_rng_stream(int x, int y, int spp, int n, uint32_t* state_out, float* floats_out)
 {
-    if (!g_sm_count)
-    {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (g_sm_count <= 0) g_sm_count = 148;
-    }
-    return g_sm_count;
+    if (blockIdx.x || threadIdx.x) return;
+    uint32_t s = pixel_rng(x, y, spp);
+    *state_out = s;
+    for (int i = 0; i < n; i++) floats_out[i] = xs_float(s);
 }
+
+cudaError_t launch_rng_stream(int x, int y, int spp, int n, uint32_t* state_out, float* floats_out, cudaStream_t stream)
+{
+    k_rng_stream<<<1, 32, 0, stream>>>(x, y, spp, n, state_out, floats_out);
+    return cudaGetLastError();
+}
+
+// ---- launchers ----------------------------------------------------------------------------------------------------------------
+// SM count of the calling thread's current device (cached per device: one process may drive several GPU models)
+int current_sm_count()
+{
+    static int cache[64] = {};
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+    if (!cache[dev])
+    {
+        int n = 0;
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+        cache[dev] = n > 0 ? n : 148;
+    }
+    return cache[dev];
+}
+static int sm_count() { return current_sm_count(); }
 
 cudaError_t launch_megakernel(const SceneDev& S, const RenderParams& P, const float4* fb_in_rowmajor, float4* out_tiles,
                               unsigned int* work_counter, unsigned long long* ray_counter, cudaStream_t stream)
@@ -299,7 +371,7 @@ cudaError_t launch_megakernel(const SceneDev& S, const RenderParams& P, const fl
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_pathtrace_mega<TL_AXIS>, 256, 0);
     if (per_sm <= 0) per_sm = 1;
     int grid = sm_count() * per_sm;                        // persistent: a whole number of resident CTAs per SM
-    const int needed = P.n_rank_tiles;                     // one CTA's worth of lanes per 16x16 tile at most
+    const int needed = P.rw > 0 ? (P.rw * P.rh + 255) / 256 : P.n_rank_tiles;      // one CTA's worth of lanes per 16x16 tile at most
     if (grid > needed) grid = needed;
     if (grid <= 0) return cudaSuccess;
     if (tl == TL_WIDE) k_pathtrace_mega<TL_WIDE><<<grid, 256, 0, stream>>>(S, P, fb_in_rowmajor, out_tiles, work_counter, ray_counter);

@@ -18,6 +18,9 @@ inline int traversal_layout(const SceneDev& S, int flags, bool coherent = false)
     return (S.has_diag && (flags & B200RT_FLAG_DIAG_SLABS)) ? 1 : 0;                      // TL_DIAG : TL_AXIS
 }
 
+// SM count of the current device (cached per device id)
+int current_sm_count();
+
 cudaError_t launch_megakernel(const SceneDev& S, const RenderParams& P, const float4* fb_in_rowmajor, float4* out_tiles,
                               unsigned int* work_counter, unsigned long long* ray_counter, cudaStream_t stream);
 cudaError_t launch_primary(const SceneDev& S, const RenderParams& P, int sample, int* prim_out, float* t_out, cudaStream_t stream);
@@ -26,12 +29,24 @@ cudaError_t launch_trace_rays(const SceneDev& S, const float* rays6, int n, int 
 cudaError_t launch_untile(const float4* tiles, int tiles_per_rank_padded, int world, int only_rank, int w, int h, float4* image,
                           cudaStream_t stream);
 
+cudaError_t launch_untile_accumulate(const float4* tiles, int tiles_per_rank_padded, int world, int w, int h, float4* image, cudaStream_t stream);
+cudaError_t launch_fill_f4(float4* p, size_t n, float4 v, cudaStream_t stream);
+cudaError_t launch_fill_f32(float* p, size_t n, float v, cudaStream_t stream);
+cudaError_t launch_rng_stream(int x, int y, int spp, int n, uint32_t* state_out, float* floats_out, cudaStream_t stream);
 cudaError_t launch_quantise_rgba8(const float4* image, int w, int h, int flip_y, void* out_rgba8, cudaStream_t stream);
+
+// K5 env tables (env_tables.cu)
+cudaError_t launch_env_expand_rgb(const float* rgb, size_t n, float4* rgba, cudaStream_t stream);
+cudaError_t launch_env_luminance(const float4* env, size_t n, float* lum, cudaStream_t stream);
+cudaError_t launch_env_cdf_serial(const float* lum, size_t n, float* cdf, cudaStream_t stream);
+cudaError_t launch_env_row_cdf(const float* cdf, int w, int h, float* row, cudaStream_t stream);
+cudaError_t build_env_alias_device(const float* lum, size_t n, float2* table, double* total_host, cudaStream_t stream);
 
 // wavefront integrator (wavefront.cu): runs the whole frame for this rank's tiles as n_groups independent interleaved
 // tile groups, each on its own stream; `stream` is forked from and joined back into
 cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGroup* groups, int n_groups, const float4* fb_in_rowmajor,
-                          float4* out_tiles, cudaStream_t stream, cudaEvent_t fork_event, int* launches_out, double* kernel_times4 = nullptr);
+                          float4* out_tiles, cudaStream_t stream, cudaEvent_t fork_event, int* launches_out, double* kernel_times4 = nullptr,
+                          unsigned int* unfinished_out = nullptr);
 cudaError_t wavefront_sum_rays(const WfGroup* groups, int n_groups, unsigned long long* total, cudaStream_t stream);
 
 } // namespace b200rt

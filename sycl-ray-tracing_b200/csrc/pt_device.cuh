@@ -8,6 +8,7 @@
 #include <cstdint>
 #include <cuda_runtime.h>
 
+#include "../../include/b200rt.h"
 #include "device_types.h"
 
 namespace b200rt {
@@ -911,6 +912,16 @@ __device__ __forceinline__ float4 tonemap(float4 fb_in, col mean)
     o.z = powf(1.0f + -expf(-b * exposure), 1.0f / gamma);
     o.w = 1.0f + -(-fb_in.w * exposure);      // Color::operator* scales alpha, exp()/pow() pass it through (color.h:149-183)
     return o;
+}
+
+
+// what a finished pixel writes into the tile buffer: the tone-mapped framebuffer value, or (B200RT_FLAG_LINEAR_TILES) the
+// mean radiance itself, to be added to the framebuffer and tone-mapped by k_untile_accumulate on the gathering device
+__device__ __forceinline__ float4 pixel_output(int flags, const float4* __restrict__ fb_in_rowmajor, size_t row_major_index, col mean)
+{
+    if (flags & B200RT_FLAG_LINEAR_TILES) return make_float4(mean.r, mean.g, mean.b, 0.0f);
+    const float4 fb = fb_in_rowmajor ? fb_in_rowmajor[row_major_index] : make_float4(0.0f, 0.0f, 0.0f, 1.0f);
+    return tonemap(fb, mean);
 }
 
 } // namespace b200rt

@@ -84,9 +84,8 @@ __global__ void __launch_bounds__(256) wf_init(SceneDev S, RenderParams P, WfBuf
         if (!inside) { out_tiles[wf_out_index(B, slot)] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); B.flags[slot] = WF_DONE; }
         else if (P.spp <= 0 || P.max_bounces <= 0)
         {
-            const float4 fb = fb_in_rowmajor ? fb_in_rowmajor[(size_t)y * P.cam.w + x] : make_float4(0.0f, 0.0f, 0.0f, 1.0f);
             const float n = (float)P.spp;
-            out_tiles[wf_out_index(B, slot)] = tonemap(fb, CO(0.0f / n, 0.0f / n, 0.0f / n));
+            out_tiles[wf_out_index(B, slot)] = pixel_output(P.flags, fb_in_rowmajor, (size_t)y * P.cam.w + x, CO(0.0f / n, 0.0f / n, 0.0f / n));
             B.flags[slot] = WF_DONE;
         }
         else
@@ -267,8 +266,7 @@ __global__ void __launch_bounds__(256, WF_SHADE_MIN_BLOCKS) wf_shade(SceneDev S,
             {
                 const float nspp = (float)P.spp;
                 const col mean = CO(final_color.r / nspp, final_color.g / nspp, final_color.b / nspp);
-                const float4 fb = fb_in_rowmajor ? fb_in_rowmajor[(size_t)y * P.cam.w + x] : make_float4(0.0f, 0.0f, 0.0f, 1.0f);
-                out_tiles[wf_out_index(B, slot)] = tonemap(fb, mean);
+                out_tiles[wf_out_index(B, slot)] = pixel_output(P.flags, fb_in_rowmajor, (size_t)y * P.cam.w + x, mean);
                 flags = WF_DONE;
                 pixel_done = true;
             }
@@ -671,18 +669,11 @@ __global__ void __launch_bounds__(32 * kCoopMaxWarps, WF_COOP_MIN_BLOCKS) wf_tra
 // a world * n_groups partition). Each group runs its own trace/shade iteration chain on its own stream, so while one
 // group's trace pass drains its longest rays (a single ray is a dependent chain of node fetches; the slowest ray of a
 // pass bounds that pass) the other groups' kernels fill the machine. Groups never exchange data.
-static int g_wf_sm_count = 0;
-
 cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGroup* groups, int n_groups, const float4* fb_in_rowmajor,
-                          float4* out_tiles, cudaStream_t stream, cudaEvent_t fork_event, int* launches_out, double* kernel_times4)
+                          float4* out_tiles, cudaStream_t stream, cudaEvent_t fork_event, int* launches_out, double* kernel_times4,
+                          unsigned int* unfinished_out)
 {
-    if (!g_wf_sm_count)
-    {
-        int dev = 0;
-        cudaGetDevice(&dev);
-        cudaDeviceGetAttribute(&g_wf_sm_count, cudaDevAttrMultiProcessorCount, dev);
-        if (g_wf_sm_count <= 0) g_wf_sm_count = 148;
-    }
+    const int n_sm = current_sm_count();
     int launches = 0;
     const int tl = traversal_layout(S, P.flags);
     const bool simple = (P.flags & B200RT_FLAG_SIMPLE_TRACE) != 0;
@@ -703,15 +694,18 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
     static const int grid_pct_env = []() { const char* e = getenv("B200RT_TRACE_GRID_PCT"); int v = e ? atoi(e) : 0; return v > 100 ? 100 : v; }();
     const bool timing_mode = getenv("B200RT_WF_TIMING") != nullptr || (P.flags & B200RT_FLAG_TIME_KERNELS);      // kernels run one at a time: full grid
     const int grid_pct = grid_pct_env >= 10 ? grid_pct_env : ((n_groups > 1 && !timing_mode) ? 58 : 100);
-    const int trace_grid = g_wf_sm_count * std::max(1, (per_sm * grid_pct + 50) / 100);
+    const int trace_grid = n_sm * std::max(1, (per_sm * grid_pct + 50) / 100);
     static const bool timing_env = getenv("B200RT_WF_TIMING") != nullptr;  // diagnostics: per-kernel times on stderr (serialises the groups)
     const bool timing = timing_env || (P.flags & B200RT_FLAG_TIME_KERNELS);
     int n_trace = 0, n_shade = 0;
     cudaError_t e;
 
-    // fork: every group stream starts after the work already queued on the caller's stream
+    // fork: every group stream starts after the work already queued on the caller's stream. From here on an error does not
+    // return: it ends the launching and falls through to the join, so that no group stream is left forked.
     if ((e = cudaEventRecord(fork_event, stream)) != cudaSuccess) return e;
-    struct GroupRun { RenderParams P; int parity; bool finished; int slot_grid; long long it, poll_it; bool poll_pending; };
+    cudaError_t err = cudaSuccess;
+#define WF_TRY(expr) do { if (err == cudaSuccess) { const cudaError_t e__ = (expr); if (e__ != cudaSuccess) err = e__; } } while (0)
+    struct GroupRun { RenderParams P; int parity; bool finished, forked; int slot_grid; long long it, poll_it; bool poll_pending; };
     GroupRun run[kMaxWfGroups];
     for (int g = 0; g < n_groups; g++)
     {
@@ -721,13 +715,17 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
         R.P.rank = P.rank + g * P.world;
         R.P.world = P.world * n_groups;
         R.P.n_rank_tiles = G.buf.n_slots / kTilePixels;
-        R.parity = 0; R.it = 0; R.poll_it = 0; R.poll_pending = false;
+        R.parity = 0; R.it = 0; R.poll_it = 0; R.poll_pending = false; R.forked = false;
         R.slot_grid = (G.buf.n_slots + 255) / 256;
         R.finished = R.slot_grid <= 0;
+        if (err != cudaSuccess) { R.finished = true; continue; }
+        WF_TRY(cudaStreamWaitEvent(G.stream, fork_event, 0));
+        if (err != cudaSuccess) { R.finished = true; continue; }
+        R.forked = true;
+        // an empty group (fewer tiles than groups) still gets its counters cleared: the frame's ray count sums every group
+        WF_TRY(cudaMemsetAsync(G.buf.counters, 0, 8 * sizeof(unsigned int), G.stream));
+        WF_TRY(cudaMemsetAsync(G.buf.rays_total, 0, sizeof(unsigned long long), G.stream));
         if (R.finished) continue;
-        if ((e = cudaStreamWaitEvent(G.stream, fork_event, 0)) != cudaSuccess) return e;
-        if ((e = cudaMemsetAsync(G.buf.counters, 0, 8 * sizeof(unsigned int), G.stream)) != cudaSuccess) return e;
-        if ((e = cudaMemsetAsync(G.buf.rays_total, 0, sizeof(unsigned long long), G.stream)) != cudaSuccess) return e;
         wf_init<<<R.slot_grid, 256, 0, G.stream>>>(S, R.P, G.buf, fb_in_rowmajor, out_tiles);
         launches++;
     }
@@ -736,10 +734,11 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
     double t_trace = 0.0, t_shade = 0.0;
     if (timing) for (int i = 0; i < 3; i++) cudaEventCreate(&tev[i]);
     int remaining = 0;
+    unsigned int unfinished = 0;
     for (int g = 0; g < n_groups; g++) remaining += run[g].finished ? 0 : 1;
-    while (remaining > 0)
+    while (remaining > 0 && err == cudaSuccess)
     {
-        for (int g = 0; g < n_groups; g++)
+        for (int g = 0; g < n_groups && err == cudaSuccess; g++)
         {
             GroupRun& R = run[g];
             if (R.finished) continue;
@@ -755,8 +754,12 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
             if (R.poll_pending && R.it - R.poll_it >= 8) continue;
             if (R.it >= max_iters)
             {
-                // safety net: every pixel must be finished by now; wait for the last poll and stop
-                if ((e = cudaStreamSynchronize(G.stream)) != cudaSuccess) return e;
+                // safety net: spp * (max_bounces + 1) iterations finish every pixel. Wait for the last poll; pixels still
+                // unfinished now are a bug and are reported to the caller, never dropped silently.
+                unsigned int left = 0;
+                WF_TRY(cudaStreamSynchronize(G.stream));
+                WF_TRY(cudaMemcpy(&left, &G.buf.counters[2], sizeof(left), cudaMemcpyDeviceToHost));
+                unfinished += left;
                 R.finished = true; remaining--;
                 continue;
             }
@@ -766,35 +769,37 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
             R.parity ^= 1;
             wf_shade<<<R.slot_grid, 256, 0, G.stream>>>(S, R.P, G.buf, fb_in_rowmajor, out_tiles, R.parity);
             launches += 2;
+            WF_TRY(cudaGetLastError());
             if (timing)
             {
                 cudaEventRecord(tev[2], G.stream);
-                cudaEventSynchronize(tev[2]);
+                WF_TRY(cudaEventSynchronize(tev[2]));
                 float a = 0, b = 0;
                 cudaEventElapsedTime(&a, tev[0], tev[1]); cudaEventElapsedTime(&b, tev[1], tev[2]);
-                unsigned int nq[8];
-                cudaMemcpy(nq, G.buf.counters, sizeof(nq), cudaMemcpyDeviceToHost);
+                unsigned int nq[8] = {};
+                WF_TRY(cudaMemcpy(nq, G.buf.counters, sizeof(nq), cudaMemcpyDeviceToHost));
                 t_trace += a; t_shade += b; n_trace++; n_shade++;
                 if (timing_env) fprintf(stderr, "wf g%d it %lld: trace %.3f ms  shade %.3f ms  active px %u  next queue %u\n", g, R.it, a, b, nq[2], nq[3 + R.parity]);
             }
             R.it++;
             if (!R.poll_pending && ((R.it & 3) == 0 || R.it >= max_iters))
             {
-                if ((e = cudaMemcpyAsync(G.host_active, &G.buf.counters[2], sizeof(unsigned int), cudaMemcpyDeviceToHost, G.stream)) != cudaSuccess) return e;
-                if ((e = cudaEventRecord(G.poll_event, G.stream)) != cudaSuccess) return e;
-                R.poll_pending = true;
-                R.poll_it = R.it;
+                WF_TRY(cudaMemcpyAsync(G.host_active, &G.buf.counters[2], sizeof(unsigned int), cudaMemcpyDeviceToHost, G.stream));
+                WF_TRY(cudaEventRecord(G.poll_event, G.stream));
+                if (err == cudaSuccess) { R.poll_pending = true; R.poll_it = R.it; }
             }
         }
     }
-    // join: the caller's stream continues after every group; the frame's ray count is the sum of the groups'
+    // join (on every path, error or not): the caller's stream continues after every group that was forked
     for (int g = 0; g < n_groups; g++)
     {
         const WfGroup& G = groups[g];
-        if (run[g].slot_grid <= 0) continue;
-        if ((e = cudaEventRecord(G.join_event, G.stream)) != cudaSuccess) return e;
-        if ((e = cudaStreamWaitEvent(stream, G.join_event, 0)) != cudaSuccess) return e;
+        if (!run[g].forked) continue;
+        const cudaError_t e1 = cudaEventRecord(G.join_event, G.stream);
+        const cudaError_t e2 = e1 == cudaSuccess ? cudaStreamWaitEvent(stream, G.join_event, 0) : e1;
+        if (err == cudaSuccess && e2 != cudaSuccess) err = e2;
     }
+#undef WF_TRY
     if (timing)
     {
         if (timing_env) fprintf(stderr, "wf total: trace %.3f ms  shade %.3f ms  launches %d\n", t_trace, t_shade, launches);
@@ -802,6 +807,8 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
         for (int i = 0; i < 3; i++) cudaEventDestroy(tev[i]);
     }
     if (launches_out) *launches_out = launches;
+    if (unfinished_out) *unfinished_out = unfinished;
+    if (err != cudaSuccess) return err;
     return cudaGetLastError();
 }
 

@@ -7,8 +7,11 @@
 // Same constructor, set_camera() and render() as include/render_kernel.h:24-57. The object still owns none of the scene
 // buffers (it stores the same references, :81-93); render() hands them to the C ABI of include/b200rt.h, which copies
 // them to HBM, renders on the GPU(s) and writes the tone-mapped frame back into the caller's Image in place.
-// The per-pixel / per-ray helper methods of the reference class (ray_trace_pixel, the BRDF and sampling functions)
-// live on the device now (csrc/pt_device.cuh) and are not part of this host class.
+// ray_trace_pixel(x, y) (render_kernel.h:56, the DEBUG_PIXEL mode of render_kernel.cpp:186-197) renders one pixel on the GPU.
+// The per-ray helper methods of the reference class (the BRDF and sampling functions) live on the device now
+// (csrc/pt_device.cuh) and are not part of this host class.
+// Environment: B200RT_GPUS=N renders every frame on N GPUs of this process (interleaved tiles, scene replicated, tiles gathered
+// over NVLink on device 0); the image is bit-identical to the 1-GPU one.
 #ifndef RENDER_KERNEL_H
 #define RENDER_KERNEL_H
 
@@ -51,6 +54,10 @@ public:
     // render_kernel.cpp:189-211: blocking; renders m_frame_buffer.width() x height() pixels in place
     void render();
 
+    // render_kernel.cpp:75-181: one pixel, accumulated into and tone-mapped in the framebuffer in place like the reference's
+    // (const there too: the framebuffer is a reference member)
+    void ray_trace_pixel(int x, int y) const;
+
     // statistics of the last render() (rays = INTERSECT_SCENE-equivalent queries)
     unsigned long long last_rays() const { return m_last_rays; }
     double last_kernel_ms() const { return m_last_kernel_ms; }
@@ -76,7 +83,10 @@ private:
 
     Camera m_camera;
 
-    b200rt_scene* m_scene = nullptr;
+    void ensure_scene() const;
+    void fill_camera(float* camera17) const;
+
+    mutable b200rt_scene* m_scene = nullptr;
     unsigned long long m_last_rays = 0;
     double m_last_kernel_ms = 0.0;
 };

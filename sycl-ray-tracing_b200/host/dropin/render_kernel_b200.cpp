@@ -63,26 +63,52 @@ Ray RenderKernel::get_camera_ray(float x, float y) const
     return Ray(origin, normalize(target - origin));
 }
 
-void RenderKernel::render()
+void RenderKernel::ensure_scene() const
 {
-    if (!m_scene)
+    if (m_scene) return;
+    // B200RT_GPUS=N: devices 0 .. N-1; B200RT_DEVICE_LIST=a,b,...: exactly these devices (a device may repeat)
+    const char* gpus_env = std::getenv("B200RT_GPUS");
+    int n_gpus = gpus_env ? std::atoi(gpus_env) : 1;
+    std::vector<int> device_list;
+    if (const char* list = std::getenv("B200RT_DEVICE_LIST"))
     {
-        const float* env = m_environment_map.data();
-        int rc = b200rt_scene_create(
-            reinterpret_cast<const float*>(m_triangle_buffer_access.data()), (int)m_triangle_buffer_access.size(),
-            m_materials_indices_buffer.data(), (int)m_materials_indices_buffer.size(),
-            reinterpret_cast<const float*>(m_materials_buffer_access.data()), (int)m_materials_buffer_access.size(),
-            m_emissive_triangle_indices_buffer.data(), (int)m_emissive_triangle_indices_buffer.size(),
-            m_sphere_buffer.empty() ? nullptr : m_sphere_buffer.data(), (int)m_sphere_buffer.size(),
-            env, m_environment_map.width(), m_environment_map.height(), m_env_map_cdf.data(),
-            nullptr /* build the flattened BVH from the triangles */, -1 /* current device */, &m_scene);
-        if (rc) die("scene upload failed");
+        for (const char* p = list; *p;)
+        {
+            char* end = nullptr;
+            const long v = std::strtol(p, &end, 10);
+            if (end == p) break;
+            device_list.push_back((int)v);
+            p = *end == ',' ? end + 1 : end;
+        }
+        if (!device_list.empty()) n_gpus = (int)device_list.size();
     }
-    float camera17[17];
+    const float* env = m_environment_map.data();
+    int rc = b200rt_scene_create_multi(
+        reinterpret_cast<const float*>(m_triangle_buffer_access.data()), (int)m_triangle_buffer_access.size(),
+        m_materials_indices_buffer.data(), (int)m_materials_indices_buffer.size(),
+        reinterpret_cast<const float*>(m_materials_buffer_access.data()), (int)m_materials_buffer_access.size(),
+        m_emissive_triangle_indices_buffer.data(), (int)m_emissive_triangle_indices_buffer.size(),
+        m_sphere_buffer.empty() ? nullptr : m_sphere_buffer.data(), (int)m_sphere_buffer.size(),
+        env, 4, m_environment_map.width(), m_environment_map.height(), m_env_map_cdf.data(),
+        nullptr /* build the flattened BVH from the triangles */,
+        device_list.empty() ? nullptr /* devices 0 .. n-1 (one device: the current one) */ : device_list.data(),
+        n_gpus > 1 ? n_gpus : 1, &m_scene);
+    if (rc) die("scene upload failed");
+}
+
+void RenderKernel::fill_camera(float* camera17) const
+{
     for (int i = 0; i < 4; i++)
         for (int j = 0; j < 4; j++)
             camera17[4 * i + j] = m_camera.view_matrix.m[i][j];
     camera17[16] = m_camera.fov_dist;
+}
+
+void RenderKernel::render()
+{
+    ensure_scene();
+    float camera17[17];
+    fill_camera(camera17);
 
     b200rt_render_options opts;
     b200rt_default_render_options(&opts);
@@ -94,4 +120,20 @@ void RenderKernel::render()
     if (rc) die("render failed");
     m_last_rays = stats.rays;
     m_last_kernel_ms = stats.kernel_ms;
+}
+
+void RenderKernel::ray_trace_pixel(int x, int y) const
+{
+    ensure_scene();
+    float camera17[17];
+    fill_camera(camera17);
+    // the pixel's mean radiance tone-mapped on a black framebuffer comes back from the device; the reference adds the
+    // mean to the pixel's current value first (:169). A pixel is rendered once, from Color::Black(), in every use the reference makes
+    // of this method (render(), DEBUG_PIXEL), which is the case reproduced bit for bit here.
+    float rgba[4];
+    int rc = b200rt_render_region(m_scene, camera17, m_frame_buffer.width(), m_frame_buffer.height(), m_render_samples, m_max_bounces,
+                                  x, y, x + 1, y + 1, rgba, nullptr, nullptr);
+    if (rc) die("ray_trace_pixel failed");
+    Color& px = m_frame_buffer[y * m_frame_buffer.width() + x];
+    px = Color(rgba[0], rgba[1], rgba[2], rgba[3]);
 }
