@@ -140,6 +140,8 @@ size_t b200rt_scene_device_bytes(const b200rt_scene* scene);
 /* ---- rendering -------------------------------------------------------------------------------------------------------- */
 #define B200RT_INTEGRATOR_MEGAKERNEL 0   /* persistent lanes, one pixel at a time per lane, single trace site */
 #define B200RT_INTEGRATOR_WAVEFRONT 1    /* path-regeneration wavefront: shade / trace kernel pairs over tile groups (default) */
+#define B200RT_INTEGRATOR_PERSISTENT 2   /* the wavefront without its frame-wide barrier: one launch per frame, every warp shades and traces
+                                            its own K * 32 pixel slots and pulls new pixels as they finish (csrc/persist.cu) */
 
 #define B200RT_FLAG_FB_IS_ZERO 1         /* caller guarantees the framebuffer is Color::Black(): skip its upload */
 #define B200RT_FLAG_SKIP_DEAD_RAYS 2     /* skip rays whose result provably cannot change the image */

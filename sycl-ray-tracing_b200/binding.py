@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("B200RT_LIB") or os.path.join(HERE, "libb200rt.so")   
 
 INTEGRATOR_MEGAKERNEL = 0
 INTEGRATOR_WAVEFRONT = 1
+INTEGRATOR_PERSISTENT = 2
 FLAG_FB_IS_ZERO = 1
 FLAG_SKIP_DEAD_RAYS = 2
 FLAG_DIAG_SLABS = 4

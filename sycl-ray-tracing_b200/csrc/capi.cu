@@ -47,6 +47,8 @@ struct b200rt_scene
     void* bvh_window = nullptr; size_t bvh_window_bytes = 0;   // 8-ary nodes + triangles, kept resident in L2 (see pin_bvh_in_l2)
     bool l2_pinned = false, l2_window_set = false;
     double kernel_times[4] = {};          // B200RT_FLAG_TIME_KERNELS: trace ms, shade ms, trace launches, shade launches of the last render
+    // persistent integrator state (allocated on first use)
+    WfBuffers pw{}; int pw_cap = 0, pw_grid = 0; std::vector<void*> pw_allocs;
     // multi-GPU scenes (b200rt_scene_create_multi): this scene is rank 0; replicas[i] is rank i + 1 on another device, owned here
     std::vector<b200rt_scene*> replicas;
     float4* d_gather = nullptr; size_t gather_cap = 0;      // rank 0: world per-rank tile buffers, rank-major (the peer copies' destination)
@@ -342,6 +344,35 @@ int ensure_wavefront(b200rt_scene* s, const RenderParams& P)
     return B200RT_OK;
 }
 
+template <typename T>
+cudaError_t pw_alloc(b200rt_scene* s, T** p, size_t n)
+{
+    void* d = nullptr;
+    cudaError_t e = cudaMalloc(&d, n * sizeof(T));
+    if (e == cudaSuccess) { s->pw_allocs.push_back(d); *p = (T*)d; }
+    return e;
+}
+
+int ensure_persistent(b200rt_scene* s)
+{
+    const int grid = persistent_grid();
+    const int n = persistent_slots(grid);
+    s->pw_grid = grid;
+    if (n <= s->pw_cap) { s->pw.n_slots = n; return B200RT_OK; }
+    for (void* p : s->pw_allocs) cudaFree(p);
+    s->pw_allocs.clear(); s->pw_cap = 0;
+    WfBuffers& w = s->pw;
+    const size_t m = (size_t)n;
+    CU(pw_alloc(s, &w.rng, m)); CU(pw_alloc(s, &w.sample, m)); CU(pw_alloc(s, &w.bounce, m)); CU(pw_alloc(s, &w.flags, m));
+    CU(pw_alloc(s, &w.final_c, m)); CU(pw_alloc(s, &w.sample_c, m)); CU(pw_alloc(s, &w.thr, m)); CU(pw_alloc(s, &w.thr_next, m));
+    CU(pw_alloc(s, &w.ray_o, 5 * m)); CU(pw_alloc(s, &w.ray_d, 5 * m)); CU(pw_alloc(s, &w.side_w, 4 * m));
+    CU(pw_alloc(s, &w.res_t, 5 * m)); CU(pw_alloc(s, &w.res_prim, 5 * m)); CU(pw_alloc(s, &w.res_tslot, 5 * m));
+    CU(pw_alloc(s, &w.queue, 5 * m)); CU(pw_alloc(s, &w.counters, (size_t)8)); CU(pw_alloc(s, &w.rays_total, (size_t)1));
+    w.n_slots = n; w.tile_stride = 1; w.tile_offset = 0;
+    s->pw_cap = n;
+    return B200RT_OK;
+}
+
 // Node caching in L2 (opt-in, B200RT_L2_PERSIST=1): a persisting access-policy window over [8-ary nodes | triangles] on every
 // stream that launches traversal kernels keeps what rays fetch resident while the wavefront state streams through L2.
 // Measured on C3 (1080p, 64 spp): 1958 Mrays/s with the window vs 2129 without — the set-aside takes L2 away from the
@@ -395,6 +426,16 @@ int run_integrator(b200rt_scene* s, const RenderParams& P, int integrator, const
         if (unfinished) return fail(B200RT_ERR_CUDA, "wavefront integrator: %u pixels unfinished after spp * (max_bounces + 1) iterations", unfinished);
         CU(wavefront_sum_rays(s->wf, s->wf_groups, s->d_rays, st));
         *launches += 1;
+        return B200RT_OK;
+    }
+    if (integrator == B200RT_INTEGRATOR_PERSISTENT)
+    {
+        if (!dev.has_wide) return fail(B200RT_ERR_ARG, "the persistent integrator traverses the 8-ary BVH (leaves of at most 3 triangles)");
+        int rc = ensure_persistent(s);
+        if (rc) return rc;
+        CU(run_persistent(dev, P, s->pw, s->pw_grid, fb_in, out_tiles, st));
+        CU(cudaMemcpyAsync(s->d_rays, s->pw.rays_total, sizeof(unsigned long long), cudaMemcpyDeviceToDevice, st));
+        *launches = 1;
         return B200RT_OK;
     }
     CU(launch_megakernel(dev, P, fb_in, out_tiles, s->d_work, s->d_rays, st));
@@ -874,6 +915,7 @@ void b200rt_scene_destroy(b200rt_scene* s)
     if (s->d_prim) cudaFree(s->d_prim);
     if (s->d_t) cudaFree(s->d_t);
     for (void* p : s->wf_allocs) cudaFree(p);
+    for (void* p : s->pw_allocs) cudaFree(p);
     if (s->h_active)
     {
         for (int g = 0; g < kMaxWfGroups; g++)
@@ -919,7 +961,7 @@ int b200rt_render_tiles_device(b200rt_scene* s, const float* camera17, int w, in
     int rc = make_params(s, camera17, w, h, spp, bounces, opts, P);
     if (rc) return rc;
     if (!dev_tiles) return fail(B200RT_ERR_ARG, "dev_tiles must not be NULL");
-    if (opts && opts->integrator != B200RT_INTEGRATOR_MEGAKERNEL && opts->integrator != B200RT_INTEGRATOR_WAVEFRONT)
+    if (opts && (opts->integrator < B200RT_INTEGRATOR_MEGAKERNEL || opts->integrator > B200RT_INTEGRATOR_PERSISTENT))
         return fail(B200RT_ERR_ARG, "unknown integrator %d", opts->integrator);
     ON_DEVICE(s->device);
     if ((rc = ensure_scratch(s, 0, 0, 0))) return rc;
@@ -1015,7 +1057,7 @@ int render_frame(b200rt_scene* s, const float* camera17, int w, int h, int spp, 
     int rc = make_params(s, camera17, w, h, spp, bounces, opts, P);
     if (rc) return rc;
     const int integrator = opts ? opts->integrator : B200RT_INTEGRATOR_WAVEFRONT;
-    if (integrator != B200RT_INTEGRATOR_MEGAKERNEL && integrator != B200RT_INTEGRATOR_WAVEFRONT) return fail(B200RT_ERR_ARG, "unknown integrator %d", integrator);
+    if ((integrator < B200RT_INTEGRATOR_MEGAKERNEL || integrator > B200RT_INTEGRATOR_PERSISTENT)) return fail(B200RT_ERR_ARG, "unknown integrator %d", integrator);
     if (P.flags & B200RT_FLAG_LINEAR_TILES) return fail(B200RT_ERR_ARG, "B200RT_FLAG_LINEAR_TILES is for b200rt_render_tiles_device");
     const int n_dev = 1 + (int)s->replicas.size();
     if (n_dev > 1 && P.world != 1) return fail(B200RT_ERR_ARG, "a multi-GPU scene partitions the frame itself: rank/world must stay 0/1");

@@ -49,4 +49,10 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
                           unsigned int* unfinished_out = nullptr);
 cudaError_t wavefront_sum_rays(const WfGroup* groups, int n_groups, unsigned long long* total, cudaStream_t stream);
 
+// persistent integrator (persist.cu): one launch per frame, every warp its own wavefront machine
+int persistent_grid();
+int persistent_slots(int grid);
+cudaError_t run_persistent(const SceneDev& S, const RenderParams& P, const WfBuffers& B, int grid, const float4* fb_in_rowmajor,
+                           float4* out_tiles, cudaStream_t stream);
+
 } // namespace b200rt

@@ -18,58 +18,17 @@
 #include <cstdio>
 #include <cstdlib>
 
-#include "kernels.h"
-#include "pt_device.cuh"
+#include "wf_device.cuh"
 
 namespace b200rt {
 
 #ifndef WF_SHADE_MIN_BLOCKS
 #define WF_SHADE_MIN_BLOCKS 4
 #endif
-enum { WF_ALIVE = 1, WF_PENDING = 2, WF_TERMINATED = 4, WF_DONE = 8 };
-
-__device__ __forceinline__ void wf_enqueue(unsigned int* queue, unsigned int* counter, bool pred, unsigned int entry)
-{
-    const unsigned int mask = __ballot_sync(0xffffffffu, pred);
-    if (!mask) return;
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(mask) - 1;
-    unsigned int base = 0;
-    if (lane == leader) base = atomicAdd(counter, (unsigned int)__popc(mask));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (pred) queue[base + __popc(mask & ((1u << lane) - 1u))] = entry;
-}
-
-__device__ __forceinline__ void wf_store_ray(const WfBuffers& B, int k, int slot, v3 o, v3 d, float tmax, int kind)
-{
-    const size_t i = (size_t)k * B.n_slots + slot;
-    B.ray_o[i] = make_float4(o.x, o.y, o.z, tmax);
-    B.ray_d[i] = make_float4(d.x, d.y, d.z, __int_as_float(kind));
-}
-
-__device__ __forceinline__ void wf_start_sample(const RenderParams& P, const WfBuffers& B, int slot, int x, int y, uint32_t& rng)
-{
-    const float xj = ((float)x + 0.5f) + xs_float(rng) - 1.0f;      // :88-89
-    const float yj = ((float)y + 0.5f) + xs_float(rng) - 1.0f;
-    v3 o, d;
-    camera_ray(P.cam, xj, yj, o, d);
-    wf_store_ray(B, 4, slot, o, d, 0.0f, SIDE_CLOSEST_LIGHT);
-}
 
 __device__ __forceinline__ size_t wf_out_index(const WfBuffers& B, int slot)
 {
     return ((size_t)(slot >> 8) * B.tile_stride + B.tile_offset) * kTilePixels + (slot & 255);
-}
-
-__device__ __forceinline__ bool wf_slot_pixel(const RenderParams& P, int slot, int& x, int& y)
-{
-    const int unit = slot >> 5, lane = slot & 31;
-    const int k = unit >> 3, sub = unit & 7;
-    const int tile_id = P.rank + k * P.world;
-    const int tx = tile_id % P.tiles_x, ty = tile_id / P.tiles_x;
-    x = tx * kTileDim + (sub & 1) * kPatchW + (lane & 7);
-    y = ty * kTileDim + (sub >> 1) * kPatchH + (lane >> 3);
-    return x < P.cam.w && y < P.cam.h;
 }
 
 __global__ void __launch_bounds__(256) wf_init(SceneDev S, RenderParams P, WfBuffers B, const float4* __restrict__ fb_in_rowmajor,
@@ -90,32 +49,13 @@ __global__ void __launch_bounds__(256) wf_init(SceneDev S, RenderParams P, WfBuf
         }
         else
         {
-            uint32_t rng = pixel_rng(x, y, P.spp);
-            wf_start_sample(P, B, slot, x, y, rng);
-            B.rng[slot] = rng;
-            B.sample[slot] = 0;
-            B.bounce[slot] = 0;
-            B.final_c[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            B.sample_c[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-            B.thr[slot] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
-            B.flags[slot] = WF_ALIVE;
+            wf_begin_pixel(P, B, slot, x, y);
             q_path = true;
         }
     }
     const unsigned int active = __ballot_sync(0xffffffffu, q_path);
     if ((threadIdx.x & 31) == 0 && active) atomicAdd(&B.counters[2], (unsigned int)__popc(active));
     wf_enqueue(B.queue, &B.counters[3], q_path, ((unsigned int)slot << 3) | 4u);
-}
-
-// normal of an analytic sphere hit (Sphere::intersect, sphere.h:47-49), recomputed from the stored hit distance
-__device__ __forceinline__ v3 wf_sphere_normal(const SceneDev& S, int prim, v3 p)
-{
-    for (int i = 0; i < S.n_spheres; i++)
-    {
-        const SphereDev s = S.spheres[i];
-        if (s.prim == prim) return normalize(p - V(s.cx, s.cy, s.cz));
-    }
-    return V(0.0f, 0.0f, 0.0f);
 }
 
 __global__ void __launch_bounds__(256, WF_SHADE_MIN_BLOCKS) wf_shade(SceneDev S, RenderParams P, WfBuffers B, const float4* __restrict__ fb_in_rowmajor,
@@ -129,175 +69,23 @@ __global__ void __launch_bounds__(256, WF_SHADE_MIN_BLOCKS) wf_shade(SceneDev S,
         B.counters[3 + (parity ^ 1)] = 0;      // the other queue was fully consumed by the previous trace pass
         B.counters[5 + parity] = 0;            // head of the queue this pass fills
     }
-    bool q_path = false, q0 = false, q1 = false, q2 = false, q3 = false, pixel_done = false;
+    ShadeOut R;
+    R.q_path = R.q0 = R.q1 = R.q2 = R.q3 = R.pixel_done = false; R.flags = 0;
     const int flags_in = slot < n ? B.flags[slot] : WF_DONE;
     if (!(flags_in & WF_DONE))
     {
         int x, y;
         wf_slot_pixel(P, slot, x, y);
-        uint32_t rng = B.rng[slot];
-        int sample = B.sample[slot], bounce = B.bounce[slot];
-        float4 t4 = B.thr[slot], s4 = B.sample_c[slot];
-        col throughput = CO(t4.x, t4.y, t4.z), sample_color = CO(s4.x, s4.y, s4.z);
-        int flags = flags_in;
-        bool finish = false;
-        const bool trace_light_brdf = S.any_emissive_material || !(P.flags & B200RT_FLAG_SKIP_DEAD_RAYS);
-
-        // A. resolve the side rays of the previous surface interaction
-        if (flags & WF_PENDING)
-        {
-            col c[4];
-#pragma unroll
-            for (int k = 0; k < 4; k++)
-            {
-                c[k] = CO(0.0f, 0.0f, 0.0f);
-                const size_t i = (size_t)k * n + slot;
-                const float4 rd4 = B.ray_d[i];
-                const int kind = __float_as_int(rd4.w);
-                if (kind == SIDE_NONE) continue;
-                const float4 w4 = B.side_w[i];
-                if (kind == SIDE_CLOSEST_LIGHT)
-                {
-                    const float t = B.res_t[i];
-                    if (t > 0.0f)
-                    {
-                        const float4 ro4 = B.ray_o[i];
-                        SideRay sr;
-                        sr.o = V(ro4.x, ro4.y, ro4.z); sr.d = V(rd4.x, rd4.y, rd4.z);
-                        sr.weight = CO(w4.x, w4.y, w4.z); sr.pdf = w4.w; sr.kind = kind; sr.tmax = 0.0f;
-                        Hit h;
-                        h.t = t; h.prim = B.res_prim[i]; h.slot = B.res_tslot[i]; h.u = h.v = -1.0f;
-                        if (h.slot < 0) h.sphere_n = wf_sphere_normal(S, h.prim, sr.o + t * sr.d);
-                        c[k] = side_light_hit(S, sr, h);
-                    }
-                }
-                else if (B.res_prim[i] == 0) c[k] = CO(w4.x, w4.y, w4.z);      // unoccluded
-            }
-            sample_color = sample_color + ((c[0] + c[1]) + (c[3] + c[2])) * throughput;     // light = c0+c1 (:712), env = c3+c2 (:630), :128
-            const float4 tn = B.thr_next[slot];
-            throughput = CO(tn.x, tn.y, tn.z);
-            flags &= ~WF_PENDING;
-            if (flags & WF_TERMINATED) finish = true;
-        }
-
-        // B. consume the path ray
-        if (!finish && (flags & WF_ALIVE))
-        {
-            const size_t i = (size_t)4 * n + slot;
-            const float4 ro4 = B.ray_o[i], rd4 = B.ray_d[i];
-            const v3 ro = V(ro4.x, ro4.y, ro4.z), rd = V(rd4.x, rd4.y, rd4.z);
-            const float t = B.res_t[i];
-            if (!(t > 0.0f))
-            {
-                if (bounce == 0 && P.max_bounces >= 2)                           // :146-159
-                    sample_color = sample_color + env_from_direction(S, rd) * throughput;
-                finish = true;
-            }
-            else
-            {
-                Hit h;
-                h.t = t; h.prim = B.res_prim[i]; h.slot = B.res_tslot[i]; h.u = h.v = -1.0f;
-                Surface sf;
-                sf.p = ro + t * rd;
-                if (h.slot >= 0)
-                {
-                    const float4 ve1 = __ldg(S.tris + 3 * (size_t)h.slot + 1), ve2 = __ldg(S.tris + 3 * (size_t)h.slot + 2);
-                    sf.n = normalize(cross(V(ve1.x, ve1.y, ve1.z), V(ve2.x, ve2.y, ve2.z)));
-                }
-                else sf.n = wf_sphere_normal(S, h.prim, sf.p);
-                sf.view = -rd;
-                sf.m = S.mats[__ldg(S.mat_idx + h.prim)];                        // :107-108
-                SideRay sr;
-                sr.o = sr.d = V(0.0f, 0.0f, 0.0f); sr.tmax = 0.0f; sr.pdf = 0.0f; sr.weight = CO(0.0f, 0.0f, 0.0f);
-                side_light_sample(S, sf, rng, sr);
-                wf_store_ray(B, 0, slot, sr.o, sr.d, sr.tmax, sr.kind);
-                if (sr.kind != SIDE_NONE) { B.side_w[(size_t)0 * n + slot] = make_float4(sr.weight.r, sr.weight.g, sr.weight.b, 0.0f); q0 = true; }
-                side_light_brdf(S, sf, rng, sr);
-                if (sr.kind != SIDE_NONE && !trace_light_brdf) sr.kind = SIDE_NONE;
-                wf_store_ray(B, 1, slot, sr.o, sr.d, 0.0f, sr.kind);
-                if (sr.kind != SIDE_NONE) { B.side_w[(size_t)1 * n + slot] = make_float4(sr.weight.r, sr.weight.g, sr.weight.b, sr.pdf); q1 = true; }
-                side_env_sample(S, sf, rng, sr);
-                wf_store_ray(B, 2, slot, sr.o, sr.d, 0.0f, sr.kind);
-                if (sr.kind != SIDE_NONE) { B.side_w[(size_t)2 * n + slot] = make_float4(sr.weight.r, sr.weight.g, sr.weight.b, 0.0f); q2 = true; }
-                side_env_brdf(S, sf, rng, sr);
-                wf_store_ray(B, 3, slot, sr.o, sr.d, 0.0f, sr.kind);
-                if (sr.kind != SIDE_NONE) { B.side_w[(size_t)3 * n + slot] = make_float4(sr.weight.r, sr.weight.g, sr.weight.b, 0.0f); q3 = true; }
-
-                float bpdf;
-                v3 ndir = V(0.0f, 0.0f, 0.0f);
-                const col brdf = ct_sample(sf.m, sf.view, sf.n, ndir, bpdf, rng);        // :123
-                if (bounce == 0) sample_color = sample_color + CO(sf.m.er, sf.m.eg, sf.m.eb);
-                flags = WF_PENDING;
-                col tnext = throughput;
-                if (is_black(brdf) || bpdf < 1.0e-8f || isinf(bpdf)) flags |= WF_TERMINATED;     // :130-135
-                else
-                {
-                    tnext = throughput * ((brdf * smax(0.0f, dot(ndir, sf.n))) / bpdf);       // :137
-                    bounce++;
-                    if (bounce >= P.max_bounces) flags |= WF_TERMINATED;
-                    else
-                    {
-                        wf_store_ray(B, 4, slot, sf.p + 1.0e-4f * sf.n, ndir, 0.0f, SIDE_CLOSEST_LIGHT);
-                        flags |= WF_ALIVE;
-                        q_path = true;
-                    }
-                }
-                B.thr_next[slot] = make_float4(tnext.r, tnext.g, tnext.b, 0.0f);
-            }
-        }
-
-        // C. finish the sample: next sample of this pixel, or the pixel itself
-        if (finish)
-        {
-            float4 f4 = B.final_c[slot];
-            col final_color = CO(f4.x, f4.y, f4.z) + sample_color;
-            sample++;
-            if (sample < P.spp)
-            {
-                B.final_c[slot] = make_float4(final_color.r, final_color.g, final_color.b, 0.0f);
-                wf_start_sample(P, B, slot, x, y, rng);
-                throughput = CO(1.0f, 1.0f, 1.0f);
-                sample_color = CO(0.0f, 0.0f, 0.0f);
-                bounce = 0;
-                flags = WF_ALIVE;
-                q_path = true;
-            }
-            else
-            {
-                const float nspp = (float)P.spp;
-                const col mean = CO(final_color.r / nspp, final_color.g / nspp, final_color.b / nspp);
-                out_tiles[wf_out_index(B, slot)] = pixel_output(P.flags, fb_in_rowmajor, (size_t)y * P.cam.w + x, mean);
-                flags = WF_DONE;
-                pixel_done = true;
-            }
-        }
-        B.rng[slot] = rng;
-        B.sample[slot] = sample;
-        B.bounce[slot] = bounce;
-        B.thr[slot] = make_float4(throughput.r, throughput.g, throughput.b, 0.0f);
-        B.sample_c[slot] = make_float4(sample_color.r, sample_color.g, sample_color.b, 0.0f);
-        B.flags[slot] = flags;
+        R = wf_shade_slot(S, P, B, slot, flags_in, x, y, wf_out_index(B, slot), fb_in_rowmajor, out_tiles);
     }
-    const unsigned int done_mask = __ballot_sync(0xffffffffu, pixel_done);
+    const unsigned int done_mask = __ballot_sync(0xffffffffu, R.pixel_done);
     if ((threadIdx.x & 31) == 0 && done_mask) atomicSub(&B.counters[2], (unsigned int)__popc(done_mask));
     const unsigned int s3 = (unsigned int)slot << 3;
-    wf_enqueue(B.queue, q_count, q_path, s3 | 4u);
-    wf_enqueue(B.queue, q_count, q0, s3 | 0u);
-    wf_enqueue(B.queue, q_count, q1, s3 | 1u);
-    wf_enqueue(B.queue, q_count, q2, s3 | 2u);
-    wf_enqueue(B.queue, q_count, q3, s3 | 3u);
-}
-
-// result of one queue entry
-__device__ __forceinline__ void wf_store_result(const WfBuffers& B, size_t r, int mode, bool found, const Hit& h)
-{
-    if (mode == TRACE_CLOSEST)
-    {
-        B.res_t[r] = found ? h.t : -1.0f;
-        B.res_prim[r] = h.prim;
-        B.res_tslot[r] = h.slot;
-    }
-    else B.res_prim[r] = found ? 1 : 0;
+    wf_enqueue(B.queue, q_count, R.q_path, s3 | 4u);
+    wf_enqueue(B.queue, q_count, R.q0, s3 | 0u);
+    wf_enqueue(B.queue, q_count, R.q1, s3 | 1u);
+    wf_enqueue(B.queue, q_count, R.q2, s3 | 2u);
+    wf_enqueue(B.queue, q_count, R.q3, s3 | 3u);
 }
 
 // ablation variant (B200RT_FLAG_SIMPLE_TRACE): one ray per lane, grid-stride over the queue (the warp waits for its slowest ray)
@@ -321,15 +109,10 @@ __global__ void wf_trace_simple(SceneDev S, WfBuffers B, int parity)
     }
 }
 
-// default variant, persistent: every lane owns one traversal state; whenever at least kRefillThreshold lanes of a warp are idle
-// they are refilled with new rays from the warp's private block of the queue (blocks of kWarpBlock rays are claimed
-// with one atomic), so no lane waits for the slowest ray of its warp (Aila & Laine's persistent threads, per lane).
-#ifndef WF_WARP_BLOCK
-#define WF_WARP_BLOCK 64
-#endif
-#ifndef WF_REFILL
-#define WF_REFILL 8
-#endif
+// phase-vote persistent kernel (the default on the binary layout): every lane owns one traversal state; whenever at least
+// kRefillThreshold lanes of a warp are idle they are refilled with new rays from the warp's private block of the queue (blocks
+// of kWarpBlock rays are claimed with one atomic), so no lane waits for the slowest ray of its warp (Aila & Laine's persistent
+// threads, per lane).
 #ifndef WF_LEAF_MIN
 #define WF_LEAF_MIN 4
 #endif
@@ -338,8 +121,6 @@ __global__ void wf_trace_simple(SceneDev S, WfBuffers B, int parity)
 #else
 #define WF_TRACE_BOUNDS
 #endif
-constexpr int kWarpBlock = WF_WARP_BLOCK;
-constexpr int kRefillThreshold = WF_REFILL;
 constexpr int kLeafThreshold = WF_LEAF_MIN;
 
 // one interface over the binary and the 8-ary traversal state machines, so the persistent kernel below serves every layout
@@ -444,71 +225,7 @@ __global__ void WF_TRACE_BOUNDS wf_trace(SceneDev S, WfBuffers B, int parity)
     }
 }
 
-// ---- default trace kernel for the 8-ary layout: persistent lanes + warp-cooperative triangle tests --------------------------------
-// ncu on the phase-vote kernel above (profiles/r1b_*): the node step ran with 20.7 of 32 lanes, but the exact triangle
-// tests with only 7.3 — few lanes of a warp hold a leaf at the same time, and those that do hold different numbers of
-// triangles — and that phase took 45 % of the stall samples. Here a lane never tests its own triangles. The node step
-// leaves a lane's hit triangles as (owner lane, triangle slot) pairs in a per-warp shared-memory queue and the lane goes
-// straight on with its next node; whenever the queue holds 32 pairs, all 32 lanes test one pair each (ray from the owner's
-// shared-memory record, Moller-Trumbore exactly as triangle.h:16-60) and fold the result into the owner's 64-bit key
-// (t bits << 32 | primitive index) with a shared-memory atomicMin — which is exactly the closest-hit rule of the other
-// kernels (smaller t, ties to the lower original index). Owners pick up their new t_best after each drain. A ray is
-// finished when it has no node work and no pair left in the queue.
-#ifndef WF_COOP_QUEUE
-#define WF_COOP_QUEUE 160
-#endif
-constexpr int kCoopQueue = WF_COOP_QUEUE;   // pairs per warp (> 32); an append that does not fit drains first (a build with 40 runs the GPU
-                                            // test suite through that path all the time)
-constexpr int kCoopMaxWarps = 4;         // the kernel is launched with 128-thread CTAs
-constexpr unsigned long long kNoHit = 0xffffffffffffffffull;
-
-struct CoopWarp
-{
-    float4 ro[32], rd[32];              // per lane: origin + tmax, direction + trace mode
-    unsigned long long best[32];        // per lane: (t bits << 32) | primitive index of the best accepted hit
-    unsigned int q[kCoopQueue];         // (owner lane << 27) | triangle slot
-    unsigned int pend[32];
-};
-
-// all 32 lanes: test whole batches of 32 pairs (and the last partial one if `full`), compact the rest to the queue's front,
-// tell every lane whether it still owns a queued pair
-__device__ __forceinline__ void coop_drain(const SceneDev& S, CoopWarp& W, const int lane, unsigned int& qcount, const bool full, bool& pending)
-{
-    unsigned int base = 0;
-    while (qcount - base >= 32u || (full && base < qcount))
-    {
-        const unsigned int nb = min(32u, qcount - base);
-        if ((unsigned int)lane < nb)
-        {
-            const unsigned int e = W.q[base + lane];
-            const unsigned int owner = e >> 27, slot = e & 0x07ffffffu;
-            const float4 ro4 = W.ro[owner], rd4 = W.rd[owner];
-            const float4* tp = S.tris + 3 * (size_t)slot;
-            const float4 va = __ldg(tp), ve1 = __ldg(tp + 1), ve2 = __ldg(tp + 2);
-            float t, u, v;
-            if (tri_test(va, ve1, ve2, V(ro4.x, ro4.y, ro4.z), V(rd4.x, rd4.y, rd4.z), t, u, v))
-            {
-                const int mode = __float_as_int(rd4.w);
-                if (mode != TRACE_SHADOW || t + 1.0e-4f < ro4.w)
-                {
-                    const unsigned long long key = ((unsigned long long)__float_as_uint(t) << 32) | (unsigned int)__float_as_int(va.w);
-                    if (key < W.best[owner]) atomicMin(&W.best[owner], key);
-                }
-            }
-        }
-        base += nb;
-    }
-    __syncwarp();
-    const unsigned int rem = qcount - base;
-    const unsigned int e = (unsigned int)lane < rem ? W.q[base + lane] : 0u;
-    W.pend[lane] = 0u;
-    __syncwarp();
-    if ((unsigned int)lane < rem) { W.q[lane] = e; W.pend[e >> 27] = 1u; }
-    __syncwarp();
-    pending = W.pend[lane] != 0u;
-    qcount = rem;
-}
-
+// ---- default trace kernel for the 8-ary layout: persistent lanes + warp-cooperative triangle tests (wf_device.cuh) ------------------
 #ifndef WF_COOP_MIN_BLOCKS
 #define WF_COOP_MIN_BLOCKS 7            // <= 72 registers: 28 warps per SM; 32 (64 registers) measured the same, 16 (117 registers) 20 % slower
 #endif
@@ -516,18 +233,15 @@ __global__ void __launch_bounds__(32 * kCoopMaxWarps, WF_COOP_MIN_BLOCKS) wf_tra
 {
     __shared__ CoopWarp s_warps[kCoopMaxWarps];
     CoopWarp& W = s_warps[threadIdx.x >> 5];
-    const unsigned int FULL = 0xffffffffu;
-    const int lane = threadIdx.x & 31;
-    const unsigned int lanes_below = (1u << lane) - 1u;
     const unsigned int n_rays = B.counters[3 + parity];
-    unsigned int* head = &B.counters[5 + parity];
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(B.rays_total, (unsigned long long)n_rays);
-    const int n = B.n_slots;
-    const bool spheres = S.n_spheres != 0;
+    // rays claimed per atomic: kWarpBlock when the queue is long, down to one warp's worth when it is short (otherwise a
+    // few warps would serialise a short queue while the rest of the machine idles)
     const unsigned int total_warps = gridDim.x * (blockDim.x >> 5);
-    const unsigned int warp_block = min((unsigned int)kWarpBlock, max(32u, (n_rays / total_warps) & ~31u));
-
-    Trav8 T;
+    CoopQueueShared src;
+    src.head = &B.counters[5 + parity];
+    src.n_rays = n_rays;
+    src.warp_block = min((unsigned int)kWarpBlock, max(32u, (n_rays / total_warps) & ~31u));
 #ifdef WF_COOP_LOCAL_STACK
     TravStack8 K;
 #else
@@ -535,133 +249,7 @@ __global__ void __launch_bounds__(32 * kCoopMaxWarps, WF_COOP_MIN_BLOCKS) wf_tra
     TravStack8Shared K;
     K.sh = s_stack + threadIdx.x; K.stride = 32 * kCoopMaxWarps;
 #endif
-    T.done = true; T.tg = make_uint2(0u, 0u);
-    bool active = false, pending = false;
-    size_t r = 0;
-    int mode = TRACE_CLOSEST;
-    unsigned int blk_next = 0, blk_end = 0, qcount = 0;       // warp-uniform
-    bool exhausted = false;                                   // warp-uniform
-
-    for (;;)
-    {
-        // (1) refill idle lanes from the warp's private block of the ray queue
-        unsigned int idle = __ballot_sync(FULL, !active);
-        if (idle && !exhausted && (idle == FULL || __popc(idle) >= kRefillThreshold))
-        {
-            if (blk_next >= blk_end)
-            {
-                unsigned int b = 0;
-                if (lane == 0) b = atomicAdd(head, warp_block);
-                b = __shfl_sync(FULL, b, 0);
-                if (b >= n_rays) exhausted = true;
-                else { blk_next = b; blk_end = min(b + warp_block, n_rays); }
-            }
-            if (blk_next < blk_end)
-            {
-                const unsigned int idx = blk_next + __popc(idle & lanes_below);
-                if (!active && idx < blk_end)
-                {
-                    const unsigned int e = B.queue[idx];
-                    const int slot = (int)(e >> 3), k = (int)(e & 7u);
-                    r = (size_t)k * n + slot;
-                    const float4 ro4 = B.ray_o[r], rd4 = B.ray_d[r];
-                    const int kind = __float_as_int(rd4.w);
-                    mode = kind == SIDE_SHADOW ? TRACE_SHADOW : (kind == SIDE_CLOSEST_LIGHT ? TRACE_CLOSEST : TRACE_ANY);
-                    const int tmode = spheres ? TRACE_CLOSEST : mode;
-                    trav8_init(T, V(ro4.x, ro4.y, ro4.z), V(rd4.x, rd4.y, rd4.z), ro4.w, tmode);
-                    W.ro[lane] = ro4;
-                    W.rd[lane] = make_float4(rd4.x, rd4.y, rd4.z, __int_as_float(tmode));
-                    W.best[lane] = kNoHit;
-                    active = true; pending = false;
-                }
-                blk_next = min(blk_next + (unsigned int)__popc(idle), blk_end);
-            }
-            __syncwarp();
-        }
-        const unsigned int m_active = __ballot_sync(FULL, active);
-        if (!m_active)
-        {
-            if (exhausted) break;
-            continue;
-        }
-        // (2) one node step for every lane that has one
-        if (active && !T.done)
-        {
-            trav8_node(S, T, K);
-            // the next node group can be fetched from the stack right away (its load overlaps the queue housekeeping below);
-            // the pending triangle group lives in T.tg / T.tvalid, which the pop does not touch
-            if (!T.done && !(T.ng.y & 0xff000000u)) trav8_pop(T, K);
-        }
-        // (3) hit triangles -> the warp's pair queue (draining first when it would overflow); the lane moves on
-        for (;;)
-        {
-            const unsigned int cnt = (active ? __popc(T.tg.y) : 0u);
-            if (!__any_sync(FULL, cnt != 0u)) break;            // node steps near the root hit no leaf child at all: no scan needed
-            unsigned int incl = cnt;
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1)
-            {
-                const unsigned int up = __shfl_up_sync(FULL, incl, o);
-                if (lane >= o) incl += up;
-            }
-            const unsigned int total = __shfl_sync(FULL, incl, 31);
-            if (!total) break;
-            const unsigned int room = kCoopQueue - qcount;
-            unsigned int at = incl - cnt;
-            if (cnt)
-            {
-                unsigned int bits = T.tg.y;
-                while (bits && at < room)
-                {
-                    const int b = __ffs((int)bits) - 1;
-                    bits &= bits - 1u;
-                    W.q[qcount + at] = ((unsigned int)lane << 27) | (unsigned int)trav8_tri_slot(T, b);
-                    at++;
-                }
-                T.tg.y = bits;
-                pending = true;
-            }
-            __syncwarp();
-            qcount += min(total, room);
-            if (total <= room) break;
-            coop_drain(S, W, lane, qcount, false, pending);
-        }
-        // (4) test queued pairs: whole batches of 32; everything when no lane has node work left or enough lanes wait
-        const unsigned int m_node = __ballot_sync(FULL, active && !T.done);
-        const unsigned int m_wait = __ballot_sync(FULL, active && T.done && pending);
-        const bool full = !m_node || __popc(m_wait) >= kRefillThreshold;
-        if (qcount >= 32u || (full && qcount))
-        {
-            coop_drain(S, W, lane, qcount, full, pending);
-            if (active)
-            {
-                const unsigned long long key = W.best[lane];
-                if (key != kNoHit)
-                {
-                    if (T.mode == TRACE_CLOSEST) T.tbest = __uint_as_float((unsigned int)(key >> 32));
-                    else T.done = true;           // occlusion established; the lane only waits for its queued pairs to leave
-                }
-            }
-        }
-        // (5) finished rays
-        if (active && T.done && !pending)
-        {
-            const unsigned long long key = W.best[lane];
-            Hit h;
-            bool found = key != kNoHit;
-            h.t = found ? __uint_as_float((unsigned int)(key >> 32)) : -1.0f;
-            h.prim = found ? (int)(unsigned int)key : -1;
-            h.slot = (found && T.mode == TRACE_CLOSEST) ? __ldg(S.slot_of_prim + h.prim) : -1;
-            h.u = h.v = -1.0f;
-            if (spheres)
-            {
-                const float4 ro4 = W.ro[lane], rd4 = W.rd[lane];
-                found = finish_with_spheres(S, V(ro4.x, ro4.y, ro4.z), V(rd4.x, rd4.y, rd4.z), ro4.w, mode, h);
-            }
-            wf_store_result(B, r, mode, found, h);
-            active = false;
-        }
-    }
+    coop_trace_queue(S, B, B.queue, src, W, K);
 }
 
 // ---- host driver ---------------------------------------------------------------------------------------------------------------

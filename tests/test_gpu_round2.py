@@ -136,11 +136,11 @@ def test_c5_full_scene_crops_against_oracle(rt):
 
 
 def test_deep_tree_exercises_the_stack_overflow_path(rt):
-    """A geometric chain of nested triangles gives the SAH builder a very deep tree (8-ary depth ~29, binary ~32): rays along
-    the chain push far more than the 10 stack entries the cooperative trace kernel keeps in shared memory, so its
+    """A geometric chain of nested triangles (sizes 1 .. 2e4) gives the SAH builder a deep tree (8-ary depth 14, binary 17): rays
+    along the chain push more than the 10 stack entries the cooperative trace kernel keeps in shared memory, so its
     local-memory overflow runs. Closest hits against numpy brute force; wavefront == megakernel bit for bit."""
     n = 2000
-    s = 1.02 ** np.arange(n)
+    s = 1.005 ** np.arange(n)
     tri = np.zeros((n, 9))
     tri[:, 0] = 3 * s; tri[:, 1] = -s; tri[:, 2] = -s
     tri[:, 3] = 3 * s; tri[:, 4] = 2 * s; tri[:, 5] = -s
@@ -149,7 +149,7 @@ def test_deep_tree_exercises_the_stack_overflow_path(rt):
     bvh = rt.BVH(tri)
     bvh.check()
     info = bvh.info()
-    assert info["wide_max_depth"] > 12, info
+    assert info["wide_max_depth"] > 10, info
     mats = np.array([[1, 0, 1, 1, 0, 0, 0, 1, 0, 1], [0, 0, 0, 1, .9, .8, .7, 1, 1.0, 0.3]], np.float32)
     sc = rt.Scene(tri, np.ones(n, np.int32), mats, np.zeros(0, np.int32), skysphere=rt.constant_env(1.0), bvh=bvh)
     rng = np.random.default_rng(3)
@@ -386,3 +386,64 @@ def test_linear_tiles_and_accumulating_untile(rt, golden_scenes, golden_cameras)
     sc.untile_accumulate_device(gathered.data_ptr(), padded, world, w, h, fb.data_ptr())
     torch.cuda.synchronize()
     assert np.array_equal(bits(fb.cpu().numpy()), bits(want))
+
+
+# ---- persistent integrator (csrc/persist.cu) ----------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("key,fixture", [("cornell", "render_cornell_c1.npz"), ("cornell", "render_cornell_env.npz"), ("mis", "render_mis_env.npz"),
+                                         ("area", "render_area_c1.npz"), ("cornell", "sphere_cornell.npz")])
+def test_persistent_integrator_equals_megakernel_bit_for_bit(rt, golden_scenes, golden_cameras, key, fixture):
+    """One launch per frame, every warp its own wavefront machine: the same device functions on the same per-pixel RNG streams as the
+    other two integrators -> identical framebuffers (NaN pixels included) and identical ray counts; and the reference's frame
+    within the stated tolerance."""
+    g = load_golden(fixture)
+    w, h, spp, b = int(g["w"]), int(g["h"]), int(g["spp"]), int(g["bounces"])
+    a = scene_arrays(golden_scenes, key)
+    if fixture == "sphere_cornell.npz":
+        n = len(a["tri9"])
+        mat_idx = np.concatenate([a["mat_idx"], np.array([len(g["mats10"]) - 1], np.int32)])
+        sph = [((float(g["spheres4"][0, 0]), float(g["spheres4"][0, 1]), float(g["spheres4"][0, 2])), float(g["spheres4"][0, 3]), n)]
+        sc = rt.Scene(a["tri9"], mat_idx, g["mats10"], a["emissive"], spheres=sph, skysphere=g["env"])
+    else:
+        sc = rt.Scene(a["tri9"], a["mat_idx"], a["mats10"], a["emissive"], skysphere=g["env"])
+    c = rt.Camera.from_array17(golden_cameras[{"cornell": "cornell", "mis": "mis", "area": "cornell"}[key]])
+    mega, st_m = sc.render(c, w, h, spp, b, integrator=rt.INTEGRATOR_MEGAKERNEL)
+    pers, st_p = sc.render(c, w, h, spp, b, integrator=rt.INTEGRATOR_PERSISTENT)
+    assert np.array_equal(bits(mega), bits(pers)), f"{(bits(mega) != bits(pers)).sum()} differing words"
+    assert st_m["rays"] == st_p["rays"] and st_p["gpu_launches"] <= 3
+    assert_radiance_parity(pers, g["image"], f"persistent {fixture}")
+    # a non-black incoming framebuffer, a frame that is not a multiple of the tile size, interleaved ranks
+    rng = np.random.default_rng(5)
+    w2, h2 = 100, 70
+    fb0 = (rng.random((h2, w2, 4)) * 0.2).astype(np.float32)
+    want = fb0.copy(); sc.render(c, w2, h2, 2, 4, framebuffer=want)
+    got = fb0.copy()
+    for rank in range(3):
+        sc.render(c, w2, h2, 2, 4, framebuffer=got, integrator=rt.INTEGRATOR_PERSISTENT, rank=rank, world=3)
+    assert np.array_equal(bits(want), bits(got))
+    zero, _ = sc.render(c, 40, 30, 0, 4, integrator=rt.INTEGRATOR_PERSISTENT)
+    zero_w, _ = sc.render(c, 40, 30, 0, 4)
+    assert np.array_equal(bits(zero), bits(zero_w))
+
+
+def test_persistent_integrator_c3_and_multi_device(rt, golden_cameras):
+    from sycl_ray_tracing_b200 import scenes
+    g = load_golden("render_c3small.npz")
+    c3 = scenes.c3_scene(roughness=float(g["roughness"]), nu=int(g["nu"]), nv=int(g["nv"]), sky_w=int(g["sky_w"]), sky_h=int(g["sky_h"]))
+    sc = scene_of(rt, c3)
+    w, h, spp, b = int(g["w"]), int(g["h"]), int(g["spp"]), int(g["bounces"])
+    wave, st_w = sc.render(c3["camera"], w, h, spp, b)
+    pers, st_p = sc.render(c3["camera"], w, h, spp, b, integrator=rt.INTEGRATOR_PERSISTENT)
+    assert np.array_equal(bits(wave), bits(pers)) and st_w["rays"] == st_p["rays"]
+    skip, st_s = sc.render(c3["camera"], w, h, spp, b, integrator=rt.INTEGRATOR_PERSISTENT, flags=rt.FLAG_SKIP_DEAD_RAYS)
+    assert np.array_equal(bits(wave), bits(skip)) and st_s["rays"] < st_p["rays"]
+    # a larger frame than the persistent grid has slots: slots are re-used as pixels finish
+    big_w, st_bw = sc.render(c3["camera"], 1280, 720, 2, 8)
+    big_p, st_bp = sc.render(c3["camera"], 1280, 720, 2, 8, integrator=rt.INTEGRATOR_PERSISTENT)
+    assert np.array_equal(bits(big_w), bits(big_p)) and st_bw["rays"] == st_bp["rays"]
+    multi = scene_of(rt, c3, devices=multi_devices(2))
+    m, st_mu = multi.render(c3["camera"], w, h, spp, b, integrator=rt.INTEGRATOR_PERSISTENT)
+    assert np.array_equal(bits(wave), bits(m)) and st_mu["rays"] == st_w["rays"]
+    # leaves of more than 3 triangles have no 8-ary layout: the persistent integrator must say so, not fall back
+    fat = scene_of(rt, c3, bvh=rt.BVH(c3["tri9"], max_leaf_size=8))
+    with pytest.raises(rt.B200RTError):
+        fat.render(c3["camera"], 32, 32, 1, 2, integrator=rt.INTEGRATOR_PERSISTENT)
