@@ -162,6 +162,10 @@ size_t b200rt_scene_device_bytes(const b200rt_scene* scene);
                                             Same per-texel probability lum/total in exact arithmetic, different draw -> texel map: the image agrees
                                             with the default statistically, not bit for bit. Needs b200rt_scene_build_env_alias(). */
 
+#define B200RT_FLAG_TIME_INLINE 512      /* wavefront: as B200RT_FLAG_TIME_KERNELS, but nothing is serialised — every launch is bracketed by events on its own
+                                            group stream while the tile groups overlap as in a normal frame, and the events are read after the frame.
+                                            stats: trace_ms / shade_ms = summed launch durations (they overlap: the sum may exceed the frame),
+                                            trace_union_ms = time during which at least one trace kernel was running */
 #define B200RT_FLAG_LINEAR_TILES 256     /* b200rt_render_tiles_device: the tile buffer receives each pixel's mean radiance (`final_color / spp`,
                                             render_kernel.cpp:167) instead of the tone-mapped value; b200rt_untile_accumulate_device then does
                                             `framebuffer += final; tone map` (:169-180) on the gathering device, so the incoming framebuffer is
@@ -185,6 +189,7 @@ typedef struct b200rt_stats
     /* only with B200RT_FLAG_TIME_KERNELS (wavefront integrator): CUDA-event time of every trace / shade launch, summed */
     double trace_ms, shade_ms;
     int trace_launches, shade_launches;
+    double trace_union_ms;          /* B200RT_FLAG_TIME_INLINE only */
 } b200rt_stats;
 
 void b200rt_default_render_options(b200rt_render_options* opts);
@@ -210,6 +215,22 @@ int b200rt_render_rgba8(b200rt_scene* scene, const float* camera17, int width, i
 int b200rt_render_region(b200rt_scene* scene, const float* camera17, int width, int height, int spp, int max_bounces,
                          int x0, int y0, int x1, int y1, float* out_rgba, const b200rt_render_options* opts_or_null,
                          b200rt_stats* stats_or_null);
+
+/* ---- progressive accumulation ----------------------------------------------------------------------------------------------------
+ * The reference's render() adds the frame's mean radiance to the Image and tone-maps it IN PLACE (render_kernel.cpp:167-180), so a
+ * second render() on the same Image is not an accumulation. An accumulator keeps every pixel's generator state and linear
+ * radiance sum on the device instead, so the samples of a frame can be streamed in chunks and looked at in between:
+ *   b200rt_accum_create   fixes scene, camera, frame size, the TOTAL spp (it seeds the per-pixel RNG: 31 + x*y*spp, :77) and max_bounces
+ *   b200rt_accum_add      renders the next n_samples samples of every pixel, continuing each pixel's RNG stream where it stopped
+ *   b200rt_accum_resolve  framebuffer_out = tone_map(framebuffer_in (NULL = Color::Black()) + sum / samples so far); any time, any number of times
+ * After spp_total samples — in any chunking — the resolved frame equals b200rt_render(spp_total) bit for bit.
+ * opts: integrator WAVEFRONT or PERSISTENT, flags as b200rt_render; rank/world must stay 0/1. Host pointers; blocking. */
+typedef struct b200rt_accum b200rt_accum;
+int b200rt_accum_create(b200rt_scene* scene, const float* camera17, int width, int height, int spp_total, int max_bounces, b200rt_accum** out);
+int b200rt_accum_add(b200rt_accum* acc, int n_samples, const b200rt_render_options* opts_or_null, b200rt_stats* stats_or_null);
+int b200rt_accum_samples(const b200rt_accum* acc);
+int b200rt_accum_resolve(b200rt_accum* acc, const float* framebuffer_rgba_in_or_null, float* framebuffer_rgba_out);
+void b200rt_accum_destroy(b200rt_accum* acc);
 
 /* Parity hook for xorshift32_generator (include/xorshift.h:10-31) as ray_trace_pixel seeds it (render_kernel.cpp:77-82):
  * *state_out = the generator state of pixel (x, y) after the 10 warm-up draws (seed 31 + x*y*spp in wrapping int arithmetic),

@@ -504,6 +504,39 @@ class Scene:
         return st.as_dict() if want_stats else None
 
 
+class Accumulator:
+    """Progressive rendering (b200rt_accum_*): the samples of a frame streamed in chunks, each pixel's RNG stream continued across
+    chunks; after spp_total samples resolve() equals Scene.render(spp_total) bit for bit."""
+
+    def __init__(self, scene: Scene, camera: Camera, w: int, h: int, spp_total: int, max_bounces: int):
+        self.scene, self.w, self.h = scene, w, h
+        hnd = C.c_void_p()
+        B.check(B.load_library().b200rt_accum_create(scene._h, B.fptr(camera.as_array17()), w, h, spp_total, max_bounces, C.byref(hnd)))
+        self._h = hnd
+
+    def __del__(self):
+        try:
+            if getattr(self, "_h", None):
+                B.load_library().b200rt_accum_destroy(self._h)
+                self._h = None
+        except Exception:
+            pass
+
+    def add(self, n_samples: int, integrator: int = B.INTEGRATOR_WAVEFRONT, flags: int = 0) -> dict:
+        st = B.Stats()
+        o = B.RenderOptions(integrator, flags, 0, 1)
+        B.check(B.load_library().b200rt_accum_add(self._h, n_samples, C.byref(o), C.byref(st)))
+        return st.as_dict()
+
+    def samples(self) -> int:
+        return int(B.load_library().b200rt_accum_samples(self._h))
+
+    def resolve(self, framebuffer_in: np.ndarray | None = None) -> np.ndarray:
+        out = np.empty((self.h, self.w, 4), np.float32)
+        B.check(B.load_library().b200rt_accum_resolve(self._h, B.fptr(framebuffer_in), B.fptr(out)))
+        return out
+
+
 # ---- RenderKernel (render_kernel.h:21-96) ----------------------------------------------------------------------------------------
 class RenderKernel:
     """Same 13-argument constructor, set_camera() and render() as the reference's RenderKernel. Buffers are borrowed

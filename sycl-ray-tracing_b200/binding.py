@@ -25,6 +25,7 @@ FLAG_ENV_ALIAS = 32
 FLAG_BVH8 = 64
 FLAG_TIME_KERNELS = 128
 FLAG_LINEAR_TILES = 256
+FLAG_TIME_INLINE = 512
 TILE_DIM = 16
 TILE_PIXELS = 256
 
@@ -53,7 +54,8 @@ class RenderOptions(C.Structure):
 class Stats(C.Structure):
     _fields_ = [("rays", C.c_ulonglong), ("samples", C.c_ulonglong), ("kernel_ms", C.c_double), ("total_ms", C.c_double),
                 ("gpu_launches", C.c_int), ("h2d_bytes", C.c_ulonglong), ("d2h_bytes", C.c_ulonglong),
-                ("trace_ms", C.c_double), ("shade_ms", C.c_double), ("trace_launches", C.c_int), ("shade_launches", C.c_int)]
+                ("trace_ms", C.c_double), ("shade_ms", C.c_double), ("trace_launches", C.c_int), ("shade_launches", C.c_int),
+                ("trace_union_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -66,6 +68,7 @@ EXPORTS = [
     "b200rt_scene_get_bvh_info", "b200rt_scene_device_bytes", "b200rt_default_render_options", "b200rt_render",
     "b200rt_trace_primary", "b200rt_trace_rays", "b200rt_tiles_for_rank", "b200rt_render_tiles_device",
     "b200rt_scene_create_multi", "b200rt_scene_device_count", "b200rt_scene_get_env_alias", "b200rt_scene_get_env_cdf",
+    "b200rt_accum_create", "b200rt_accum_add", "b200rt_accum_samples", "b200rt_accum_resolve", "b200rt_accum_destroy",
     "b200rt_render_rgba8", "b200rt_render_region", "b200rt_rng_stream", "b200rt_host_alloc", "b200rt_host_free", "b200rt_untile_accumulate_device",
     "b200rt_untile_device", "b200rt_trace_primary_device", "b200rt_trace_rays_device", "b200rt_quantise_rgba8", "b200rt_quantise_rgba8_device", "b200rt_last_error", "b200rt_version",
 ]
@@ -101,6 +104,12 @@ def load_library(path: str = LIB_PATH) -> C.CDLL:
     L.b200rt_scene_get_env_cdf.argtypes = [VP, FP]
     L.b200rt_render_rgba8.argtypes = [VP, FP, I, I, I, I, FP, I, C.POINTER(C.c_ubyte), C.POINTER(RenderOptions), C.POINTER(Stats)]
     L.b200rt_render_region.argtypes = [VP, FP, I, I, I, I, I, I, I, I, FP, C.POINTER(RenderOptions), C.POINTER(Stats)]
+    L.b200rt_accum_create.argtypes = [VP, FP, I, I, I, I, C.POINTER(VP)]
+    L.b200rt_accum_add.argtypes = [VP, I, C.POINTER(RenderOptions), C.POINTER(Stats)]
+    L.b200rt_accum_samples.argtypes = [VP]
+    L.b200rt_accum_resolve.argtypes = [VP, FP, FP]
+    L.b200rt_accum_destroy.argtypes = [VP]
+    L.b200rt_accum_destroy.restype = None
     L.b200rt_rng_stream.argtypes = [I, I, I, I, C.POINTER(C.c_uint32), FP]
     L.b200rt_host_alloc.argtypes = [C.c_size_t, C.POINTER(VP)]
     L.b200rt_host_free.argtypes = [VP]

@@ -47,6 +47,8 @@ struct b200rt_scene
     void* bvh_window = nullptr; size_t bvh_window_bytes = 0;   // 8-ary nodes + triangles, kept resident in L2 (see pin_bvh_in_l2)
     bool l2_pinned = false, l2_window_set = false;
     double kernel_times[4] = {};          // B200RT_FLAG_TIME_KERNELS: trace ms, shade ms, trace launches, shade launches of the last render
+    WfTimeline timeline;                  // B200RT_FLAG_TIME_INLINE: per-launch events of the last wavefront frame
+    bool timeline_valid = false;
     // persistent integrator state (allocated on first use)
     WfBuffers pw{}; int pw_cap = 0, pw_grid = 0; std::vector<void*> pw_allocs;
     // multi-GPU scenes (b200rt_scene_create_multi): this scene is rank 0; replicas[i] is rank i + 1 on another device, owned here
@@ -145,6 +147,7 @@ int make_params(const b200rt_scene* s, const float* camera17, int w, int h, int 
     P.n_rank_tiles = b200rt_tiles_for_rank(w, h, d.rank, d.world);
     P.flags = d.flags;
     P.rx0 = P.ry0 = P.rw = P.rh = 0;
+    P.sample_begin = 0; P.sample_end = spp; P.acc_rng = nullptr; P.acc_sum = nullptr;
     return B200RT_OK;
 }
 
@@ -409,6 +412,7 @@ int pin_bvh_in_l2(b200rt_scene* s, cudaStream_t extra)
 int run_integrator(b200rt_scene* s, const RenderParams& P, int integrator, const float4* fb_in, float4* out_tiles, cudaStream_t st, int* launches)
 {
     s->kernel_times[0] = s->kernel_times[1] = s->kernel_times[2] = s->kernel_times[3] = 0.0;
+    s->timeline_valid = false;
     SceneDev dev = s->dev;
     if (P.flags & B200RT_FLAG_ENV_ALIAS)
     {
@@ -422,7 +426,8 @@ int run_integrator(b200rt_scene* s, const RenderParams& P, int integrator, const
         if (rc) return rc;
         if (!s->l2_window_set) { if ((rc = pin_bvh_in_l2(s, nullptr))) return rc; s->l2_window_set = true; }
         unsigned int unfinished = 0;
-        CU(run_wavefront(dev, P, s->wf, s->wf_groups, fb_in, out_tiles, st, s->fork_event, launches, s->kernel_times, &unfinished));
+        s->timeline_valid = (P.flags & B200RT_FLAG_TIME_INLINE) && !(P.flags & B200RT_FLAG_TIME_KERNELS);
+        CU(run_wavefront(dev, P, s->wf, s->wf_groups, fb_in, out_tiles, st, s->fork_event, launches, s->kernel_times, &unfinished, &s->timeline));
         if (unfinished) return fail(B200RT_ERR_CUDA, "wavefront integrator: %u pixels unfinished after spp * (max_bounces + 1) iterations", unfinished);
         CU(wavefront_sum_rays(s->wf, s->wf_groups, s->d_rays, st));
         *launches += 1;
@@ -440,6 +445,23 @@ int run_integrator(b200rt_scene* s, const RenderParams& P, int integrator, const
     }
     CU(launch_megakernel(dev, P, fb_in, out_tiles, s->d_work, s->d_rays, st));
     *launches = 1;
+    return B200RT_OK;
+}
+
+// per-kernel timing fields of the stats struct (the frame must have completed)
+int fill_kernel_times(b200rt_scene* s, b200rt_stats* stats)
+{
+    stats->trace_ms = s->kernel_times[0]; stats->shade_ms = s->kernel_times[1];
+    stats->trace_launches = (int)s->kernel_times[2]; stats->shade_launches = (int)s->kernel_times[3];
+    stats->trace_union_ms = 0.0;
+    if (s->timeline_valid)
+    {
+        WfTimelineSummary t;
+        CU(wavefront_timeline_summary(s->timeline, &t));
+        stats->trace_ms = t.trace_ms; stats->shade_ms = t.shade_ms;
+        stats->trace_launches = t.trace_launches; stats->shade_launches = t.shade_launches;
+        stats->trace_union_ms = t.trace_union_ms;
+    }
     return B200RT_OK;
 }
 
@@ -904,6 +926,7 @@ void b200rt_scene_destroy(b200rt_scene* s)
     if (s->d_gather) cudaFree(s->d_gather);
     if (s->d_rgba8) cudaFree(s->d_rgba8);
     if (s->mg_stream) cudaStreamDestroy(s->mg_stream);
+    s->timeline.destroy();
     for (int i = 0; i < 2; i++) { if (s->h_stage[i]) cudaFreeHost(s->h_stage[i]); if (s->stage_ev[i]) cudaEventDestroy(s->stage_ev[i]); }
     for (void* p : s->allocs) cudaFree(p);
     if (s->d_mats) cudaFree(s->d_mats);
@@ -980,8 +1003,7 @@ int b200rt_render_tiles_device(b200rt_scene* s, const float* camera17, int w, in
         std::memset(stats, 0, sizeof(*stats));
         CU(cudaMemcpy(&stats->rays, s->d_rays, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
         stats->kernel_ms = ms; stats->total_ms = ms; stats->gpu_launches = launches;
-        stats->trace_ms = s->kernel_times[0]; stats->shade_ms = s->kernel_times[1];
-        stats->trace_launches = (int)s->kernel_times[2]; stats->shade_launches = (int)s->kernel_times[3];
+        if ((rc = fill_kernel_times(s, stats))) return rc;
         // pixels of this rank that lie inside the frame
         unsigned long long px = 0;
         for (int k = 0; k < P.n_rank_tiles; k++)
@@ -1163,8 +1185,7 @@ int render_frame(b200rt_scene* s, const float* camera17, int w, int h, int spp, 
         else stats->samples = (unsigned long long)image_px * (unsigned long long)spp;
         stats->rays = rays;
         stats->kernel_ms = kernel_ms;
-        stats->trace_ms = s->kernel_times[0]; stats->shade_ms = s->kernel_times[1];
-        stats->trace_launches = (int)s->kernel_times[2]; stats->shade_launches = (int)s->kernel_times[3];
+        if ((rc = fill_kernel_times(s, stats))) return rc;
         stats->gpu_launches = launches;
         stats->h2d_bytes = h2d; stats->d2h_bytes = d2h;
         stats->total_ms = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
@@ -1230,6 +1251,104 @@ int b200rt_render_region(b200rt_scene* s, const float* camera17, int w, int h, i
         stats->h2d_bytes = 17 * sizeof(float); stats->d2h_bytes = px * sizeof(float4);
     }
     return B200RT_OK;
+}
+
+struct b200rt_accum
+{
+    b200rt_scene* scene = nullptr;
+    float camera17[17] = {};
+    int w = 0, h = 0, spp_total = 0, bounces = 0, done = 0;
+    size_t n_slots = 0;                  // tile-major pixel slots of the whole frame
+    uint32_t* d_rng = nullptr; float4* d_sum = nullptr; float4* d_tiles = nullptr;
+};
+
+int b200rt_accum_create(b200rt_scene* s, const float* camera17, int w, int h, int spp_total, int bounces, b200rt_accum** out)
+{
+    if (!out) return fail(B200RT_ERR_ARG, "out must not be NULL");
+    *out = nullptr;
+    if (!s || !camera17) return fail(B200RT_ERR_ARG, "scene and camera must not be NULL");
+    if (w <= 0 || h <= 0 || spp_total <= 0 || bounces <= 0) return fail(B200RT_ERR_ARG, "bad accumulator arguments");
+    if (!s->replicas.empty()) return fail(B200RT_ERR_ARG, "accumulators run on single-device scenes");
+    ON_DEVICE(s->device);
+    b200rt_accum* a = new (std::nothrow) b200rt_accum;
+    if (!a) return fail(B200RT_ERR_ALLOC, "out of host memory");
+    a->scene = s; a->w = w; a->h = h; a->spp_total = spp_total; a->bounces = bounces;
+    std::memcpy(a->camera17, camera17, sizeof(a->camera17));
+    a->n_slots = (size_t)b200rt_tiles_for_rank(w, h, 0, 1) * kTilePixels;
+    cudaError_t e = cudaMalloc(&a->d_rng, a->n_slots * sizeof(uint32_t));
+    if (e == cudaSuccess) e = cudaMalloc(&a->d_sum, a->n_slots * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMalloc(&a->d_tiles, a->n_slots * sizeof(float4));
+    if (e == cudaSuccess) e = cudaMemset(a->d_tiles, 0, a->n_slots * sizeof(float4));
+    if (e != cudaSuccess) { b200rt_accum_destroy(a); return fail(B200RT_ERR_CUDA, "accumulator allocation: %s", cudaGetErrorString(e)); }
+    *out = a;
+    return B200RT_OK;
+}
+
+int b200rt_accum_samples(const b200rt_accum* a) { return a ? a->done : 0; }
+
+int b200rt_accum_add(b200rt_accum* a, int n_samples, const b200rt_render_options* opts, b200rt_stats* stats)
+{
+    if (!a) return fail(B200RT_ERR_ARG, "NULL accumulator");
+    if (n_samples <= 0 || a->done + n_samples > a->spp_total) return fail(B200RT_ERR_ARG, "%d more samples after %d of %d", n_samples, a->done, a->spp_total);
+    b200rt_scene* s = a->scene;
+    RenderParams P;
+    int rc = make_params(s, a->camera17, a->w, a->h, a->spp_total, a->bounces, opts, P);
+    if (rc) return rc;
+    if (P.world != 1) return fail(B200RT_ERR_ARG, "accumulators render whole frames (rank/world must stay 0/1)");
+    const int integrator = opts ? opts->integrator : B200RT_INTEGRATOR_WAVEFRONT;
+    if (integrator != B200RT_INTEGRATOR_WAVEFRONT && integrator != B200RT_INTEGRATOR_PERSISTENT)
+        return fail(B200RT_ERR_ARG, "accumulators run on the wavefront or the persistent integrator");
+    ON_DEVICE(s->device);
+    if ((rc = ensure_scratch(s, 0, 0, 0))) return rc;
+    P.flags |= B200RT_FLAG_LINEAR_TILES;
+    P.sample_begin = a->done; P.sample_end = a->done + n_samples;
+    P.acc_rng = a->d_rng; P.acc_sum = a->d_sum;
+    cudaStream_t st = 0;
+    CU(cudaMemsetAsync(s->d_rays, 0, sizeof(unsigned long long), st));
+    CU(cudaEventRecord(s->ev0, st));
+    int launches = 0;
+    if ((rc = run_integrator(s, P, integrator, nullptr, a->d_tiles, st, &launches))) return rc;
+    CU(cudaEventRecord(s->ev1, st));
+    CU(cudaStreamSynchronize(st));
+    a->done += n_samples;
+    if (stats)
+    {
+        std::memset(stats, 0, sizeof(*stats));
+        float ms = 0.0f;
+        CU(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+        CU(cudaMemcpy(&stats->rays, s->d_rays, sizeof(unsigned long long), cudaMemcpyDeviceToHost));
+        stats->samples = (unsigned long long)a->w * a->h * (unsigned long long)n_samples;
+        stats->kernel_ms = ms; stats->total_ms = ms; stats->gpu_launches = launches;
+        if ((rc = fill_kernel_times(s, stats))) return rc;
+    }
+    return B200RT_OK;
+}
+
+int b200rt_accum_resolve(b200rt_accum* a, const float* fb_in, float* fb_out)
+{
+    if (!a || !fb_out) return fail(B200RT_ERR_ARG, "NULL argument");
+    if (a->done <= 0) return fail(B200RT_ERR_ARG, "nothing accumulated yet");
+    b200rt_scene* s = a->scene;
+    ON_DEVICE(s->device);
+    const size_t image_px = (size_t)a->w * a->h;
+    int rc = ensure_scratch(s, 0, image_px, 0);
+    if (rc) return rc;
+    cudaStream_t st = 0;
+    if (fb_in) { if ((rc = copy_to_device(s, s->d_image, fb_in, image_px * sizeof(float4), st))) return rc; }
+    else CU(launch_fill_f4(s->d_image, image_px, make_float4(0.0f, 0.0f, 0.0f, 1.0f), st));
+    CU(launch_untile_accumulate(a->d_tiles, (int)(a->n_slots / kTilePixels), 1, a->w, a->h, s->d_image, st));
+    return copy_to_host(s, fb_out, s->d_image, image_px * sizeof(float4), st);
+}
+
+void b200rt_accum_destroy(b200rt_accum* a)
+{
+    if (!a) return;
+    if (a->scene)
+    {
+        DeviceScope scope(a->scene->device);
+        cudaFree(a->d_rng); cudaFree(a->d_sum); cudaFree(a->d_tiles);
+    }
+    delete a;
 }
 
 int b200rt_rng_stream(int x, int y, int spp, int n, uint32_t* state_out, float* floats_out)

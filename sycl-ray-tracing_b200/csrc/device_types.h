@@ -66,6 +66,13 @@ struct RenderParams
     // region mode (b200rt_render_region, megakernel only): slots are the pixels of the rectangle [rx0, rx0 + rw) x [ry0, ry0 + rh)
     // of the frame in row-major order instead of this rank's tiles; rw == 0 = off
     int rx0, ry0, rw, rh;
+    // progressive accumulation (b200rt_accum_*, wavefront / persistent integrators): this launch renders samples
+    // [sample_begin, sample_end) of every pixel. spp stays the TOTAL sample count of the frame: it seeds the per-pixel RNG
+    // (31 + x*y*spp, render_kernel.cpp:77). acc_rng / acc_sum (indexed like the tile buffer) carry each pixel's generator state
+    // and radiance sum from one launch to the next; null = an ordinary one-shot frame (sample_begin = 0, sample_end = spp).
+    int sample_begin, sample_end;
+    uint32_t* acc_rng;
+    float4* acc_sum;
 };
 
 // wavefront integrator state: one slot per pixel of this rank's tile-major buffer (SoA, HBM resident)

@@ -1,5 +1,7 @@
 // Launchers of the sm_100a kernels (kernels.cu). Host code only sees these.
 #pragma once
+#include <vector>
+
 #include <cuda_runtime.h>
 
 #include "../../include/b200rt.h"
@@ -42,12 +44,35 @@ cudaError_t launch_env_cdf_serial(const float* lum, size_t n, float* cdf, cudaSt
 cudaError_t launch_env_row_cdf(const float* cdf, int w, int h, float* row, cudaStream_t stream);
 cudaError_t build_env_alias_device(const float* lum, size_t n, float2* table, double* total_host, cudaStream_t stream);
 
+// B200RT_FLAG_TIME_INLINE: every trace / shade launch of a frame bracketed by CUDA events on its own group stream, nothing
+// serialised or synchronised while the frame runs; read back after the frame has finished (wavefront_timeline_summary)
+struct WfTimeline
+{
+    struct Launch { int group; size_t e0, e1, e2; };      // events: trace start, trace end = shade start, shade end
+    std::vector<cudaEvent_t> pool;
+    size_t used = 0;
+    std::vector<Launch> launches;
+    cudaEvent_t origin = nullptr;                         // recorded on the caller's stream at the fork
+    cudaEvent_t take();
+    void reset() { used = 0; launches.clear(); }
+    void destroy();
+};
+// sums (ms) and launch counts of the recorded frame, and the length of the union of the trace kernels' intervals: the time during
+// which at least one trace kernel was running. The frame must have completed (stream synchronised).
+struct WfTimelineSummary { double trace_ms, shade_ms, trace_union_ms; int trace_launches, shade_launches; };
+cudaError_t wavefront_timeline_summary(const WfTimeline& tl, WfTimelineSummary* out);
+
 // wavefront integrator (wavefront.cu): runs the whole frame for this rank's tiles as n_groups independent interleaved
 // tile groups, each on its own stream; `stream` is forked from and joined back into
 cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGroup* groups, int n_groups, const float4* fb_in_rowmajor,
                           float4* out_tiles, cudaStream_t stream, cudaEvent_t fork_event, int* launches_out, double* kernel_times4 = nullptr,
-                          unsigned int* unfinished_out = nullptr);
+                          unsigned int* unfinished_out = nullptr, WfTimeline* timeline = nullptr);
 cudaError_t wavefront_sum_rays(const WfGroup* groups, int n_groups, unsigned long long* total, cudaStream_t stream);
+
+// barrier-free tail of a pass-synchronous frame (persist.cu): finishes the group's unfinished slots in one launch
+cudaError_t launch_wavefront_tail(const SceneDev& S, const RenderParams& P, const WfBuffers& B, int max_ctas, const float4* fb_in_rowmajor,
+                                  float4* out_tiles, cudaStream_t stream);
+int wavefront_tail_max_ctas();
 
 // persistent integrator (persist.cu): one launch per frame, every warp its own wavefront machine
 int persistent_grid();

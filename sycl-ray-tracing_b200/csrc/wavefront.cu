@@ -17,6 +17,8 @@
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
+#include <utility>
+#include <vector>
 
 #include "wf_device.cuh"
 
@@ -25,11 +27,6 @@ namespace b200rt {
 #ifndef WF_SHADE_MIN_BLOCKS
 #define WF_SHADE_MIN_BLOCKS 4
 #endif
-
-__device__ __forceinline__ size_t wf_out_index(const WfBuffers& B, int slot)
-{
-    return ((size_t)(slot >> 8) * B.tile_stride + B.tile_offset) * kTilePixels + (slot & 255);
-}
 
 __global__ void __launch_bounds__(256) wf_init(SceneDev S, RenderParams P, WfBuffers B, const float4* __restrict__ fb_in_rowmajor,
                                                float4* __restrict__ out_tiles)
@@ -41,7 +38,7 @@ __global__ void __launch_bounds__(256) wf_init(SceneDev S, RenderParams P, WfBuf
         int x, y;
         const bool inside = wf_slot_pixel(P, slot, x, y);
         if (!inside) { out_tiles[wf_out_index(B, slot)] = make_float4(0.0f, 0.0f, 0.0f, 0.0f); B.flags[slot] = WF_DONE; }
-        else if (P.spp <= 0 || P.max_bounces <= 0)
+        else if (P.sample_end <= P.sample_begin || P.max_bounces <= 0)
         {
             const float n = (float)P.spp;
             out_tiles[wf_out_index(B, slot)] = pixel_output(P.flags, fb_in_rowmajor, (size_t)y * P.cam.w + x, CO(0.0f / n, 0.0f / n, 0.0f / n));
@@ -49,7 +46,7 @@ __global__ void __launch_bounds__(256) wf_init(SceneDev S, RenderParams P, WfBuf
         }
         else
         {
-            wf_begin_pixel(P, B, slot, x, y);
+            wf_begin_pixel(P, B, slot, x, y, wf_out_index(B, slot));
             q_path = true;
         }
     }
@@ -259,7 +256,7 @@ __global__ void __launch_bounds__(32 * kCoopMaxWarps, WF_COOP_MIN_BLOCKS) wf_tra
 // pass bounds that pass) the other groups' kernels fill the machine. Groups never exchange data.
 cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGroup* groups, int n_groups, const float4* fb_in_rowmajor,
                           float4* out_tiles, cudaStream_t stream, cudaEvent_t fork_event, int* launches_out, double* kernel_times4,
-                          unsigned int* unfinished_out)
+                          unsigned int* unfinished_out, WfTimeline* timeline)
 {
     const int n_sm = current_sm_count();
     int launches = 0;
@@ -285,6 +282,13 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
     const int trace_grid = n_sm * std::max(1, (per_sm * grid_pct + 50) / 100);
     static const bool timing_env = getenv("B200RT_WF_TIMING") != nullptr;  // diagnostics: per-kernel times on stderr (serialises the groups)
     const bool timing = timing_env || (P.flags & B200RT_FLAG_TIME_KERNELS);
+    WfTimeline* const tln = (!timing && (P.flags & B200RT_FLAG_TIME_INLINE)) ? timeline : nullptr;
+    if (tln)
+    {
+        tln->reset();
+        if (!tln->origin) cudaEventCreate(&tln->origin);
+        cudaEventRecord(tln->origin, stream);
+    }
     int n_trace = 0, n_shade = 0;
     cudaError_t e;
 
@@ -293,7 +297,14 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
     if ((e = cudaEventRecord(fork_event, stream)) != cudaSuccess) return e;
     cudaError_t err = cudaSuccess;
 #define WF_TRY(expr) do { if (err == cudaSuccess) { const cudaError_t e__ = (expr); if (e__ != cudaSuccess) err = e__; } } while (0)
-    struct GroupRun { RenderParams P; int parity; bool finished, forked; int slot_grid; long long it, poll_it; bool poll_pending; };
+    struct GroupRun { RenderParams P; int parity; bool finished, forked; int slot_grid; long long it, poll_it; bool poll_pending; unsigned int tail_below; };
+    // barrier-free tail (persist.cu): when a group has at most B200RT_WF_TAIL_PCT % of its pixels (and at most B200RT_WF_TAIL_CAP) left,
+    // or is smaller than B200RT_WF_TAIL_MIN pixels to begin with. 8-ary layout, default trace kernel only; not in the per-kernel timing modes.
+    static const int tail_pct = []() { const char* e = getenv("B200RT_WF_TAIL_PCT"); int v = e ? atoi(e) : 40; return v < 0 ? 0 : (v > 100 ? 100 : v); }();
+    static const long long tail_cap = []() { const char* e = getenv("B200RT_WF_TAIL_CAP"); return e ? atoll(e) : 100000ll; }();
+    static const int tail_min = []() { const char* e = getenv("B200RT_WF_TAIL_MIN"); return e ? atoi(e) : 16384; }();
+    const bool tail_ok = coop && tail_pct > 0 && !timing && !(P.flags & B200RT_FLAG_TIME_INLINE);
+    const int tail_ctas = tail_ok ? std::max(1, wavefront_tail_max_ctas() / n_groups) : 0;
     GroupRun run[kMaxWfGroups];
     for (int g = 0; g < n_groups; g++)
     {
@@ -316,8 +327,16 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
         if (R.finished) continue;
         wf_init<<<R.slot_grid, 256, 0, G.stream>>>(S, R.P, G.buf, fb_in_rowmajor, out_tiles);
         launches++;
+        R.tail_below = (unsigned int)std::min<long long>(tail_cap, (long long)G.buf.n_slots * tail_pct / 100);
+        if (tail_ok && G.buf.n_slots <= tail_min)
+        {
+            // a group this small is latency-bound from its first pass on: barrier-free from the start
+            WF_TRY(launch_wavefront_tail(S, R.P, G.buf, tail_ctas, fb_in_rowmajor, out_tiles, G.stream));
+            launches += 2;
+            R.finished = true;
+        }
     }
-    const long long max_iters = (long long)P.spp * (P.max_bounces + 1) + 2;
+    const long long max_iters = (long long)(P.sample_end - P.sample_begin) * (P.max_bounces + 1) + 2;
     cudaEvent_t tev[3] = { nullptr, nullptr, nullptr };
     double t_trace = 0.0, t_shade = 0.0;
     if (timing) for (int i = 0; i < 3; i++) cudaEventCreate(&tev[i]);
@@ -336,6 +355,14 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
             {
                 R.poll_pending = false;
                 if (*G.host_active == 0) { R.finished = true; remaining--; continue; }
+                if (tail_ok && *G.host_active <= R.tail_below)
+                {
+                    // few pixels left: no more passes; one barrier-free launch finishes them (persist.cu), behind the passes already queued
+                    WF_TRY(launch_wavefront_tail(S, R.P, G.buf, tail_ctas, fb_in_rowmajor, out_tiles, G.stream));
+                    launches += 2;
+                    R.finished = true; remaining--;
+                    continue;
+                }
             }
             // bounded run-ahead: at most kRunAhead iterations queued behind an unanswered poll (a finished group would
             // otherwise leave a long train of empty launches behind)
@@ -351,11 +378,15 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
                 R.finished = true; remaining--;
                 continue;
             }
+            WfTimeline::Launch tll = { g, 0, 0, 0 };
             if (timing) cudaEventRecord(tev[0], G.stream);
+            if (tln) { tll.e0 = tln->used; cudaEventRecord(tln->take(), G.stream); }
             trace_kernel<<<trace_grid, tb, 0, G.stream>>>(S, G.buf, R.parity);
             if (timing) cudaEventRecord(tev[1], G.stream);
+            if (tln) { tll.e1 = tln->used; cudaEventRecord(tln->take(), G.stream); }
             R.parity ^= 1;
             wf_shade<<<R.slot_grid, 256, 0, G.stream>>>(S, R.P, G.buf, fb_in_rowmajor, out_tiles, R.parity);
+            if (tln) { tll.e2 = tln->used; cudaEventRecord(tln->take(), G.stream); tln->launches.push_back(tll); }
             launches += 2;
             WF_TRY(cudaGetLastError());
             if (timing)
@@ -398,6 +429,52 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
     if (unfinished_out) *unfinished_out = unfinished;
     if (err != cudaSuccess) return err;
     return cudaGetLastError();
+}
+
+cudaEvent_t WfTimeline::take()
+{
+    if (used == pool.size())
+    {
+        cudaEvent_t e = nullptr;
+        cudaEventCreate(&e);
+        pool.push_back(e);
+    }
+    return pool[used++];
+}
+
+void WfTimeline::destroy()
+{
+    for (cudaEvent_t e : pool) if (e) cudaEventDestroy(e);
+    pool.clear(); used = 0; launches.clear();
+    if (origin) { cudaEventDestroy(origin); origin = nullptr; }
+}
+
+cudaError_t wavefront_timeline_summary(const WfTimeline& tl, WfTimelineSummary* out)
+{
+    WfTimelineSummary s = { 0.0, 0.0, 0.0, 0, 0 };
+    std::vector<std::pair<float, float>> iv;
+    iv.reserve(tl.launches.size());
+    for (const WfTimeline::Launch& L : tl.launches)
+    {
+        float t0 = 0.0f, a = 0.0f, b = 0.0f;
+        cudaError_t e = cudaEventElapsedTime(&t0, tl.origin, tl.pool[L.e0]);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&a, tl.pool[L.e0], tl.pool[L.e1]);
+        if (e == cudaSuccess) e = cudaEventElapsedTime(&b, tl.pool[L.e1], tl.pool[L.e2]);
+        if (e != cudaSuccess) return e;
+        s.trace_ms += a; s.shade_ms += b; s.trace_launches++; s.shade_launches++;
+        iv.emplace_back(t0, t0 + a);
+    }
+    std::sort(iv.begin(), iv.end());
+    float cur0 = 0.0f, cur1 = -1.0f;
+    for (const auto& p : iv)
+    {
+        if (cur1 < cur0) { cur0 = p.first; cur1 = p.second; }
+        else if (p.first <= cur1) cur1 = std::max(cur1, p.second);
+        else { s.trace_union_ms += cur1 - cur0; cur0 = p.first; cur1 = p.second; }
+    }
+    if (cur1 >= cur0) s.trace_union_ms += cur1 - cur0;
+    *out = s;
+    return cudaSuccess;
 }
 
 // sums the groups' ray counters into *total (one tiny launch on the caller's stream, after the join)

@@ -38,6 +38,12 @@ __device__ __forceinline__ void wf_start_sample(const RenderParams& P, const WfB
     wf_store_ray(B, 4, slot, o, d, 0.0f, SIDE_CLOSEST_LIGHT);
 }
 
+// where slot `slot` of a tile group writes its pixel: group g of G owns every G-th tile of the rank's tile-major buffer
+__device__ __forceinline__ size_t wf_out_index(const WfBuffers& B, int slot)
+{
+    return ((size_t)(slot >> 8) * B.tile_stride + B.tile_offset) * kTilePixels + (slot & 255);
+}
+
 // pixel index of this rank's tile-major buffer (8x4 patches inside 16x16 tiles) -> pixel; false outside the frame
 __device__ __forceinline__ bool wf_slot_pixel(const RenderParams& P, int slot, int& x, int& y)
 {
@@ -61,15 +67,18 @@ __device__ __forceinline__ v3 wf_sphere_normal(const SceneDev& S, int prim, v3 p
     return V(0.0f, 0.0f, 0.0f);
 }
 
-// starts pixel (x, y) in state slot `slot`: RNG seed + warm-up (:77-82), first camera ray into ray slot 4
-__device__ __forceinline__ void wf_begin_pixel(const RenderParams& P, const WfBuffers& B, int slot, int x, int y)
+// starts pixel (x, y) in state slot `slot`: RNG seed + warm-up (:77-82) — or, when a progressive accumulation continues, the
+// generator state and radiance sum the pixel's previous samples left in acc_rng / acc_sum[out_index] — and the first camera
+// ray into ray slot 4
+__device__ __forceinline__ void wf_begin_pixel(const RenderParams& P, const WfBuffers& B, int slot, int x, int y, size_t out_index)
 {
-    uint32_t rng = pixel_rng(x, y, P.spp);
+    const bool resume = P.acc_rng != nullptr && P.sample_begin > 0;
+    uint32_t rng = resume ? P.acc_rng[out_index] : pixel_rng(x, y, P.spp);
     wf_start_sample(P, B, slot, x, y, rng);
     B.rng[slot] = rng;
-    B.sample[slot] = 0;
+    B.sample[slot] = P.sample_begin;
     B.bounce[slot] = 0;
-    B.final_c[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    B.final_c[slot] = resume ? P.acc_sum[out_index] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     B.sample_c[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     B.thr[slot] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
     B.flags[slot] = WF_ALIVE;
@@ -209,7 +218,7 @@ __device__ __forceinline__ ShadeOut wf_shade_slot(const SceneDev& S, const Rende
         float4 f4 = B.final_c[slot];
         col final_color = CO(f4.x, f4.y, f4.z) + sample_color;
         sample++;
-        if (sample < P.spp)
+        if (sample < P.sample_end)
         {
             B.final_c[slot] = make_float4(final_color.r, final_color.g, final_color.b, 0.0f);
             wf_start_sample(P, B, slot, x, y, rng);
@@ -221,7 +230,8 @@ __device__ __forceinline__ ShadeOut wf_shade_slot(const SceneDev& S, const Rende
         }
         else
         {
-            const float nspp = (float)P.spp;
+            if (P.acc_rng) { P.acc_rng[out_index] = rng; P.acc_sum[out_index] = make_float4(final_color.r, final_color.g, final_color.b, 0.0f); }
+            const float nspp = (float)P.sample_end;          // == spp for a one-shot frame and for the last chunk of an accumulation
             const col mean = CO(final_color.r / nspp, final_color.g / nspp, final_color.b / nspp);
             out_tiles[out_index] = pixel_output(P.flags, fb_in_rowmajor, (size_t)y * P.cam.w + x, mean);
             flags = WF_DONE;

@@ -78,3 +78,15 @@ def test_reference_main_cpp_drives_the_b200_path(rt, tmp_path):
     assert png[..., :3].std() > 10, "the frame must not be blank"
     for name in ("RT_output_denoised_1.png", "RT_output_denoised_0.75.png", "RT_output_denoised_0.5.png"):
         assert os.path.exists(tmp_path / name)          # main.cpp:118-125 ran to the end
+    # the same unmodified main.cpp on several ranks behind the boundary (b200rt_scene_create_multi): B200RT_GPUS=2 when the box has two
+    # GPUs, and B200RT_DEVICE_LIST=0,0,0 (three ranks sharing the one device) everywhere. The PNG must be byte-identical.
+    import torch
+    variants = [{"B200RT_DEVICE_LIST": "0,0,0"}] + ([{"B200RT_GPUS": "2"}] if torch.cuda.device_count() >= 2 else [])
+    for extra in variants:
+        out = tmp_path / ("multi_" + "_".join(extra.values()).replace(",", ""))
+        out.mkdir()
+        r2 = subprocess.run([BIN, f"--sky={tmp_path / 'sky.hdr'}", f"--w={w}", f"--h={h}", f"--samples={spp}", f"--bounces={bounces}", base + ".obj"],
+                            cwd=out, capture_output=True, text=True, timeout=600, env=dict(os.environ, **extra))
+        assert r2.returncode == 0, r2.stdout[-2000:] + r2.stderr[-2000:]
+        png2 = np.asarray(PILImage.open(out / "RT_output.png").convert("RGBA"))
+        assert np.array_equal(png, png2), extra

@@ -142,9 +142,9 @@ def test_deep_tree_exercises_the_stack_overflow_path(rt):
     n = 2000
     s = 1.005 ** np.arange(n)
     tri = np.zeros((n, 9))
-    tri[:, 0] = 3 * s; tri[:, 1] = -s; tri[:, 2] = -s
-    tri[:, 3] = 3 * s; tri[:, 4] = 2 * s; tri[:, 5] = -s
-    tri[:, 6] = 3 * s; tri[:, 7] = -s; tri[:, 8] = 2 * s
+    tri[:, 0] = 3 * s; tri[:, 1] = -s; tri[:, 2] = -s           # wound so that the geometric normal faces -x, towards the camera below
+    tri[:, 3] = 3 * s; tri[:, 4] = -s; tri[:, 5] = 2 * s
+    tri[:, 6] = 3 * s; tri[:, 7] = 2 * s; tri[:, 8] = -s
     tri = tri.astype(np.float32)
     bvh = rt.BVH(tri)
     bvh.check()
@@ -172,6 +172,8 @@ def test_deep_tree_exercises_the_stack_overflow_path(rt):
     mega, st_m = sc.render(cam, 96, 64, 3, 6, integrator=rt.INTEGRATOR_MEGAKERNEL)
     assert np.array_equal(bits(wave), bits(mega)) and st_w["rays"] == st_m["rays"]
     assert st_w["rays"] > 96 * 64 * 3 * 2, "the camera must see the chain"
+    pers, st_p = sc.render(cam, 96, 64, 3, 6, integrator=rt.INTEGRATOR_PERSISTENT)
+    assert np.array_equal(bits(wave), bits(pers)) and st_p["rays"] == st_w["rays"]
     simple, _ = sc.render(cam, 96, 64, 3, 6, flags=rt.FLAG_SIMPLE_TRACE)
     assert np.array_equal(bits(wave), bits(simple))
 
@@ -447,3 +449,32 @@ def test_persistent_integrator_c3_and_multi_device(rt, golden_cameras):
     fat = scene_of(rt, c3, bvh=rt.BVH(c3["tri9"], max_leaf_size=8))
     with pytest.raises(rt.B200RTError):
         fat.render(c3["camera"], 32, 32, 1, 2, integrator=rt.INTEGRATOR_PERSISTENT)
+
+
+def test_progressive_accumulation_equals_one_shot(rt, golden_scenes, golden_cameras):
+    """b200rt_accum_*: 16 spp streamed as 1 + 4 + 3 + 8 samples (each pixel's RNG stream continued across the chunks, linear sums
+    kept on the device) == one b200rt_render(16), bit for bit, with a non-black incoming framebuffer; the intermediate resolves
+    are proper running means; both barrier styles of the integrator."""
+    g = load_golden("render_cornell_env.npz")
+    a = scene_arrays(golden_scenes, "cornell")
+    sc = rt.Scene(a["tri9"], a["mat_idx"], a["mats10"], a["emissive"], skysphere=g["env"])
+    c = rt.Camera.from_array17(golden_cameras["cornell"])
+    w, h, spp, b = 100, 70, 16, 5
+    rng = np.random.default_rng(6)
+    fb0 = (rng.random((h, w, 4)) * 0.2).astype(np.float32)
+    want = fb0.copy()
+    _, st = sc.render(c, w, h, spp, b, framebuffer=want)
+    for integ in (rt.INTEGRATOR_WAVEFRONT, rt.INTEGRATOR_PERSISTENT):
+        acc = rt.Accumulator(sc, c, w, h, spp, b)
+        rays, partial = 0, None
+        for i, n in enumerate((1, 4, 3, 8)):
+            rays += acc.add(n, integrator=integ)["rays"]
+            if i == 1:
+                partial = acc.resolve()
+        assert acc.samples() == spp and rays == st["rays"]
+        assert np.array_equal(bits(acc.resolve(fb0)), bits(want)), integ
+        assert np.array_equal(bits(acc.resolve(fb0)), bits(want)), "resolve must not consume the accumulator"
+        five, _ = sc.render(c, w, h, 5, b)          # a 5-spp frame uses another seed (31 + x*y*5): only statistically comparable
+        assert abs(float(partial[..., :3].mean()) - float(five[..., :3].mean())) < 0.02
+        with pytest.raises(rt.B200RTError):
+            acc.add(1)
