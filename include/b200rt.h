@@ -137,6 +137,24 @@ int b200rt_env_alias_table(const float* env_rgba, int env_w, int env_h, float* p
 int b200rt_scene_get_bvh_info(const b200rt_scene* scene, b200rt_bvh_info* out);
 size_t b200rt_scene_device_bytes(const b200rt_scene* scene);
 
+/* ---- ingest ----------------------------------------------------------------------------------------------------------------------
+ * b200rt_obj_load replaces Utils::parse_obj (source/utils.cpp:16-98: rapidobj parse + Triangulate -> ParsedOBJ): the same triangle
+ * list in the same order (quads cut along their shorter diagonal like rapidobj; larger polygons fanned), material indices shifted
+ * by one (slot 0 = the default material, emission (1, 0, 1)), roughness clamped to >= 1e-2, illum 0 -> roughness 1 / metalness 0,
+ * emissive triangles listed. The arrays are exactly what b200rt_scene_create[_multi] takes; borrowed, valid until b200rt_obj_destroy.
+ * b200rt_hdr_load replaces the stbi_loadf call of Utils::read_image_float (utils.cpp:100-124) for Radiance .hdr files: RGB triplets
+ * (pass them to b200rt_scene_create_multi with env_channels = 3: the RGBA expansion happens on the device), row 0 = bottom row
+ * when flip_y != 0, as the reference loads it. Host code. */
+typedef struct b200rt_obj b200rt_obj;
+int b200rt_obj_load(const char* path, b200rt_obj** out);
+int b200rt_obj_get(const b200rt_obj* obj, const float** tri_xyz9, int* n_tri, const int** tri_material, const float** materials10,
+                   int* n_materials, const int** emissive_tri, int* n_emissive);
+void b200rt_obj_destroy(b200rt_obj* obj);
+typedef struct b200rt_hdr b200rt_hdr;
+int b200rt_hdr_load(const char* path, int flip_y, b200rt_hdr** out);
+int b200rt_hdr_get(const b200rt_hdr* hdr, const float** rgb, int* width, int* height);
+void b200rt_hdr_destroy(b200rt_hdr* hdr);
+
 /* ---- rendering -------------------------------------------------------------------------------------------------------- */
 #define B200RT_INTEGRATOR_MEGAKERNEL 0   /* persistent lanes, one pixel at a time per lane, single trace site */
 #define B200RT_INTEGRATOR_WAVEFRONT 1    /* path-regeneration wavefront: shade / trace kernel pairs over tile groups (default) */
@@ -236,6 +254,11 @@ void b200rt_accum_destroy(b200rt_accum* acc);
  * *state_out = the generator state of pixel (x, y) after the 10 warm-up draws (seed 31 + x*y*spp in wrapping int arithmetic),
  * floats_out[0..n) = the next n floats. Runs on the calling thread's current device. */
 int b200rt_rng_stream(int x, int y, int spp, int n, uint32_t* state_out, float* floats_out);
+
+/* Parity hook for env_map_cdf_search (render_kernel.cpp:532-567): the texel (x, y) the reference's two binary searches pick for each of
+ * n values (value = draw * cdf total), as the integrators evaluate it. use_guide != 0: through the guide table built at scene creation
+ * (the default path when the CDF is non-decreasing); 0: the reference's plain searches. Both must agree. xy_out: 2*n ints. Host pointers. */
+int b200rt_env_cdf_search(b200rt_scene* scene, const float* values, int n, int use_guide, int* xy_out);
 
 /* Page-locked host memory for framebuffers / result arrays: copies from and to such buffers run at the full PCIe rate and are
  * not staged. Pageable buffers are accepted everywhere too (staged through the library's own pinned chunks). */

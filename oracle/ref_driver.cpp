@@ -419,6 +419,25 @@ int refo_write_png(const float* rgba, int w, int h, const char* path, int flip_y
     return write_image_png(img, path, flip_y != 0) ? 0 : 1;
 }
 
+// the reference's own HDR round trip: write_image_hdr (source/image_io.cpp:208-215, stb's RGBE writer) and
+// Utils::read_image_float (source/utils.cpp:100-124, stbi_loadf with the vertical flip): the ingest checker for b200rt_hdr_load
+int refo_write_hdr(const float* rgba, int w, int h, const char* path, int flip_y)
+{
+    Image img(w, h);
+    for (int i = 0; i < w * h; i++) img[i] = Color(rgba[4 * i], rgba[4 * i + 1], rgba[4 * i + 2], rgba[4 * i + 3]);
+    return write_image_hdr(img, path, flip_y != 0) ? 0 : 1;
+}
+
+// returns 0 and fills rgba_out (w*h*4, the Image read_image_float builds: alpha 0) when out_w/out_h match the file
+int refo_read_image_float(const char* path, int flip_y, int expect_w, int expect_h, float* rgba_out)
+{
+    int w = 0, h = 0;
+    Image img = Utils::read_image_float(path, w, h, flip_y != 0);
+    if (w != expect_w || h != expect_h) return 1;
+    for (int i = 0; i < w * h; i++) { Color c = img[i]; rgba_out[4 * i] = c.r; rgba_out[4 * i + 1] = c.g; rgba_out[4 * i + 2] = c.b; rgba_out[4 * i + 3] = c.a; }
+    return 0;
+}
+
 // octree statistics (diagnostics only)
 static void walk(const BVH::OctreeNode* n, int depth, long long* st)
 {

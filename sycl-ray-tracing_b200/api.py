@@ -149,6 +149,37 @@ def rng_stream(x: int, y: int, spp: int, n: int = 16):
     return int(st.value), fl
 
 
+def parse_obj(path: str) -> dict:
+    """Utils::parse_obj (utils.cpp:16-98) through the library's own ingest (b200rt_obj_load): dict(tri9, mat_idx, mats10, emissive)."""
+    L = B.load_library()
+    h = C.c_void_p()
+    B.check(L.b200rt_obj_load(str(path).encode(), C.byref(h)))
+    try:
+        FP, IP = C.POINTER(C.c_float), C.POINTER(C.c_int)
+        tri, mi, mats, em = FP(), IP(), FP(), IP()
+        nt, nm, ne = C.c_int(), C.c_int(), C.c_int()
+        B.check(L.b200rt_obj_get(h, C.byref(tri), C.byref(nt), C.byref(mi), C.byref(mats), C.byref(nm), C.byref(em), C.byref(ne)))
+        cp = lambda p, n, dt: (np.ctypeslib.as_array(p, shape=(n,)).astype(dt, copy=True) if n else np.zeros(0, dt))
+        return dict(tri9=cp(tri, nt.value * 9, np.float32).reshape(-1, 9), mat_idx=cp(mi, nt.value, np.int32),
+                    mats10=cp(mats, nm.value * 10, np.float32).reshape(-1, 10), emissive=cp(em, ne.value, np.int32))
+    finally:
+        L.b200rt_obj_destroy(h)
+
+
+def read_image_float(path: str, flip_y: bool = True) -> np.ndarray:
+    """Utils::read_image_float for Radiance .hdr files (utils.cpp:100-124) through b200rt_hdr_load: (h, w, 3) float32 RGB — pass it as
+    a Scene's skysphere (the RGBA expansion, alpha 0, happens on the device)."""
+    L = B.load_library()
+    h = C.c_void_p()
+    B.check(L.b200rt_hdr_load(str(path).encode(), 1 if flip_y else 0, C.byref(h)))
+    try:
+        p, w, ht = C.POINTER(C.c_float)(), C.c_int(), C.c_int()
+        B.check(L.b200rt_hdr_get(h, C.byref(p), C.byref(w), C.byref(ht)))
+        return np.ctypeslib.as_array(p, shape=(ht.value, w.value, 3)).astype(np.float32, copy=True)
+    finally:
+        L.b200rt_hdr_destroy(h)
+
+
 # ---- Image (image.h:25-178) ----------------------------------------------------------------------------------------------
 class Image:
     """RGBA float32, row-major, row 0 = bottom. Image(w, h) starts as Color::Black() = (0, 0, 0, 1)."""
@@ -388,6 +419,13 @@ class Scene:
         """The CDF the integrator searches (device-computed when none was passed in)."""
         out = np.empty(self.env.shape[0] * self.env.shape[1], np.float32)
         B.check(B.load_library().b200rt_scene_get_env_cdf(self._h, B.fptr(out)))
+        return out
+
+    def env_cdf_search(self, values, use_guide: bool = True) -> np.ndarray:
+        """env_map_cdf_search (render_kernel.cpp:532-567) for a batch of values on the device: (n, 2) int32 texels (x, y)."""
+        v = _f32(values).reshape(-1)
+        out = np.empty((len(v), 2), np.int32)
+        B.check(B.load_library().b200rt_env_cdf_search(self._h, B.fptr(v), len(v), 1 if use_guide else 0, B.iptr(out)))
         return out
 
     def build_env_alias(self) -> None:

@@ -16,8 +16,12 @@
 #include "bvh_build.h"
 #include "device_types.h"
 #include "kernels.h"
+#include "obj_ingest.h"
 
 using namespace b200rt;
+
+struct b200rt_obj { ParsedObjArrays a; };
+struct b200rt_hdr { std::vector<float> rgb; int w = 0, h = 0; };
 
 struct b200rt_bvh { FlatBVH flat; };
 
@@ -700,6 +704,17 @@ int create_on_device(const SceneArgs& a, const FlatBVH& f, const SceneHostData& 
         if (ce == cudaSuccess) ce = cudaMemcpy(&s->dev.cdf_total, d_cdf + n_texels - 1, sizeof(float), cudaMemcpyDeviceToHost);
         if (ce != cudaSuccess) { rc = fail(B200RT_ERR_CUDA, "env tables: %s", cudaGetErrorString(ce)); break; }
         s->dev.cdf = d_cdf; s->dev.row_cdf = d_row; s->d_env_lum = d_lum;
+        // guide table of the CDF search (bit-identical texel choice, ~2 probes instead of log2(W) + log2(H)); B200RT_CDF_GUIDE=0 turns it off
+        static const int guide_buckets = []() { const char* e = getenv("B200RT_CDF_GUIDE"); int v = e ? atoi(e) : 65536; return v < 0 ? 0 : v; }();
+        if (guide_buckets > 0 && n_texels >= 64)
+        {
+            unsigned int* d_guide = nullptr;
+            if ((rc = device_alloc(s, &d_guide, (size_t)guide_buckets + 2))) break;
+            float scale = 0.0f; int built = 0;
+            ce = build_env_cdf_guide(d_cdf, n_texels, s->dev.cdf_total, guide_buckets, d_guide, &scale, &built, 0);
+            if (ce != cudaSuccess) { rc = fail(B200RT_ERR_CUDA, "env CDF guide: %s", cudaGetErrorString(ce)); break; }
+            if (built) { s->dev.cdf_guide = d_guide; s->dev.cdf_guide_scale = scale; s->dev.cdf_guide_n = guide_buckets; }
+        }
     } while (0);
     if (rc) { b200rt_scene_destroy(s); return rc; }
     rc = b200rt_scene_set_materials(s, a.materials10, a.n_materials);
@@ -1368,6 +1383,86 @@ int b200rt_rng_stream(int x, int y, int spp, int n, uint32_t* state_out, float* 
     } while (0);
     cudaFree(d_state); cudaFree(d_f);
     if (e != cudaSuccess) return fail(B200RT_ERR_CUDA, "rng_stream: %s", cudaGetErrorString(e));
+    return B200RT_OK;
+}
+
+int b200rt_obj_load(const char* path, b200rt_obj** out)
+{
+    if (!path || !out) return fail(B200RT_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    b200rt_obj* o = new (std::nothrow) b200rt_obj;
+    if (!o) return fail(B200RT_ERR_ALLOC, "out of host memory");
+    std::string err;
+    bool ok = false;
+    try { ok = load_obj(path, o->a, err); }
+    catch (const std::exception& e) { err = e.what(); }
+    if (!ok) { delete o; return fail(B200RT_ERR_ARG, "OBJ ingest: %s", err.c_str()); }
+    *out = o;
+    return B200RT_OK;
+}
+
+int b200rt_obj_get(const b200rt_obj* o, const float** tri_xyz9, int* n_tri, const int** tri_material, const float** materials10,
+                   int* n_materials, const int** emissive_tri, int* n_emissive)
+{
+    if (!o) return fail(B200RT_ERR_ARG, "NULL obj");
+    if (tri_xyz9) *tri_xyz9 = o->a.tri_xyz9.data();
+    if (n_tri) *n_tri = (int)(o->a.tri_xyz9.size() / 9);
+    if (tri_material) *tri_material = o->a.tri_material.data();
+    if (materials10) *materials10 = o->a.materials10.data();
+    if (n_materials) *n_materials = (int)(o->a.materials10.size() / 10);
+    if (emissive_tri) *emissive_tri = o->a.emissive_tri.data();
+    if (n_emissive) *n_emissive = (int)o->a.emissive_tri.size();
+    return B200RT_OK;
+}
+
+void b200rt_obj_destroy(b200rt_obj* o) { delete o; }
+
+int b200rt_hdr_load(const char* path, int flip_y, b200rt_hdr** out)
+{
+    if (!path || !out) return fail(B200RT_ERR_ARG, "NULL argument");
+    *out = nullptr;
+    b200rt_hdr* h = new (std::nothrow) b200rt_hdr;
+    if (!h) return fail(B200RT_ERR_ALLOC, "out of host memory");
+    std::string err;
+    bool ok = false;
+    try { ok = load_hdr(path, flip_y != 0, h->rgb, h->w, h->h, err); }
+    catch (const std::exception& e) { err = e.what(); }
+    if (!ok) { delete h; return fail(B200RT_ERR_ARG, "HDR ingest: %s", err.c_str()); }
+    *out = h;
+    return B200RT_OK;
+}
+
+int b200rt_hdr_get(const b200rt_hdr* h, const float** rgb, int* width, int* height)
+{
+    if (!h) return fail(B200RT_ERR_ARG, "NULL hdr");
+    if (rgb) *rgb = h->rgb.data();
+    if (width) *width = h->w;
+    if (height) *height = h->h;
+    return B200RT_OK;
+}
+
+void b200rt_hdr_destroy(b200rt_hdr* h) { delete h; }
+
+int b200rt_env_cdf_search(b200rt_scene* s, const float* values, int n, int use_guide, int* xy_out)
+{
+    if (!s || n < 0 || (n > 0 && (!values || !xy_out))) return fail(B200RT_ERR_ARG, "bad env_cdf_search arguments");
+    if (n == 0) return B200RT_OK;
+    ON_DEVICE(s->device);
+    SceneDev dev = s->dev;
+    if (!use_guide) dev.cdf_guide = nullptr;
+    else if (!dev.cdf_guide) return fail(B200RT_ERR_ARG, "this scene has no CDF guide table (the running sum is not monotone, or B200RT_CDF_GUIDE=0)");
+    float* d_v = nullptr; int* d_xy = nullptr;
+    cudaError_t e = cudaSuccess;
+    do
+    {
+        if ((e = cudaMalloc(&d_v, sizeof(float) * (size_t)n)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&d_xy, sizeof(int) * 2 * (size_t)n)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(d_v, values, sizeof(float) * (size_t)n, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = launch_env_cdf_search(dev, d_v, n, d_xy, 0)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(xy_out, d_xy, sizeof(int) * 2 * (size_t)n, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+    } while (0);
+    cudaFree(d_v); cudaFree(d_xy);
+    if (e != cudaSuccess) return fail(B200RT_ERR_CUDA, "env_cdf_search: %s", cudaGetErrorString(e));
     return B200RT_OK;
 }
 

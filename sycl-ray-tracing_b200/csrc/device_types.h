@@ -38,6 +38,9 @@ struct SceneDev
     const float* cdf;          // running luminance sum, row-major
     const float2* env_alias;   // per texel {acceptance probability, as_float(alias texel)}; null until b200rt_scene_build_env_alias
     const float* row_cdf;      // cdf[y * env_w + env_w - 1] for every row (the row search's probes, contiguous)
+    const unsigned int* cdf_guide; // [cdf_guide_n + 2] lower bounds of the CDF search per value bucket (env_tables.cu); null = plain binary searches
+    float cdf_guide_scale;     // bucket = min(cdf_guide_n - 1, (unsigned)(value * cdf_guide_scale))
+    int cdf_guide_n;
     int n_tri, n_mats, n_emissive, n_spheres;
     int env_w, env_h;
     float cdf_total;

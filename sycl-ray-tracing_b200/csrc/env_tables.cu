@@ -102,6 +102,58 @@ cudaError_t launch_env_row_cdf(const float* cdf, int w, int h, float* row, cudaS
     return cudaGetLastError();
 }
 
+// ---- guide table of the CDF search ---------------------------------------------------------------------------------------------------
+// first index whose running sum exceeds v (n if none), v in double (the float table converts exactly)
+__device__ __forceinline__ unsigned int cdf_first_above(const float* __restrict__ cdf, unsigned int n, double v)
+{
+    unsigned int lo = 0, hi = n;
+    while (lo < hi) { const unsigned int m = (lo + hi) >> 1; if (v < (double)cdf[m]) hi = m; else lo = m + 1; }
+    return lo;
+}
+
+// guide[b] = first_above((b / scale) * (1 - 1e-6)): a value v with (unsigned)(v * scale) == b (float multiply, |rounding| <= 2^-24)
+// satisfies v >= (b / scale) * (1 - 2^-23) and v < ((b + 1) / scale) * (1 + 2^-23) < ((b + 2) / scale) * (1 - 1e-6), so its texel lies
+// in [guide[b], guide[b + 2]] (first_above is non-decreasing in v)
+__global__ void __launch_bounds__(256) k_env_cdf_guide(const float* __restrict__ cdf, unsigned int n, float scale, int n_buckets, unsigned int* __restrict__ guide)
+{
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b > n_buckets + 1) return;
+    guide[b] = b >= n_buckets ? n : cdf_first_above(cdf, n, ((double)b / (double)scale) * (1.0 - 1.0e-6));
+}
+
+__global__ void __launch_bounds__(256) k_env_cdf_monotone(const float* __restrict__ cdf, size_t n, int* __restrict__ violations)
+{
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x + 1; i < n; i += (size_t)gridDim.x * blockDim.x)
+        if (!(cdf[i] >= cdf[i - 1])) atomicAdd(violations, 1);
+}
+
+// builds the guide when the table allows it (finite positive total, non-decreasing sums); *built_out = 0 otherwise
+cudaError_t build_env_cdf_guide(const float* cdf, size_t n, float total, int n_buckets, unsigned int* guide, float* scale_out, int* built_out, cudaStream_t stream)
+{
+    *built_out = 0;
+    if (!(total > 0.0f) || !isfinite(total) || n < 2 || n >= 0x7fffffffu) return cudaSuccess;
+    const float scale = (float)n_buckets / total;
+    if (!(scale > 0.0f) || !isfinite(scale)) return cudaSuccess;
+    int* d_viol = nullptr;
+    cudaError_t e = cudaMalloc(&d_viol, sizeof(int));
+    if (e != cudaSuccess) return e;
+    int viol = 0;
+    do
+    {
+        if ((e = cudaMemsetAsync(d_viol, 0, sizeof(int), stream)) != cudaSuccess) break;
+        k_env_cdf_monotone<<<(unsigned int)std::min<size_t>((n + 255) / 256, 148 * 16), 256, 0, stream>>>(cdf, n, d_viol);
+        if ((e = cudaMemcpyAsync(&viol, d_viol, sizeof(int), cudaMemcpyDeviceToHost, stream)) != cudaSuccess) break;
+        if ((e = cudaStreamSynchronize(stream)) != cudaSuccess) break;
+        if (viol) break;
+        k_env_cdf_guide<<<(n_buckets + 2 + 255) / 256, 256, 0, stream>>>(cdf, (unsigned int)n, scale, n_buckets, guide);
+        if ((e = cudaGetLastError()) != cudaSuccess) break;
+        *scale_out = scale;
+        *built_out = 1;
+    } while (0);
+    cudaFree(d_viol);
+    return e;
+}
+
 // ---- alias table -----------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) k_alias_positive(const float* __restrict__ lum, size_t n, double* __restrict__ pos)
 {

@@ -342,6 +342,23 @@ cudaError_t launch_rng_stream(int x, int y, int spp, int n, uint32_t* state_out,
     return cudaGetLastError();
 }
 
+// ---- parity hook: env_map_cdf_search (render_kernel.cpp:532-567) for a batch of values, with or without the guide table ----------
+__global__ void __launch_bounds__(256) k_env_cdf_search(SceneDev S, const float* __restrict__ values, int n, int* __restrict__ xy)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    int x, y;
+    env_cdf_search(S, values[i], x, y);
+    xy[2 * i] = x; xy[2 * i + 1] = y;
+}
+
+cudaError_t launch_env_cdf_search(const SceneDev& S, const float* values, int n, int* xy, cudaStream_t stream)
+{
+    if (n <= 0) return cudaSuccess;
+    k_env_cdf_search<<<(n + 255) / 256, 256, 0, stream>>>(S, values, n, xy);
+    return cudaGetLastError();
+}
+
 // ---- launchers ----------------------------------------------------------------------------------------------------------------
 // SM count of the calling thread's current device (cached per device: one process may drive several GPU models)
 int current_sm_count()

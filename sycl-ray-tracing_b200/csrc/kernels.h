@@ -34,6 +34,7 @@ cudaError_t launch_untile(const float4* tiles, int tiles_per_rank_padded, int wo
 cudaError_t launch_untile_accumulate(const float4* tiles, int tiles_per_rank_padded, int world, int w, int h, float4* image, cudaStream_t stream);
 cudaError_t launch_fill_f4(float4* p, size_t n, float4 v, cudaStream_t stream);
 cudaError_t launch_fill_f32(float* p, size_t n, float v, cudaStream_t stream);
+cudaError_t launch_env_cdf_search(const SceneDev& S, const float* values, int n, int* xy, cudaStream_t stream);
 cudaError_t launch_rng_stream(int x, int y, int spp, int n, uint32_t* state_out, float* floats_out, cudaStream_t stream);
 cudaError_t launch_quantise_rgba8(const float4* image, int w, int h, int flip_y, void* out_rgba8, cudaStream_t stream);
 
@@ -42,6 +43,7 @@ cudaError_t launch_env_expand_rgb(const float* rgb, size_t n, float4* rgba, cuda
 cudaError_t launch_env_luminance(const float4* env, size_t n, float* lum, cudaStream_t stream);
 cudaError_t launch_env_cdf_serial(const float* lum, size_t n, float* cdf, cudaStream_t stream);
 cudaError_t launch_env_row_cdf(const float* cdf, int w, int h, float* row, cudaStream_t stream);
+cudaError_t build_env_cdf_guide(const float* cdf, size_t n, float total, int n_buckets, unsigned int* guide, float* scale_out, int* built_out, cudaStream_t stream);
 cudaError_t build_env_alias_device(const float* lum, size_t n, float2* table, double* total_host, cudaStream_t stream);
 
 // B200RT_FLAG_TIME_INLINE: every trace / shade launch of a frame bracketed by CUDA events on its own group stream, nothing

@@ -735,6 +735,24 @@ __device__ __forceinline__ col env_from_direction(const SceneDev& S, v3 d)
 }
 __device__ __forceinline__ void env_cdf_search(const SceneDev& S, float value, int& xo, int& yo)
 {
+    if (S.cdf_guide)
+    {
+        // The reference's two binary searches (row on the last column, then column inside the row, :532-567) return the first texel
+        // whose running sum exceeds `value` in row-major order (the last texel if none does) whenever the running sum is
+        // non-decreasing — which env_tables.cu verified before it built this guide. The guide brackets that texel per value bucket
+        // (~2 probes instead of 21 dependent ones on the 2048x1024 sky); the bracketed search returns the same texel, bit for bit.
+        const unsigned int b = min((unsigned int)(S.cdf_guide_n - 1), __float2uint_rz(value * S.cdf_guide_scale));
+        const unsigned int n_texels = (unsigned int)(S.env_w * S.env_h);
+        unsigned int lower = __ldg(S.cdf_guide + b), upper = min(__ldg(S.cdf_guide + b + 2), n_texels - 1u);
+        while (lower < upper)
+        {
+            const unsigned int mid = (lower + upper) >> 1;
+            if (value < __ldg(S.cdf + mid)) upper = mid; else lower = mid + 1u;
+        }
+        yo = (int)(lower / (unsigned int)S.env_w);
+        xo = (int)(lower - (unsigned int)yo * (unsigned int)S.env_w);
+        return;
+    }
     int lower = 0, upper = S.env_h - 1;
     while (lower < upper)
     {

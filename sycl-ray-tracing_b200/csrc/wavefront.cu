@@ -300,8 +300,10 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
     struct GroupRun { RenderParams P; int parity; bool finished, forked; int slot_grid; long long it, poll_it; bool poll_pending; unsigned int tail_below; };
     // barrier-free tail (persist.cu): when a group has at most B200RT_WF_TAIL_PCT % of its pixels (and at most B200RT_WF_TAIL_CAP) left,
     // or is smaller than B200RT_WF_TAIL_MIN pixels to begin with. 8-ary layout, default trace kernel only; not in the per-kernel timing modes.
-    static const int tail_pct = []() { const char* e = getenv("B200RT_WF_TAIL_PCT"); int v = e ? atoi(e) : 40; return v < 0 ? 0 : (v > 100 ? 100 : v); }();
-    static const long long tail_cap = []() { const char* e = getenv("B200RT_WF_TAIL_CAP"); return e ? atoll(e) : 100000ll; }();
+    // Measured on C3 at 64 spp (profiles/r2_tail.jsonl): whole frame 433.3 ms without, 428.9 with a 30 k cap (445 with 100 k: the tail
+    // kernel's throughput is below the pass kernels', it only pays once passes are latency-bound); one rank of 8: 108.1 -> 101.7 ms at 20 %.
+    static const int tail_pct = []() { const char* e = getenv("B200RT_WF_TAIL_PCT"); int v = e ? atoi(e) : 20; return v < 0 ? 0 : (v > 100 ? 100 : v); }();
+    static const long long tail_cap = []() { const char* e = getenv("B200RT_WF_TAIL_CAP"); return e ? atoll(e) : 30000ll; }();
     static const int tail_min = []() { const char* e = getenv("B200RT_WF_TAIL_MIN"); return e ? atoi(e) : 16384; }();
     const bool tail_ok = coop && tail_pct > 0 && !timing && !(P.flags & B200RT_FLAG_TIME_INLINE);
     const int tail_ctas = tail_ok ? std::max(1, wavefront_tail_max_ctas() / n_groups) : 0;

@@ -418,10 +418,18 @@ def test_persistent_integrator_equals_megakernel_bit_for_bit(rt, golden_scenes, 
     w2, h2 = 100, 70
     fb0 = (rng.random((h2, w2, 4)) * 0.2).astype(np.float32)
     want = fb0.copy(); sc.render(c, w2, h2, 2, 4, framebuffer=want)
+    one = fb0.copy(); sc.render(c, w2, h2, 2, 4, framebuffer=one, integrator=rt.INTEGRATOR_PERSISTENT)
+    assert np.array_equal(bits(want), bits(one)), f"non-black framebuffer: {(bits(want) != bits(one)).any(axis=-1).sum()} pixels differ"
+    black_w, _ = sc.render(c, w2, h2, 2, 4)
+    black = rt.Image(w2, h2).pixels
+    for rank in range(3):
+        sc.render(c, w2, h2, 2, 4, framebuffer=black, integrator=rt.INTEGRATOR_PERSISTENT, rank=rank, world=3)
+    assert np.array_equal(bits(black_w), bits(black)), f"ranks: {(bits(black_w) != bits(black)).any(axis=-1).sum()} pixels differ"
     got = fb0.copy()
     for rank in range(3):
         sc.render(c, w2, h2, 2, 4, framebuffer=got, integrator=rt.INTEGRATOR_PERSISTENT, rank=rank, world=3)
-    assert np.array_equal(bits(want), bits(got))
+    diff = (bits(want) != bits(got)).any(axis=-1)
+    assert not diff.any(), f"ranks + non-black framebuffer: {diff.sum()} pixels differ, first at {np.argwhere(diff)[:5].tolist()}"
     zero, _ = sc.render(c, 40, 30, 0, 4, integrator=rt.INTEGRATOR_PERSISTENT)
     zero_w, _ = sc.render(c, 40, 30, 0, 4)
     assert np.array_equal(bits(zero), bits(zero_w))
@@ -478,3 +486,29 @@ def test_progressive_accumulation_equals_one_shot(rt, golden_scenes, golden_came
         assert abs(float(partial[..., :3].mean()) - float(five[..., :3].mean())) < 0.02
         with pytest.raises(rt.B200RTError):
             acc.add(1)
+
+
+def test_env_cdf_search_guide_is_exact(rt):
+    """env_map_cdf_search (render_kernel.cpp:532-567) on the device, through the guide table and without it, against a numpy
+    restatement of the reference's two binary searches: the same texel for every value — random draws, every bucket boundary
+    neighbourhood, exact table values, 0 and the largest draw — on the 2048x1024 sun+sky (whose float running sum stagnates)."""
+    from sycl_ray_tracing_b200 import scenes
+    c3 = scenes.c3_scene(nu=20, nv=10)
+    sc = scene_of(rt, c3)
+    cdf = rt.compute_env_map_cdf(c3["env"])
+    h, w = c3["env"].shape[:2]
+    total = cdf[-1]
+    rng = np.random.default_rng(9)
+    draws = np.minimum(rng.integers(0, 2 ** 32, 300000, dtype=np.uint64).astype(np.float32) * np.float32(2.0 ** -32), np.float32(1.0 - 1.0e-6))
+    vals = [draws * total, cdf[rng.integers(0, cdf.size, 50000)], np.nextafter(cdf[rng.integers(0, cdf.size, 50000)], np.float32(0)),
+            (np.arange(0, 65537, dtype=np.float64) / (65536.0 / float(total))).astype(np.float32),
+            np.array([0.0, np.float32(1.0 - 1.0e-6) * total, total, np.nextafter(total, np.float32(0))], np.float32)]
+    v = np.concatenate(vals).astype(np.float32)
+    # the reference's searches: first row whose last column exceeds the value (else the last row), then first column in that row (else the last)
+    rows = cdf.reshape(h, w)
+    y = np.minimum(np.searchsorted(rows[:, -1], v, side="right"), h - 1)
+    x = np.array([min(int(np.searchsorted(rows[yy], vv, side="right")), w - 1) for yy, vv in zip(y[:20000], v[:20000])])
+    plain = sc.env_cdf_search(v, use_guide=False)
+    guided = sc.env_cdf_search(v, use_guide=True)
+    assert np.array_equal(plain, guided), f"{(plain != guided).any(axis=1).sum()} values pick another texel through the guide"
+    assert np.array_equal(plain[:, 1], y) and np.array_equal(plain[:20000, 0], x)
