@@ -1,13 +1,16 @@
 #!/usr/bin/env python
 """bench.py — the path-tracing hot path on N B200s of one node.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c3|c2|c1|c5]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload c3|c3k|c2|c1|c5]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
 
 Workload (default) = BASELINE.json config 3, the one the metric is quoted on: "Dragon" at 1920x1080, 64 spp, 8 bounces,
 HDR skysphere with env-map importance sampling + BRDF importance sampling + MIS. The reference ships neither the Dragon
 OBJ nor the HDR (.MISSING_LARGE_BLOBS), so the Dragon-class procedural stand-in of SURVEY.md Appendix A is used
-(1 000 002 triangles, gold metal roughness 0.25, 2048x1024 sun+sky) — `data` says so.
+(1 000 002 triangles, gold metal roughness 0.25, 2048x1024 sun+sky) — `data` says so. When data/OBJs/pbrt_dragon.obj and
+data/Skyspheres/evening_road_01_puresky_2k.hdr exist (under $B200RT_ASSET_ROOT, this directory or /root/reference) they are
+ingested by the library (b200rt_obj_load / b200rt_hdr_load) and used instead. `--workload c3k` is the same configuration on
+the concave stand-in (displaced torus knot).
 
 A step = one full frame: every rank renders its interleaved 16x16 tiles (wavefront integrator by default: wf_shade /
 wf_trace kernel pairs over 4 tile groups on 4 streams), the tile buffers are gathered to rank 0 (NCCL) and un-tiled there. value = INTERSECT_SCENE-equivalent rays of the whole frame / step time
@@ -35,6 +38,8 @@ WORKLOADS = {
     "c2": (1920, 1080, 1, 1, "1M-triangle displaced sphere, 1920x1080 un-jittered primary rays (BASELINE config 2)"),
     "c3": (1920, 1080, 64, 8, "Dragon-class stand-in (1,000,002 tris, gold metal r=0.25), 1920x1080 64spp 8 bounces, "
                               "2048x1024 sun+sky env-map IS + BRDF IS + MIS (BASELINE config 3)"),
+    "c3k": (1920, 1080, 64, 8, "concave Dragon-class stand-in (displaced (2,3) torus knot, 1,000,002 tris, gold metal r=0.25), 1920x1080 "
+                               "64spp 8 bounces, 2048x1024 sun+sky env-map IS + BRDF IS + MIS (BASELINE config 3, SURVEY 8d's 'better' stand-in)"),
     "c5": (3840, 2160, 1024, 8, "20M-triangle procedural scene 3840x2160 1024spp 8 bounces (BASELINE config 5)"),
 }
 
@@ -49,7 +54,8 @@ def parse_args():
     p.add_argument("--spp", type=int, default=0, help="override samples per pixel (0 = the workload's)")
     p.add_argument("--width", type=int, default=0)
     p.add_argument("--height", type=int, default=0)
-    p.add_argument("--integrator", type=int, default=1, help="0 = megakernel, 1 = wavefront (default)")
+    p.add_argument("--integrator", type=int, default=1, help="0 = megakernel, 1 = wavefront (default), 2 = persistent")
+    p.add_argument("--warmup-spp", type=int, default=0, help="spp of the warm-up frames (0 = the workload's; c5 defaults to 8: a 1024-spp warm-up frame is minutes)")
     p.add_argument("--flags", type=int, default=0)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-sample", default="", help="WxHxSPP of the bounded CPU sample (default per workload)")
@@ -69,7 +75,14 @@ def load_workload(name, args):
         s = scenes.c2_scene()
         s["env"] = rt.constant_env(1.0)
     elif name == "c3":
-        s = scenes.c3_scene()
+        real = scenes.find_real_dragon([os.environ.get("B200RT_ASSET_ROOT"), ROOT, "/root/reference"])
+        if real:
+            s = scenes.real_dragon_scene(*real)
+            desc = f"PBRT Dragon ({len(s['tri9'])} tris, {os.path.basename(real[0])}) under {os.path.basename(real[1])}, 1920x1080 64spp 8 bounces (BASELINE config 3, real assets)"
+        else:
+            s = scenes.c3_scene()
+    elif name == "c3k":
+        s = scenes.c3_knot_scene()
     else:
         s = scenes.c5_scene()
     w = args.width or w
@@ -142,7 +155,7 @@ def cpu_sample_shape(name, args, w, h, spp):
     if args.cpu_sample:
         a = [int(v) for v in args.cpu_sample.lower().split("x")]
         return a[0], a[1], a[2]
-    if name == "c3":
+    if name in ("c3", "c3k"):
         return 768, 432, 4          # 4/25 of the pixels, 1/16 of the spp: ~10-30 s of reference CPU work on 16 cores
     if name == "c5":
         return 192, 108, 1
@@ -216,6 +229,18 @@ def reference_arm(args):
     print(json.dumps(line), flush=True)
 
 
+def ncu_counters(workload):
+    """What actually bounds the dominant kernel, from the committed ncu capture of this round (profiles/r2_counters.json, written by
+    tools/ncu_counters.py from the .ncu-rep of the shipping kernel): reported next to the nominal HBM fraction."""
+    path = os.path.join(ROOT, "profiles", "r2_counters.json")
+    if os.path.exists(path):
+        try:
+            return json.load(open(path)).get(workload)
+        except Exception:
+            return None
+    return None
+
+
 def main():
     args = parse_args()
     if args.impl == "reference":
@@ -248,11 +273,15 @@ def main():
     n_tri = len(s["tri9"])
     bytes_per_ray = scenes.algorithmic_bytes_per_ray(n_tri)
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=device)      # > 126 MB L2
+    warm_spp = args.warmup_spp or (8 if args.workload == "c5" and spp > 8 else spp)
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def cur_stream():
+        return torch.cuda.current_stream(device).cuda_stream
 
     primary_only = args.workload == "c2"
     if primary_only:
@@ -260,29 +289,35 @@ def main():
         tbuf = torch.empty((h, w), dtype=torch.float32, device=device)
 
         def step():
-            st = torch.cuda.current_stream(device).cuda_stream
-            scene.trace_primary_device(cam, w, h, prim.data_ptr(), tbuf.data_ptr(), stream_ptr=st, rank=rank, world=world, flags=args.flags)
+            scene.trace_primary_device(cam, w, h, prim.data_ptr(), tbuf.data_ptr(), stream_ptr=cur_stream(), rank=rank, world=world, flags=args.flags)
+        warm_step = step
         rays_per_frame = w * h
         kernel_name = "k_primary"
         launches_per_step = 1
     else:
         g = D.make_cuda_gatherer(scene, cam, w, h, spp, bounces, rank, world, device, integrator=args.integrator, flags=args.flags)
         step = g.frame
-        # rays of the whole frame (deterministic): counted once on an untimed pass
+        warm_step = step if warm_spp == spp else D.make_cuda_gatherer(scene, cam, w, h, warm_spp, bounces, rank, world, device,
+                                                                     integrator=args.integrator, flags=args.flags).frame
+        kernel_name = {0: "k_pathtrace_mega", 1: "wf_trace_coop", 2: "pt_persist"}[args.integrator]
+
+    for _ in range(args.warmup):
+        warm_step()
+    barrier()
+
+    if not primary_only:
+        # rays of the whole frame (deterministic) and this rank's launch count: one untimed pass with stats
         tiles_probe = torch.empty_like(g.tiles)
-        st = scene.render_tiles_device(cam, w, h, spp, bounces, tiles_probe.data_ptr(), stream_ptr=torch.cuda.current_stream(device).cuda_stream,
+        st = scene.render_tiles_device(cam, w, h, spp, bounces, tiles_probe.data_ptr(), stream_ptr=cur_stream(),
                                        integrator=args.integrator, flags=args.flags, rank=rank, world=world, want_stats=True)
         rays_t = torch.tensor([st["rays"]], dtype=torch.int64, device=device)
         if world > 1:
             dist.all_reduce(rays_t)
         rays_per_frame = int(rays_t.item())
+        rank_rays = int(st["rays"])
         del tiles_probe
-        kernel_name = "k_pathtrace_mega" if args.integrator == 0 else "wf_trace_coop + wf_shade, all launches of the frame"
-        launches_per_step = int(st["gpu_launches"]) + (1 if rank == 0 else 0)
+        launches_per_step = int(st["gpu_launches"]) + (2 if rank == 0 else 0)       # + framebuffer fill and the accumulating un-tile on rank 0
 
-    for _ in range(args.warmup):
-        step()
-    barrier()
     verified = None
     if args.verify and not primary_only:
         img = step()
@@ -312,49 +347,75 @@ def main():
     ms_per_step = float(total_ms.item()) / args.steps
     value = rays_per_frame / (ms_per_step * 1e-3) / 1e6
 
-    # dominant kernel alone (CUDA events on its launching stream), for the roofline
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    kms = []
-    probe = torch.empty((D.tiles_for_rank(w, h, 0, world) * 256, 4), dtype=torch.float32, device=device)
-    for i in range(args.steps):
-        flush.fill_(i & 0xff)
-        stp = torch.cuda.current_stream(device).cuda_stream
-        k0.record()
-        if primary_only:
-            scene.trace_primary_device(cam, w, h, prim.data_ptr(), tbuf.data_ptr(), stream_ptr=stp, rank=rank, world=world, flags=args.flags)
-        else:
-            scene.render_tiles_device(cam, w, h, spp, bounces, probe.data_ptr(), stream_ptr=stp, integrator=args.integrator, flags=args.flags,
-                                      rank=rank, world=world)
-        k1.record()
-        torch.cuda.synchronize()
-        kms.append(k0.elapsed_time(k1))
-    kernel_ms = torch.tensor([sum(kms) / len(kms)], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(kernel_ms, op=dist.ReduceOp.MAX)
-    kernel_ms = float(kernel_ms.item())
+    # ---- roofline of the dominant kernel, measured live (CUDA events on the streams the kernels are launched on) ---------------------
     peak, peak_src = measured_peak()
-    rays_per_launch = rays_per_frame / world
-    achieved = rays_per_launch * bytes_per_ray / (kernel_ms * 1e-3) / 1e9
-
-    # the dominant kernel by itself: one more frame with every trace / shade launch bracketed by CUDA events on its launching
-    # stream (B200RT_FLAG_TIME_KERNELS; the tile groups then run one after the other, so this frame is slower than a timed step)
-    dominant = None
-    if not primary_only and args.integrator == 1:
+    probe = torch.empty((D.tiles_for_rank(w, h, 0, world) * 256, 4), dtype=torch.float32, device=device)
+    roofline = {"bound": "hbm", "kernel": kernel_name, "peak": peak, "unit": "GB/s", "peak_source": peak_src, "bytes_per_ray": bytes_per_ray,
+                "bound_note": "nominal: algorithmic bytes of the reference's data shapes over the measured HBM copy peak (SURVEY 8d); the BVH is "
+                              "L1/L2-resident, so DRAM is not what bounds the kernel: see 'ncu'"}
+    if primary_only or args.integrator != 1:
+        # one launch per step: the kernel's duration is the frame's render time
+        kms = []
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        for i in range(args.steps):
+            flush.fill_(i & 0xff)
+            k0.record()
+            if primary_only:
+                scene.trace_primary_device(cam, w, h, prim.data_ptr(), tbuf.data_ptr(), stream_ptr=cur_stream(), rank=rank, world=world, flags=args.flags)
+            else:
+                scene.render_tiles_device(cam, w, h, spp, bounces, probe.data_ptr(), stream_ptr=cur_stream(), integrator=args.integrator,
+                                          flags=args.flags, rank=rank, world=world)
+            k1.record()
+            torch.cuda.synchronize()
+            kms.append(k0.elapsed_time(k1))
+        kernel_ms = torch.tensor([sum(kms) / len(kms)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(kernel_ms, op=dist.ReduceOp.MAX)
+        kernel_ms = float(kernel_ms.item())
+        rays_per_launch = rays_per_frame / world
+        achieved = rays_per_launch * bytes_per_ray / (kernel_ms * 1e-3) / 1e9
+        roofline.update({"achieved": achieved, "frac": achieved / peak, "launches": 1, "avg_launch_ms": kernel_ms, "rays_per_launch": rays_per_launch})
+    else:
+        # Wavefront: the frame is ~3 400 launches on 3-4 overlapping streams. One more frame runs with every launch bracketed by CUDA
+        # events on its own group stream (B200RT_FLAG_TIME_INLINE: nothing serialised, same schedule as a timed step). achieved =
+        # algorithmic bytes of this rank's rays / the time during which at least one wf_trace_coop launch was running (the union of
+        # the launch intervals, <= ms_per_step); sum_launch_ms adds up the overlapping launches and may exceed the step.
         flush.fill_(7)
-        kst = scene.render_tiles_device(cam, w, h, spp, bounces, probe.data_ptr(), stream_ptr=torch.cuda.current_stream(device).cuda_stream,
-                                        integrator=args.integrator, flags=args.flags | rt.FLAG_TIME_KERNELS, rank=rank, world=world, want_stats=True)
-        if kst["trace_launches"] > 0 and kst["trace_ms"] > 0:
-            t_ach = kst["rays"] * bytes_per_ray / (kst["trace_ms"] * 1e-3) / 1e9
-            dominant = {"kernel": "wf_trace_coop" if not (args.flags & (rt.FLAG_BVH2 | rt.FLAG_DIAG_SLABS | rt.FLAG_SIMPLE_TRACE)) else "wf_trace",
-                        "launches": kst["trace_launches"], "avg_launch_ms": kst["trace_ms"] / kst["trace_launches"],
-                        "rays_per_launch": kst["rays"] / kst["trace_launches"], "achieved": t_ach, "frac": t_ach / peak,
-                        "share_of_kernel_time": kst["trace_ms"] / (kst["trace_ms"] + kst["shade_ms"]),
-                        "shade_avg_launch_ms": kst["shade_ms"] / max(1, kst["shade_launches"])}
+        t0e, t1e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0e.record()
+        kst = scene.render_tiles_device(cam, w, h, spp, bounces, probe.data_ptr(), stream_ptr=cur_stream(), integrator=args.integrator,
+                                        flags=args.flags | rt.FLAG_TIME_INLINE, rank=rank, world=world, want_stats=True)
+        t1e.record()
+        torch.cuda.synchronize()
+        frame_ms = t0e.elapsed_time(t1e)
+        union = max(kst["trace_union_ms"], 1e-9)
+        achieved = kst["rays"] * bytes_per_ray / (union * 1e-3) / 1e9
+        roofline.update({"achieved": achieved, "frac": achieved / peak, "launches": kst["trace_launches"],
+                         "avg_launch_ms": kst["trace_ms"] / max(1, kst["trace_launches"]), "sum_launch_ms": kst["trace_ms"],
+                         "union_launch_ms": kst["trace_union_ms"], "timed_frame_ms": frame_ms, "share_of_step": kst["trace_union_ms"] / frame_ms,
+                         "rays_per_launch": kst["rays"] / max(1, kst["trace_launches"]),
+                         "shade": {"kernel": "wf_shade", "launches": kst["shade_launches"], "sum_launch_ms": kst["shade_ms"],
+                                   "avg_launch_ms": kst["shade_ms"] / max(1, kst["shade_launches"])},
+                         "tail": {"kernel": "wf_tail", "launches": kst["tail_launches"], "sum_launch_ms": kst["tail_ms"]}})
+        # the same kernel with the machine to itself (B200RT_FLAG_TIME_KERNELS: groups one after the other, full persistent grid): round 1's figure
+        flush.fill_(9)
+        ast = scene.render_tiles_device(cam, w, h, spp, bounces, probe.data_ptr(), stream_ptr=cur_stream(), integrator=args.integrator,
+                                        flags=args.flags | rt.FLAG_TIME_KERNELS, rank=rank, world=world, want_stats=True)
+        if ast["trace_launches"] > 0 and ast["trace_ms"] > 0:
+            a_ach = ast["rays"] * bytes_per_ray / (ast["trace_ms"] * 1e-3) / 1e9
+            roofline["alone"] = {"launches": ast["trace_launches"], "avg_launch_ms": ast["trace_ms"] / ast["trace_launches"], "achieved": a_ach,
+                                 "frac": a_ach / peak, "share_of_kernel_time": ast["trace_ms"] / (ast["trace_ms"] + ast["shade_ms"])}
+    tpr = profile_traffic(args.workload + "_trace_bytes_per_ray")
+    roofline["traffic"] = (tpr * roofline["rays_per_launch"]) if (tpr and not primary_only and args.integrator == 1) else None
+    roofline["ncu"] = ncu_counters(args.workload)
 
-    # end to end through the public host API: host buffers in, host framebuffer out, copies inside the timed region
+    # ---- end to end through the public host API: pinned host buffers in and out, copies inside the timed region ---------------------
     e2e = None
     if world == 1:
-        fb = rt.Image(w, h).pixels
+        fbimg = rt.Image(w, h, pinned=True)
+        fb = fbimg.pixels
+        prim_h = rt.pinned_array((h, w), np.int32) if primary_only else None
+        t_h = rt.pinned_array((h, w), np.float32) if primary_only else None
         times = []
         stats = None
         for i in range(max(1, min(args.steps, 3))):
@@ -362,36 +423,48 @@ def main():
             torch.cuda.synchronize()
             t0 = time.perf_counter()
             if primary_only:
-                _, _, stats = scene.trace_primary(cam, w, h, flags=args.flags)
+                stats = scene.trace_primary_into(cam, w, h, prim_h, t_h, flags=args.flags)
             else:
                 _, stats = scene.render(cam, w, h, spp, bounces, framebuffer=fb, integrator=args.integrator, flags=args.flags)
             times.append(time.perf_counter() - t0)
         e_sec = sum(times) / len(times)
         e2e = {"value": rays_per_frame / e_sec / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(stats["h2d_bytes"]),
-               "d2h_bytes_per_step": int(stats["d2h_bytes"]), "api": "b200rt_trace_primary" if primary_only else "b200rt_render"}
+               "d2h_bytes_per_step": int(stats["d2h_bytes"]), "api": "b200rt_trace_primary" if primary_only else "b200rt_render",
+               "host_buffers": "page-locked (b200rt_host_alloc)"}
+        if not primary_only:
+            # the same frame leaving the GPU as the PNG's RGBA8 bytes (b200rt_render_rgba8: 4 B/pixel down instead of 16)
+            out8 = rt.pinned_array((h, w, 4), np.uint8)
+            t0 = time.perf_counter()
+            _, st8 = scene.render_rgba8(cam, w, h, spp, bounces, framebuffer=fb, out=out8, integrator=args.integrator, flags=args.flags)
+            e8 = time.perf_counter() - t0
+            e2e["rgba8"] = {"value": rays_per_frame / e8 / 1e6, "h2d_bytes_per_step": int(st8["h2d_bytes"]), "d2h_bytes_per_step": int(st8["d2h_bytes"]),
+                            "api": "b200rt_render_rgba8"}
     else:
         pinned = torch.empty((h, w, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
+        fb_host = torch.zeros((h, w, 4), dtype=torch.float32).pin_memory() if rank == 0 else None
+        if rank == 0:
+            fb_host[..., 3] = 1.0
         cam_host = torch.from_numpy(cam.as_array17()).pin_memory()
         cam_dev = torch.empty(17, dtype=torch.float32, device=device)
         barrier()
         t0 = time.perf_counter()
         n_e2e = max(1, min(args.steps, 3))
         for i in range(n_e2e):
-            cam_dev.copy_(cam_host, non_blocking=True)          # the frame's input
-            img = step()
+            cam_dev.copy_(cam_host, non_blocking=True)          # the frame's inputs: camera on every rank, the incoming framebuffer on rank 0
+            img = g.frame(fb_in_host=fb_host)
             if rank == 0:
                 pinned.copy_(img, non_blocking=True)
             torch.cuda.synchronize()
         barrier()
         e_sec = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=device)
         dist.all_reduce(e_sec, op=dist.ReduceOp.MAX)
-        e2e = {"value": rays_per_frame / float(e_sec.item()) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 68,
-               "d2h_bytes_per_step": w * h * 16, "api": "distributed.FrameGatherer.frame + D2H (rank 0)"}
+        e2e = {"value": rays_per_frame / float(e_sec.item()) / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": 68 + w * h * 16,
+               "d2h_bytes_per_step": w * h * 16, "api": "distributed.FrameGatherer.frame (pinned framebuffer up, gathered frame down, rank 0)"}
 
     # same frame with the rays that provably cannot change the image skipped (B200RT_FLAG_SKIP_DEAD_RAYS): reported next to
     # the headline, which keeps the reference's full ray set
     dead = None
-    if not primary_only:
+    if not primary_only and args.workload != "c5":
         g2 = D.make_cuda_gatherer(scene, cam, w, h, spp, bounces, rank, world, device, integrator=args.integrator,
                                   flags=args.flags | rt.binding.FLAG_SKIP_DEAD_RAYS)
         g2.frame()
@@ -424,38 +497,23 @@ def main():
         except Exception as e:          # the baseline is reported context, never a reason to lose the GPU numbers
             cpu_baseline = {"value": None, "unit": "Mrays/s", "cores": 0, "kind": "port", "sample": f"failed: {e}"}
 
-    # roofline of the dominant kernel (contract): algorithmic bytes per launch / its average launch duration, CUDA events on its
-    # launching stream. Path tracing: wf_trace_coop, every launch of one frame timed alone (B200RT_FLAG_TIME_KERNELS: one tile
-    # group at a time, full persistent grid); "frame" is the same arithmetic over the whole overlapped frame (trace + shade).
-    traffic_total = profile_traffic(args.workload)
-    frame_view = {"kernel": kernel_name, "achieved": achieved, "frac": achieved / peak, "kernel_ms": kernel_ms,
-                  "traffic": (traffic_total / world) if traffic_total else None}
-    if dominant:
-        tpr = profile_traffic(args.workload + "_trace_bytes_per_ray")
-        roofline = {"bound": "hbm", "kernel": dominant["kernel"], "achieved": dominant["achieved"], "peak": peak, "unit": "GB/s",
-                    "frac": dominant["frac"], "traffic": (tpr * dominant["rays_per_launch"]) if tpr else None,
-                    "bytes_per_ray": bytes_per_ray, "launches": dominant["launches"], "avg_launch_ms": dominant["avg_launch_ms"],
-                    "rays_per_launch": dominant["rays_per_launch"], "share_of_kernel_time": dominant["share_of_kernel_time"],
-                    "shade_avg_launch_ms": dominant["shade_avg_launch_ms"], "peak_source": peak_src, "frame": frame_view}
-    else:
-        roofline = {"bound": "hbm", "kernel": kernel_name, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                    "traffic": frame_view["traffic"], "bytes_per_ray": bytes_per_ray, "rays_per_launch": rays_per_launch,
-                    "kernel_ms": kernel_ms, "peak_source": peak_src}
-
     if rank == 0:
         info = scene.bvh_info()
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic (procedural stand-ins: the reference ships neither the Dragon OBJ nor the HDR skysphere)"
+            "data": ("the reference's own assets, ingested by the library" if "real assets" in desc else
+                     "synthetic (procedural stand-ins: the reference ships neither the Dragon OBJ nor the HDR skysphere)")
                     if args.workload != "c1" else "bundled cornell_pbr.obj (parsed by the reference, committed fixture)",
             "spp_per_s": (w * h * spp) / (ms_per_step * 1e-3),
             "rays_per_frame": rays_per_frame, "rays_per_sample": rays_per_frame / (w * h * spp),
             "config": {"workload": desc, "width": w, "height": h, "spp": spp, "max_bounces": bounces, "triangles": n_tri,
-                       "integrator": "megakernel" if args.integrator == 0 else "wavefront", "flags": args.flags,
-                       "partition": f"interleaved 16x16 tiles over {world} rank(s), scene replicated, NCCL gather to rank 0",
+                       "integrator": {0: "megakernel", 1: "wavefront", 2: "persistent"}[args.integrator], "flags": args.flags,
+                       "partition": f"interleaved 16x16 tiles over {world} rank(s), scene replicated, NCCL gather of mean-radiance tiles to rank 0, "
+                                    "framebuffer += / tone map there",
                        "l2": "256 MiB buffer written between timed iterations (L2 flush)",
-                       "bvh": {k: info[k] for k in ("n_inner_nodes", "n_leaves", "max_depth", "has_diag_slabs", "n_wide_nodes", "wide_max_depth")},
+                       "warmup_spp": warm_spp,
+                       "bvh": {k: info[k] for k in ("n_inner_nodes", "n_leaves", "max_depth", "has_diag_slabs", "n_wide_nodes", "wide_max_depth", "build_seconds")},
                        "scene_build_s": build_s, "scene_device_bytes": scene.device_bytes()},
             "skip_dead_rays": dead, "verified_equal_to_1_rank": verified,
             "clocks": sampler.result(),

@@ -208,6 +208,8 @@ typedef struct b200rt_stats
     double trace_ms, shade_ms;
     int trace_launches, shade_launches;
     double trace_union_ms;          /* B200RT_FLAG_TIME_INLINE only */
+    double tail_ms;                 /* B200RT_FLAG_TIME_INLINE only: summed duration of the barrier-free tail launches (csrc/persist.cu) */
+    int tail_launches;
 } b200rt_stats;
 
 void b200rt_default_render_options(b200rt_render_options* opts);
@@ -309,6 +311,13 @@ int b200rt_trace_rays_device(b200rt_scene* scene, const void* dev_rays6, int n_r
  * pixel: run it on the device right after a render and the frame leaves the GPU at a quarter of the bytes. */
 int b200rt_quantise_rgba8(const float* image_rgba, int width, int height, int flip_y, unsigned char* out_rgba8);
 int b200rt_quantise_rgba8_device(const void* dev_image_rgba, int width, int height, int flip_y, void* dev_out_rgba8, void* cuda_stream);
+
+/* The denoise stage of main.cpp:118-120 (Utils::OIDN_denoise, source/utils.cpp:144-196: OIDN "RT" filter on the tone-mapped beauty
+ * image alone, then out = blend * denoised + (1 - blend) * noisy, alpha 1). The reference does not ship OIDN's binaries or weights,
+ * so there is nothing to be bit-compatible with: this is an edge-avoiding a-trous wavelet filter (5 passes, colour-guided) in the same
+ * place — a functional stand-in, not a parity claim. channels: 3 (OIDN's float3 buffers) or 4 (Image). iterations <= 0
+ * and sigma <= 0 select the defaults (5, 0.45). in == out is allowed. Host pointers; runs on the current device. */
+int b200rt_denoise(const float* image, int channels, int width, int height, float blend_factor, int iterations, float sigma, float* out);
 
 const char* b200rt_last_error(void);
 const char* b200rt_version(void);

@@ -253,6 +253,16 @@ def env_alias_table(skysphere):
     return prob, alias, total.value
 
 
+def OIDN_denoise(image, blend_factor: float = 1.0, iterations: int = 0, sigma: float = 0.0) -> np.ndarray:
+    """The denoise stage of main.cpp:118-120 (Utils::OIDN_denoise, utils.cpp:144-196) on the GPU: an edge-avoiding a-trous filter
+    standing in for OIDN (whose binaries the reference does not ship), then blend * denoised + (1 - blend) * noisy. (h, w, 3|4)."""
+    img = _f32(image.pixels if isinstance(image, Image) else image)
+    h, w, ch = img.shape
+    out = np.empty_like(img)
+    B.check(B.load_library().b200rt_denoise(B.fptr(img), ch, w, h, blend_factor, iterations, sigma, B.fptr(out)))
+    return out
+
+
 def quantise_rgba8(image, flip_y: bool = True) -> np.ndarray:
     """write_image_png's quantisation (image_io.cpp:165-182) on the GPU: (h, w, 4) float32 -> (h, w, 4) uint8."""
     img = _f32(image)
@@ -489,6 +499,16 @@ class Scene:
         B.check(B.load_library().b200rt_trace_primary(self._h, B.fptr(camera.as_array17()), w, h, sample, spp_for_seed,
                                                       B.iptr(prim), B.fptr(t), C.byref(o), C.byref(st)))
         return prim, t, st.as_dict()
+
+    def trace_primary_into(self, camera: Camera, w: int, h: int, prim: np.ndarray, t: np.ndarray, sample: int = -1, spp_for_seed: int = 1,
+                           flags: int = 0):
+        """trace_primary into caller-owned (e.g. page-locked) (h, w) int32 / float32 arrays; returns the stats."""
+        assert prim.dtype == np.int32 and t.dtype == np.float32 and prim.shape == (h, w) and t.shape == (h, w)
+        st = B.Stats()
+        o = self._opts(0, flags, 0, 1)
+        B.check(B.load_library().b200rt_trace_primary(self._h, B.fptr(camera.as_array17()), w, h, sample, spp_for_seed,
+                                                      B.iptr(prim), B.fptr(t), C.byref(o), C.byref(st)))
+        return st.as_dict()
 
     def trace_rays(self, rays6, any_hit: bool = False, flags: int = 0):
         rays6 = _f32(rays6).reshape(-1, 6)

@@ -457,7 +457,7 @@ int fill_kernel_times(b200rt_scene* s, b200rt_stats* stats)
 {
     stats->trace_ms = s->kernel_times[0]; stats->shade_ms = s->kernel_times[1];
     stats->trace_launches = (int)s->kernel_times[2]; stats->shade_launches = (int)s->kernel_times[3];
-    stats->trace_union_ms = 0.0;
+    stats->trace_union_ms = 0.0; stats->tail_ms = 0.0; stats->tail_launches = 0;
     if (s->timeline_valid)
     {
         WfTimelineSummary t;
@@ -465,6 +465,7 @@ int fill_kernel_times(b200rt_scene* s, b200rt_stats* stats)
         stats->trace_ms = t.trace_ms; stats->shade_ms = t.shade_ms;
         stats->trace_launches = t.trace_launches; stats->shade_launches = t.shade_launches;
         stats->trace_union_ms = t.trace_union_ms;
+        stats->tail_ms = t.tail_ms; stats->tail_launches = t.tail_launches;
     }
     return B200RT_OK;
 }
@@ -1511,6 +1512,31 @@ int b200rt_quantise_rgba8(const float* image_rgba, int w, int h, int flip_y, uns
     } while (0);
     cudaFree(d_in); cudaFree(d_out);
     if (e != cudaSuccess) return fail(B200RT_ERR_CUDA, "quantise_rgba8: %s", cudaGetErrorString(e));
+    return B200RT_OK;
+}
+
+int b200rt_denoise(const float* image, int channels, int w, int h, float blend, int iterations, float sigma, float* out)
+{
+    if (!image || !out || w <= 0 || h <= 0 || (channels != 3 && channels != 4)) return fail(B200RT_ERR_ARG, "bad denoise arguments");
+    int n_dev = 0;
+    if (cudaGetDeviceCount(&n_dev) != cudaSuccess || n_dev <= 0) return fail(B200RT_ERR_CUDA, "no CUDA device: b200rt has no CPU fallback");
+    if (iterations <= 0) iterations = 5;
+    if (iterations > 8) iterations = 8;
+    if (!(sigma > 0.0f)) sigma = 0.45f;
+    const size_t bytes = (size_t)w * h * channels * sizeof(float);
+    float *d_in = nullptr, *d_tmp = nullptr, *d_out = nullptr;
+    cudaError_t e = cudaSuccess;
+    do
+    {
+        if ((e = cudaMalloc(&d_in, bytes)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&d_tmp, bytes)) != cudaSuccess) break;
+        if ((e = cudaMalloc(&d_out, bytes)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(d_in, image, bytes, cudaMemcpyHostToDevice)) != cudaSuccess) break;
+        if ((e = launch_denoise(d_in, channels, w, h, iterations, sigma, blend, d_tmp, d_out, 0)) != cudaSuccess) break;
+        if ((e = cudaMemcpy(out, d_out, bytes, cudaMemcpyDeviceToHost)) != cudaSuccess) break;
+    } while (0);
+    cudaFree(d_in); cudaFree(d_tmp); cudaFree(d_out);
+    if (e != cudaSuccess) return fail(B200RT_ERR_CUDA, "denoise: %s", cudaGetErrorString(e));
     return B200RT_OK;
 }
 

@@ -38,6 +38,10 @@ cudaError_t launch_env_cdf_search(const SceneDev& S, const float* values, int n,
 cudaError_t launch_rng_stream(int x, int y, int spp, int n, uint32_t* state_out, float* floats_out, cudaStream_t stream);
 cudaError_t launch_quantise_rgba8(const float4* image, int w, int h, int flip_y, void* out_rgba8, cudaStream_t stream);
 
+// output stage: edge-avoiding a-trous denoiser (denoise.cu)
+cudaError_t launch_denoise(const float* d_in, int channels, int w, int h, int iterations, float sigma, float blend, float* d_tmp, float* d_out,
+                           cudaStream_t stream);
+
 // K5 env tables (env_tables.cu)
 cudaError_t launch_env_expand_rgb(const float* rgb, size_t n, float4* rgba, cudaStream_t stream);
 cudaError_t launch_env_luminance(const float4* env, size_t n, float* lum, cudaStream_t stream);
@@ -54,14 +58,15 @@ struct WfTimeline
     std::vector<cudaEvent_t> pool;
     size_t used = 0;
     std::vector<Launch> launches;
+    std::vector<Launch> tails;                            // barrier-free tail launches (e0 .. e1; e2 unused)
     cudaEvent_t origin = nullptr;                         // recorded on the caller's stream at the fork
     cudaEvent_t take();
-    void reset() { used = 0; launches.clear(); }
+    void reset() { used = 0; launches.clear(); tails.clear(); }
     void destroy();
 };
 // sums (ms) and launch counts of the recorded frame, and the length of the union of the trace kernels' intervals: the time during
 // which at least one trace kernel was running. The frame must have completed (stream synchronised).
-struct WfTimelineSummary { double trace_ms, shade_ms, trace_union_ms; int trace_launches, shade_launches; };
+struct WfTimelineSummary { double trace_ms, shade_ms, trace_union_ms, tail_ms; int trace_launches, shade_launches, tail_launches; };
 cudaError_t wavefront_timeline_summary(const WfTimeline& tl, WfTimelineSummary* out);
 
 // wavefront integrator (wavefront.cu): runs the whole frame for this rank's tiles as n_groups independent interleaved

@@ -305,7 +305,7 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
     static const int tail_pct = []() { const char* e = getenv("B200RT_WF_TAIL_PCT"); int v = e ? atoi(e) : 20; return v < 0 ? 0 : (v > 100 ? 100 : v); }();
     static const long long tail_cap = []() { const char* e = getenv("B200RT_WF_TAIL_CAP"); return e ? atoll(e) : 30000ll; }();
     static const int tail_min = []() { const char* e = getenv("B200RT_WF_TAIL_MIN"); return e ? atoi(e) : 16384; }();
-    const bool tail_ok = coop && tail_pct > 0 && !timing && !(P.flags & B200RT_FLAG_TIME_INLINE);
+    const bool tail_ok = coop && tail_pct > 0 && !timing;
     const int tail_ctas = tail_ok ? std::max(1, wavefront_tail_max_ctas() / n_groups) : 0;
     GroupRun run[kMaxWfGroups];
     for (int g = 0; g < n_groups; g++)
@@ -333,7 +333,10 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
         if (tail_ok && G.buf.n_slots <= tail_min)
         {
             // a group this small is latency-bound from its first pass on: barrier-free from the start
+            WfTimeline::Launch tlt = { g, 0, 0, 0 };
+            if (tln) { tlt.e0 = tln->used; cudaEventRecord(tln->take(), G.stream); }
             WF_TRY(launch_wavefront_tail(S, R.P, G.buf, tail_ctas, fb_in_rowmajor, out_tiles, G.stream));
+            if (tln) { tlt.e1 = tln->used; cudaEventRecord(tln->take(), G.stream); tln->tails.push_back(tlt); }
             launches += 2;
             R.finished = true;
         }
@@ -360,7 +363,10 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
                 if (tail_ok && *G.host_active <= R.tail_below)
                 {
                     // few pixels left: no more passes; one barrier-free launch finishes them (persist.cu), behind the passes already queued
+                    WfTimeline::Launch tlt = { g, 0, 0, 0 };
+                    if (tln) { tlt.e0 = tln->used; cudaEventRecord(tln->take(), G.stream); }
                     WF_TRY(launch_wavefront_tail(S, R.P, G.buf, tail_ctas, fb_in_rowmajor, out_tiles, G.stream));
+                    if (tln) { tlt.e1 = tln->used; cudaEventRecord(tln->take(), G.stream); tln->tails.push_back(tlt); }
                     launches += 2;
                     R.finished = true; remaining--;
                     continue;
@@ -453,7 +459,14 @@ void WfTimeline::destroy()
 
 cudaError_t wavefront_timeline_summary(const WfTimeline& tl, WfTimelineSummary* out)
 {
-    WfTimelineSummary s = { 0.0, 0.0, 0.0, 0, 0 };
+    WfTimelineSummary s = { 0.0, 0.0, 0.0, 0.0, 0, 0, 0 };
+    for (const WfTimeline::Launch& L : tl.tails)
+    {
+        float a = 0.0f;
+        const cudaError_t e = cudaEventElapsedTime(&a, tl.pool[L.e0], tl.pool[L.e1]);
+        if (e != cudaSuccess) return e;
+        s.tail_ms += a; s.tail_launches++;
+    }
     std::vector<std::pair<float, float>> iv;
     iv.reserve(tl.launches.size());
     for (const WfTimeline::Launch& L : tl.launches)

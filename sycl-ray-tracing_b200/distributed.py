@@ -55,14 +55,14 @@ class FrameGatherer:
     """Owns the per-rank tile buffer, the gathered buffer and the final image (rank 0) and runs
     fill -> gather -> untile for one frame."""
 
-    def __init__(self, w: int, h: int, rank: int, world: int, device, fill_tiles, untile, channels: int = 4):
+    def __init__(self, w: int, h: int, rank: int, world: int, device, fill_tiles, untile, channels: int = 4, init_image=None):
         import torch
         import torch.distributed as dist
         self.torch, self.dist = torch, dist
         self.w, self.h, self.rank, self.world = w, h, rank, world
         self.tiles_padded = tiles_for_rank(w, h, 0, world)
         self.n_my_tiles = tiles_for_rank(w, h, rank, world)
-        self.fill_tiles, self.untile = fill_tiles, untile
+        self.fill_tiles, self.untile, self.init_image = fill_tiles, untile, init_image
         self.tiles = torch.zeros((self.tiles_padded * TILE_PX, channels), dtype=torch.float32, device=device)
         self.gathered = None
         self.image = None
@@ -70,8 +70,12 @@ class FrameGatherer:
             self.gathered = torch.zeros((world, self.tiles_padded * TILE_PX, channels), dtype=torch.float32, device=device)
             self.image = torch.zeros((h, w, channels), dtype=torch.float32, device=device)
 
-    def frame(self):
-        """Renders this rank's tiles, gathers to rank 0 and un-tiles there. Returns the image tensor on rank 0, else None."""
+    def frame(self, fb_in_host=None):
+        """Renders this rank's tiles, gathers to rank 0 and un-tiles there. Returns the image tensor on rank 0, else None.
+        fb_in_host (rank 0, optional): the incoming framebuffer as a pinned host tensor (h, w, 4), copied up inside the frame;
+        default Color::Black(). The un-tile step does `framebuffer += final; tone map` (render_kernel.cpp:169-180) on it."""
+        if self.rank == 0 and self.image is not None and self.init_image is not None:
+            self.init_image(self.image, fb_in_host)
         self.fill_tiles(self.tiles)
         if self.world > 1:
             if self.rank == 0:
@@ -88,19 +92,30 @@ class FrameGatherer:
 
 
 def make_cuda_gatherer(scene, camera, w, h, spp, max_bounces, rank, world, device, integrator=0, flags=0):
-    """FrameGatherer whose fill/untile steps are the CUDA kernels, launched on torch's current stream."""
+    """FrameGatherer whose fill/untile steps are the CUDA kernels, launched on torch's current stream. Every rank renders its tiles
+    as mean radiance (B200RT_FLAG_LINEAR_TILES); rank 0 holds the incoming framebuffer and does `framebuffer += final; tone map`
+    while un-tiling the gathered buffer (b200rt_untile_accumulate_device), so the incoming framebuffer is honoured without
+    shipping it to every rank."""
     import torch
+    from .binding import FLAG_LINEAR_TILES
 
     def fill(tiles):
         st = torch.cuda.current_stream(device).cuda_stream
         scene.render_tiles_device(camera, w, h, spp, max_bounces, tiles.data_ptr(), stream_ptr=st, integrator=integrator,
-                                  flags=flags, rank=rank, world=world)
+                                  flags=flags | FLAG_LINEAR_TILES, rank=rank, world=world)
 
     g = None
+    black = torch.tensor([0.0, 0.0, 0.0, 1.0], dtype=torch.float32, device=device)
+
+    def init_image(image, fb_in_host):
+        if fb_in_host is not None:
+            image.copy_(fb_in_host, non_blocking=True)
+        else:
+            image.copy_(black.expand_as(image))           # Color::Black(), image.h:34
 
     def untile(src, image):
         st = torch.cuda.current_stream(device).cuda_stream
-        scene.untile_device(src.data_ptr(), g.tiles_padded, world, w, h, image.data_ptr(), stream_ptr=st)
+        scene.untile_accumulate_device(src.data_ptr(), g.tiles_padded, world, w, h, image.data_ptr(), stream_ptr=st)
 
-    g = FrameGatherer(w, h, rank, world, device, fill, untile)
+    g = FrameGatherer(w, h, rank, world, device, fill, untile, init_image=init_image)
     return g

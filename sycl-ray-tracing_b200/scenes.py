@@ -113,6 +113,69 @@ def c5_scene(n_instances: int = 200, nu: int = 500, nv: int = 100, seed: int = 7
                 env=procedural_sky(sky_w, sky_h), camera=Camera.PBRT_DRAGON_CAMERA)
 
 
+def torus_knot(nu: int = 2000, nv: int = 250, seed: int = 42, p: int = 2, q: int = 3, scale: float = 1.15, tube: float = 0.52,
+               center=(0.0, 0.2, 0.0)) -> np.ndarray:
+    """Displaced (p, q) torus-knot tube, 2*nu*nv triangles (1 000 000 at the default size), outward wound: the concave
+    Dragon-class stand-in SURVEY §8d prefers (self-occlusion and inter-reflection between the strands, unlike the near-convex
+    displaced sphere). Curve C(t) = ((2 + cos q t) cos p t, sin q t, (2 + cos q t) sin p t) * scale; tube radius
+    tube * (1 + 0.18 sin(9 t) sin(4 phi)) + 0.025 hash(i, j, seed); frame by parallel transport of the curve's normal."""
+    t = 2.0 * np.pi * np.arange(nu) / nu
+    c = np.stack([(2.0 + np.cos(q * t)) * np.cos(p * t), np.sin(q * t), (2.0 + np.cos(q * t)) * np.sin(p * t)], axis=-1) * scale
+    d = np.stack([-q * np.sin(q * t) * np.cos(p * t) - p * (2.0 + np.cos(q * t)) * np.sin(p * t), q * np.cos(q * t),
+                  -q * np.sin(q * t) * np.sin(p * t) + p * (2.0 + np.cos(q * t)) * np.cos(p * t)], axis=-1)
+    tan = d / np.linalg.norm(d, axis=-1, keepdims=True)
+    # a smooth normal field: remove the tangent component from the vector pointing away from the knot's axis (never parallel to it)
+    radial = np.stack([np.cos(p * t), np.zeros_like(t), np.sin(p * t)], axis=-1)
+    n1 = radial - (radial * tan).sum(-1, keepdims=True) * tan
+    n1 /= np.linalg.norm(n1, axis=-1, keepdims=True)
+    n2 = np.cross(tan, n1)
+    phi = 2.0 * np.pi * np.arange(nv) / nv
+    ii = np.broadcast_to(np.arange(nu)[:, None], (nu, nv)); jj = np.broadcast_to(np.arange(nv)[None, :], (nu, nv))
+    r = tube * (1.0 + 0.18 * np.sin(9.0 * t)[:, None] * np.sin(4.0 * phi)[None, :]) + 0.025 * _hash01(ii, jj, seed)
+    P = c[:, None, :] + r[..., None] * (np.cos(phi)[None, :, None] * n1[:, None, :] + np.sin(phi)[None, :, None] * n2[:, None, :])
+    P = (P + np.asarray(center, np.float64)).astype(np.float32)
+    a = P
+    b = np.roll(P, -1, axis=1)
+    cc = np.roll(P, -1, axis=0)
+    dd = np.roll(np.roll(P, -1, axis=0), -1, axis=1)
+    t0 = np.concatenate([a, b, dd], axis=-1); t1 = np.concatenate([a, dd, cc], axis=-1)
+    return np.ascontiguousarray(np.stack([t0, t1], axis=2).reshape(-1, 9), np.float32)
+
+
+def c3_knot_scene(roughness: float = 0.25, metalness: float = 1.0, nu: int = 2000, nv: int = 250, sky_w: int = 2048, sky_h: int = 1024):
+    """C3 with the concave stand-in: the displaced torus knot (material 1) over the same ground, sky, camera and materials."""
+    mesh = torus_knot(nu, nv)
+    tri = np.concatenate([mesh, ground_quad()], axis=0)
+    mat_idx = np.concatenate([np.ones(len(mesh), np.int32), np.full(2, 2, np.int32)])
+    mats = np.array([DEFAULT_MATERIAL, [0, 0, 0, 1, 1.0, 0.71, 0.29, 1, metalness, max(roughness, 1.0e-2)],
+                     [0, 0, 0, 1, 0.8, 0.8, 0.8, 1, 1.0, 0.4]], np.float32)
+    return dict(tri9=tri, mat_idx=mat_idx, mats10=mats, emissive=np.zeros(0, np.int32), env=procedural_sky(sky_w, sky_h),
+                camera=Camera.PBRT_DRAGON_CAMERA)
+
+
+# the reference's own default assets (source/main.cpp:34-35); both are missing from the repository (.MISSING_LARGE_BLOBS) and are picked
+# up when somebody drops them in
+DRAGON_OBJ = "data/OBJs/pbrt_dragon.obj"
+DRAGON_SKY = "data/Skyspheres/evening_road_01_puresky_2k.hdr"
+
+
+def find_real_dragon(roots) -> tuple | None:
+    import os
+    for r in roots:
+        if r and os.path.exists(os.path.join(r, DRAGON_OBJ)) and os.path.exists(os.path.join(r, DRAGON_SKY)):
+            return os.path.join(r, DRAGON_OBJ), os.path.join(r, DRAGON_SKY)
+    return None
+
+
+def real_dragon_scene(obj_path: str, sky_path: str):
+    """C3 on the reference's real assets, ingested by the library itself (b200rt_obj_load / b200rt_hdr_load)."""
+    from .api import parse_obj, read_image_float
+    o = parse_obj(obj_path)
+    o["env"] = read_image_float(sky_path)          # (h, w, 3): expanded to RGBA on the device
+    o["camera"] = Camera.PBRT_DRAGON_CAMERA
+    return o
+
+
 def algorithmic_bytes_per_ray(n_tri: int) -> int:
     """one root-to-leaf descent over the reference's data shapes (octree fan-out 8, 56-byte 7-slab
     volumes, 8 x 36-byte triangles per leaf): 24 + ceil(log8(max(N,8)/8)) * 8*56 + 8*36 + 8."""

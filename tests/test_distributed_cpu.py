@@ -40,6 +40,21 @@ def _worker(rank, world, port, w, h, out_path):
         img = g.frame()
     if rank == 0:
         np.save(out_path, img.numpy())
+
+    # the accumulating flavour (what make_cuda_gatherer wires up): rank 0 starts every frame from the incoming framebuffer and the
+    # un-tile step adds the gathered tiles to it — a second frame must not see the first one's result
+    def init_image(image, fb_in_host):
+        image.copy_(fb_in_host if fb_in_host is not None else torch.zeros_like(image))
+
+    def untile_add(src, image):
+        image.add_(torch.from_numpy(D.untile_numpy(src.numpy(), w, h, world)))
+
+    g2 = D.FrameGatherer(w, h, rank, world, torch.device("cpu"), fill, untile_add, init_image=init_image)
+    fb = torch.full((h, w, 4), 1000.0) if rank == 0 else None
+    for _ in range(2):
+        img2 = g2.frame(fb_in_host=fb)
+    if rank == 0:
+        np.save(out_path.replace(".npy", "_acc.npy"), img2.numpy())
     dist.barrier()
     dist.destroy_process_group()
 
@@ -56,3 +71,5 @@ def test_gloo_tile_gather_reassembles_frame(tmp_path, world, w, h):
     tiles_x = (w + 15) // 16
     owner = ((ys // 16) * tiles_x + xs // 16) % world
     assert np.array_equal(img[..., 2], owner), "pixel written by the rank that owns its tile"
+    acc = np.load(out.replace(".npy", "_acc.npy"))
+    assert np.array_equal(acc, img + 1000.0), "framebuffer += gathered tiles, once per frame"

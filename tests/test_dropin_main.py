@@ -1,6 +1,6 @@
 """-m gpu: the reference's UNMODIFIED source/main.cpp, linked against the drop-in RenderKernel
 (sycl-ray-tracing_b200/host/dropin, built in the build container where /root/reference exists; the binary travels with
-the repo snapshot), renders an OBJ + MTL + HDR from disk on the GPU and writes RT_output.png. The PNG must match a render
+the repo snapshot), renders an OBJ + MTL + HDR from disk on the GPU, denoises on the GPU and writes its four PNGs. The PNG must match a render
 of the same scene through the Python mirror."""
 import os
 import subprocess
@@ -76,8 +76,15 @@ def test_reference_main_cpp_drives_the_b200_path(rt, tmp_path):
     diff = np.abs(png.astype(np.int32) - expect.astype(np.int32))
     assert (diff <= 1).mean() > 0.995, f"{(diff > 1).sum()} of {diff.size} bytes differ by more than one level"
     assert png[..., :3].std() > 10, "the frame must not be blank"
-    for name in ("RT_output_denoised_1.png", "RT_output_denoised_0.75.png", "RT_output_denoised_0.5.png"):
-        assert os.path.exists(tmp_path / name)          # main.cpp:118-125 ran to the end
+    # main.cpp:118-125 ran to the end: three blends of the denoised frame. The OIDN entry points are served by the library's GPU denoise
+    # stage (host/dropin/b200rt_oidn.c): blend 1 must equal b200rt_denoise of the frame, the others lie between it and the noisy frame
+    den = rt.OIDN_denoise(np.ascontiguousarray(img[..., :3]))
+    for name, blend in (("RT_output_denoised_1.png", 1.0), ("RT_output_denoised_0.75.png", 0.75), ("RT_output_denoised_0.5.png", 0.5)):
+        assert os.path.exists(tmp_path / name)
+        p = np.asarray(PILImage.open(tmp_path / name).convert("RGBA")).astype(np.int32)
+        want = np.clip((blend * den + (1.0 - blend) * img[..., :3]) * np.float32(255.0), 0, 255).astype(np.uint8)[::-1].astype(np.int32)
+        assert (np.abs(p[..., :3] - want) <= 1).mean() > 0.995, name
+    assert (np.asarray(PILImage.open(tmp_path / "RT_output_denoised_1.png").convert("RGBA")) != png).mean() > 0.05, "the denoised frame is really filtered"
     # the same unmodified main.cpp on several ranks behind the boundary (b200rt_scene_create_multi): B200RT_GPUS=2 when the box has two
     # GPUs, and B200RT_DEVICE_LIST=0,0,0 (three ranks sharing the one device) everywhere. The PNG must be byte-identical.
     import torch

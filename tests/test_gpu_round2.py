@@ -512,3 +512,28 @@ def test_env_cdf_search_guide_is_exact(rt):
     guided = sc.env_cdf_search(v, use_guide=True)
     assert np.array_equal(plain, guided), f"{(plain != guided).any(axis=1).sum()} values pick another texel through the guide"
     assert np.array_equal(plain[:, 1], y) and np.array_equal(plain[:20000, 0], x)
+
+
+def test_denoise_stage(rt, golden_cameras):
+    """b200rt_denoise (the stage Utils::OIDN_denoise occupies, utils.cpp:144-196): not OIDN, so no parity claim — functional checks:
+    a constant image is a fixed point, blend 0 returns the input, a clean step edge stays a step, and on a noisy 4-spp render the
+    filtered frame is closer to the 1024-spp frame than the noisy one (RMSE), for float3 and RGBA layouts alike."""
+    from sycl_ray_tracing_b200 import scenes
+    const = np.full((40, 60, 3), 0.37, np.float32)
+    assert np.allclose(rt.OIDN_denoise(const), const, atol=1e-6)
+    step = np.zeros((64, 64, 4), np.float32); step[:, 32:, :3] = 0.9; step[..., 3] = 2.5
+    out = rt.OIDN_denoise(step)
+    assert np.abs(out[..., :3] - step[..., :3]).max() < 2e-3 and np.allclose(out[..., 3], 1.0), "edges survive; alpha -> 1 (utils.cpp:186)"
+    c3 = scenes.c3_scene(nu=100, nv=50, sky_w=64, sky_h=32)
+    sc = scene_of(rt, c3)
+    noisy, _ = sc.render(c3["camera"], 320, 180, 4, 8)
+    ref, _ = sc.render(c3["camera"], 320, 180, 1024, 8)
+    assert np.array_equal(bits(rt.OIDN_denoise(noisy, blend_factor=0.0)[..., :3]), bits(noisy[..., :3]))
+    den4 = rt.OIDN_denoise(noisy)
+    den3 = rt.OIDN_denoise(np.ascontiguousarray(noisy[..., :3]))
+    assert np.array_equal(bits(den4[..., :3]), bits(den3))
+    rmse = lambda a: float(np.sqrt(((a[..., :3].astype(np.float64) - ref[..., :3]) ** 2).mean()))
+    half = rt.OIDN_denoise(noisy, blend_factor=0.5)
+    print("rmse noisy", rmse(noisy), "denoised", rmse(den4), "blend 0.5", rmse(half))
+    assert rmse(den4) < 0.8 * rmse(noisy) and rmse(den4) < rmse(half) < rmse(noisy)
+    assert np.allclose(half[..., :3], 0.5 * den4[..., :3] + 0.5 * noisy[..., :3], atol=1e-6)
