@@ -4,8 +4,13 @@
 // Only the closest-hit RESULT is contractual, not the tree shape, so this is a linear BVH:
 //   1. per-triangle boxes, scene bounds                                   (lb_bounds)
 //   2. 63-bit Morton codes of the box centres, radix sort                 (lb_morton, cub::DeviceRadixSort — library call, one-shot setup)
-//   3. binary radix tree over the sorted codes, all nodes in parallel     (lb_tree; Karras, "Maximizing parallelism in the construction of BVHs...", HPG 2012)
-//   4. bottom-up box fit with one atomic counter per node                 (lb_fit)
+//   3. binary tree over the sorted triangles by PARALLEL LOCALLY-ORDERED CLUSTERING (pl_*; Meister & Bittner, "Parallel locally-ordered
+//      clustering for bounding volume hierarchy construction", TVCG 2018): every cluster looks 16 places left and right along the
+//      Morton curve for the neighbour whose merged box has the smallest surface area; mutual nearest neighbours merge; repeat
+//      (~30 rounds). A surface-area-driven agglomerative build: round 1 built the radix tree of the Morton codes instead (Karras 2012,
+//      still available as B200RT_DEVICE_BUILDER=lbvh: lb_tree + lb_fit), whose splits ignore surface area — path tracing was 8-13 %
+//      and coherent camera rays 57 % slower on its trees than on the host builder's binned-SAH ones
+//   4. the clustered tree is laid out depth-first (pl_layout): every subtree covers a contiguous range of the triangle order
 //   5. subtrees of <= 3 triangles become leaves; level-by-level collapse into the 8-ary layout: every wide node opens its
 //      largest children until it has 8, assigns them to octant slots     (lw_expand, lw_link; prefix sums give child_base / tri_base)
 //   6. emit: quantised 80-byte wide nodes + the leaf-ordered triangle stream (lw_emit), binary two-children records (lb_emit)
@@ -18,6 +23,7 @@
 #include <cfloat>
 #include <chrono>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -201,6 +207,129 @@ __global__ void lb_fit(DevArrays A, int* max_depth)
     }
     for (int o = 16; o > 0; o >>= 1) depth = max(depth, __shfl_xor_sync(0xffffffffu, depth, o));
     if ((threadIdx.x & 31) == 0) atomicMax(max_depth, depth);
+}
+
+// ---- parallel locally-ordered clustering -----------------------------------------------------------------------------------------
+constexpr int kPlocRadius = 16;
+constexpr int kPlocBlock = 256;
+
+struct PlocArrays
+{
+    int *cid[2];                   // cluster -> tree reference (inner node index, or sorted position | kLeafBit), ping-pong
+    float4 *clo[2], *chi[2];       // cluster boxes, ping-pong
+    int* nn;                       // nearest neighbour (cluster index)
+    int* valid;                    // 1: the cluster survives this round (merged clusters live at the lower index)
+    int* pos;                      // exclusive scan of valid
+    int* size;                     // per inner node: triangles below
+    int* next_node;                // next free inner node index (counts down to 0: the root is created last)
+};
+
+__device__ __forceinline__ float union_area(float4 alo, float4 ahi, float4 blo, float4 bhi)
+{
+    const float dx = fmaxf(ahi.x, bhi.x) - fminf(alo.x, blo.x), dy = fmaxf(ahi.y, bhi.y) - fminf(alo.y, blo.y), dz = fmaxf(ahi.z, bhi.z) - fminf(alo.z, blo.z);
+    return dx * dy + dy * dz + dz * dx;
+}
+
+// nearest neighbour within kPlocRadius places. Pairs are ordered by (area, lower index, higher index): a total order, so the globally
+// best pair is always mutual and every round merges at least one pair.
+__global__ void __launch_bounds__(kPlocBlock) pl_nearest(const float4* __restrict__ clo, const float4* __restrict__ chi, int n, int* __restrict__ nn)
+{
+    __shared__ float4 slo[kPlocBlock + 2 * kPlocRadius], shi[kPlocBlock + 2 * kPlocRadius];
+    const int base = blockIdx.x * kPlocBlock - kPlocRadius;
+    for (int t = threadIdx.x; t < kPlocBlock + 2 * kPlocRadius; t += kPlocBlock)
+    {
+        const int g = base + t;
+        if (g >= 0 && g < n) { slo[t] = clo[g]; shi[t] = chi[g]; }
+    }
+    __syncthreads();
+    const int i = blockIdx.x * kPlocBlock + threadIdx.x;
+    if (i >= n) return;
+    const float4 lo = slo[threadIdx.x + kPlocRadius], hi = shi[threadIdx.x + kPlocRadius];
+    float best = FLT_MAX; int bj = -1;
+    for (int d = -kPlocRadius; d <= kPlocRadius; d++)
+    {
+        const int j = i + d;
+        if (d == 0 || j < 0 || j >= n) continue;
+        const float a = union_area(lo, hi, slo[threadIdx.x + kPlocRadius + d], shi[threadIdx.x + kPlocRadius + d]);
+        // (area, min(i, j), max(i, j)) lexicographic; candidates come in increasing j
+        bool better = a < best;
+        if (!better && a == best && bj >= 0)
+        {
+            const int m0 = min(i, j), m1 = max(i, j), b0 = min(i, bj), b1 = max(i, bj);
+            better = m0 < b0 || (m0 == b0 && m1 < b1);
+        }
+        if (better || bj < 0) { best = a; bj = j; }
+    }
+    nn[i] = bj;
+}
+
+__global__ void pl_merge(DevArrays A, PlocArrays P, int cur, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int j = P.nn[i];
+    if (j < 0 || P.nn[j] != i) { P.valid[i] = 1; return; }          // no mutual neighbour this round: carried over unchanged
+    if (i > j) { P.valid[i] = 0; return; }                         // the pair lives on at the lower index
+    const int node = atomicSub(P.next_node, 1);
+    const int L = P.cid[cur][i], R = P.cid[cur][j];
+    A.left[node] = L; A.right[node] = R;
+    if (L & kLeafBit) A.parent_leaf[L & ~kLeafBit] = node; else A.parent_node[L] = node;
+    if (R & kLeafBit) A.parent_leaf[R & ~kLeafBit] = node; else A.parent_node[R] = node;
+    const float4 alo = P.clo[cur][i], ahi = P.chi[cur][i], blo = P.clo[cur][j], bhi = P.chi[cur][j];
+    const float4 lo = make_float4(fminf(alo.x, blo.x), fminf(alo.y, blo.y), fminf(alo.z, blo.z), 0.0f);
+    const float4 hi = make_float4(fmaxf(ahi.x, bhi.x), fmaxf(ahi.y, bhi.y), fmaxf(ahi.z, bhi.z), 0.0f);
+    A.nlo[node] = lo; A.nhi[node] = hi;
+    P.size[node] = ((L & kLeafBit) ? 1 : P.size[L]) + ((R & kLeafBit) ? 1 : P.size[R]);
+    P.cid[cur][i] = node; P.clo[cur][i] = lo; P.chi[cur][i] = hi;
+    P.valid[i] = 1;
+}
+
+__global__ void pl_compact(PlocArrays P, int cur, int n)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n || !P.valid[i]) return;
+    const int o = P.pos[i];
+    P.cid[cur ^ 1][o] = P.cid[cur][i]; P.clo[cur ^ 1][o] = P.clo[cur][i]; P.chi[cur ^ 1][o] = P.chi[cur][i];
+}
+
+__global__ void pl_init(DevArrays A, PlocArrays P)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n) return;
+    const int t = A.vals[i];
+    P.cid[0][i] = i | kLeafBit; P.clo[0][i] = A.plo[t]; P.chi[0][i] = A.phi[t];
+}
+
+// depth-first layout, one tree level per launch: a node's triangles occupy [first, first + size) of the final order; its left
+// subtree comes first. frontier: inner nodes of this level; leaves get their final position in newpos.
+__global__ void pl_layout(DevArrays A, PlocArrays P, const int* frontier, int n_front, int* next_frontier, int* n_next, int* newpos)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_front) return;
+    const int node = frontier[k];
+    const int first = A.first[node];
+    A.last[node] = first + P.size[node] - 1;
+    const int L = A.left[node], R = A.right[node];
+    const int ls = (L & kLeafBit) ? 1 : P.size[L];
+    if (L & kLeafBit) newpos[L & ~kLeafBit] = first; else { A.first[L] = first; next_frontier[atomicAdd(n_next, 1)] = L; }
+    if (R & kLeafBit) newpos[R & ~kLeafBit] = first + ls; else { A.first[R] = first + ls; next_frontier[atomicAdd(n_next, 1)] = R; }
+}
+
+// leaves move to their depth-first positions: the triangle order (vals) is permuted and the leaf references / parents follow
+__global__ void pl_permute_vals(const int* vals, const int* newpos, const int* parent_leaf, int n, int* vals_out, int* parent_leaf_out)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= n) return;
+    vals_out[newpos[p]] = vals[p];
+    parent_leaf_out[newpos[p]] = parent_leaf[p];
+}
+__global__ void pl_relabel(DevArrays A, const int* newpos)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= A.n - 1) return;
+    const int L = A.left[i], R = A.right[i];
+    if (L & kLeafBit) A.left[i] = newpos[L & ~kLeafBit] | kLeafBit;
+    if (R & kLeafBit) A.right[i] = newpos[R & ~kLeafBit] | kLeafBit;
 }
 
 // ---- 8-ary collapse ------------------------------------------------------------------------------------------------------------
@@ -502,8 +631,73 @@ int build_flat_bvh_device(const float* tri9_host, int n_tri, int device, FlatBVH
     n_tri -= n_large;                         // the tree is built over the first n_tri sorted triangles
     A.n = n_tri;
     grid_n = (n_tri + tb - 1) / tb;
-    lb_tree<<<grid_n, tb>>>(A);
-    lb_fit<<<grid_n, tb>>>(A, d_misc);
+    static const bool use_lbvh = []() { const char* e = getenv("B200RT_DEVICE_BUILDER"); return e && std::string(e) == "lbvh"; }();
+    if (use_lbvh)
+    {
+        lb_tree<<<grid_n, tb>>>(A);
+        lb_fit<<<grid_n, tb>>>(A, d_misc);
+    }
+    else
+    {
+        PlocArrays P;
+        memset(&P, 0, sizeof(P));
+        for (int b = 0; b < 2; b++) { GCU(pool.get(&P.cid[b], n)); GCU(pool.get(&P.clo[b], n)); GCU(pool.get(&P.chi[b], n)); }
+        GCU(pool.get(&P.nn, n)); GCU(pool.get(&P.valid, n)); GCU(pool.get(&P.pos, n)); GCU(pool.get(&P.size, n)); GCU(pool.get(&P.next_node, 1));
+        size_t pscan_bytes = 0;
+        GCU(cub::DeviceScan::ExclusiveSum(nullptr, pscan_bytes, P.valid, P.pos, n_tri));
+        char* pscan_tmp = nullptr;
+        GCU(pool.get(&pscan_tmp, pscan_bytes));
+        const int first_node = n_tri - 2;
+        GCU(cudaMemcpy(P.next_node, &first_node, sizeof(int), cudaMemcpyHostToDevice));
+        pl_init<<<grid_n, tb>>>(A, P);
+        int nc = n_tri, cur = 0, rounds = 0;
+        while (nc > 1)
+        {
+            if (++rounds > 4096) { err = "clustering did not converge"; return 1; }
+            const int g = (nc + kPlocBlock - 1) / kPlocBlock;
+            pl_nearest<<<g, kPlocBlock>>>(P.clo[cur], P.chi[cur], nc, P.nn);
+            pl_merge<<<g, kPlocBlock>>>(A, P, cur, nc);
+            GCU(cub::DeviceScan::ExclusiveSum(pscan_tmp, pscan_bytes, P.valid, P.pos, nc));
+            pl_compact<<<g, kPlocBlock>>>(P, cur, nc);
+            int last_pos = 0, last_valid = 0;
+            GCU(cudaMemcpy(&last_pos, P.pos + nc - 1, sizeof(int), cudaMemcpyDeviceToHost));
+            GCU(cudaMemcpy(&last_valid, P.valid + nc - 1, sizeof(int), cudaMemcpyDeviceToHost));
+            const int next = last_pos + last_valid;
+            if (next >= nc) { err = "clustering round merged nothing"; return 1; }
+            nc = next; cur ^= 1;
+        }
+        // the root is the node created last: index 0
+        {
+            const int none = -1, zero = 0;
+            GCU(cudaMemcpy(A.parent_node, &none, sizeof(int), cudaMemcpyHostToDevice));
+            GCU(cudaMemcpy(A.first, &zero, sizeof(int), cudaMemcpyHostToDevice));
+        }
+        // depth-first layout level by level (P.cid / P.nn / P.pos are free again: frontiers and the leaf permutation)
+        int* front[2] = { P.cid[0], P.cid[1] };
+        int* d_nnext = P.next_node;
+        int* newpos = P.nn;
+        {
+            const int zero = 0;
+            GCU(cudaMemcpy(front[0], &zero, sizeof(int), cudaMemcpyHostToDevice));
+        }
+        int n_front = 1, f = 0, depth = 1;
+        while (n_front > 0)
+        {
+            depth++;
+            if (depth > 4096) { err = "layout did not terminate"; return 1; }
+            GCU(cudaMemset(d_nnext, 0, sizeof(int)));
+            pl_layout<<<(n_front + 255) / 256, 256>>>(A, P, front[f], n_front, front[f ^ 1], d_nnext, newpos);
+            GCU(cudaMemcpy(&n_front, d_nnext, sizeof(int), cudaMemcpyDeviceToHost));
+            f ^= 1;
+        }
+        GCU(cudaMemcpy(d_misc, &depth, sizeof(int), cudaMemcpyHostToDevice));
+        pl_permute_vals<<<grid_n, tb>>>(A.vals, newpos, A.parent_leaf, n_tri, A.vals_alt, P.pos);
+        pl_relabel<<<grid_n, tb>>>(A, newpos);
+        // the outsized triangles behind the tree keep their places in the order
+        if (n_large) GCU(cudaMemcpy(A.vals_alt + n_tri, A.vals + n_tri, (size_t)n_large * sizeof(int), cudaMemcpyDeviceToDevice));
+        std::swap(A.vals, A.vals_alt);
+        GCU(cudaMemcpy(A.parent_leaf, P.pos, (size_t)n_tri * sizeof(int), cudaMemcpyDeviceToDevice));
+    }
     int scene_h[8];
     int misc_h[4];
     GCU(cudaMemcpy(scene_h, A.scene, sizeof(scene_h), cudaMemcpyDeviceToHost));
