@@ -230,8 +230,19 @@ __device__ __forceinline__ float union_area(float4 alo, float4 ahi, float4 blo, 
     return dx * dy + dy * dz + dz * dx;
 }
 
-// nearest neighbour within kPlocRadius places. Pairs are ordered by (area, lower index, higher index): a total order, so the globally
-// best pair is always mutual and every round merges at least one pair.
+// nearest neighbour within kPlocRadius places. Pairs are ordered by (area, distance along the curve, parity of the lower index,
+// lower index): a total order, so the globally best pair is always mutual and every round merges at least one pair; the
+// parity term makes runs of identical boxes (duplicated geometry) pair up as (0,1) (2,3) ... instead of one pair per round.
+__device__ __forceinline__ bool pl_pair_less(float a, int i, int j, float b, int k)
+{
+    if (a != b) return a < b;
+    const int dj = abs(i - j), dk = abs(i - k);
+    if (dj != dk) return dj < dk;
+    const int mj = min(i, j), mk = min(i, k);
+    if ((mj & 1) != (mk & 1)) return (mj & 1) == 0;
+    return mj < mk;
+}
+
 __global__ void __launch_bounds__(kPlocBlock) pl_nearest(const float4* __restrict__ clo, const float4* __restrict__ chi, int n, int* __restrict__ nn)
 {
     __shared__ float4 slo[kPlocBlock + 2 * kPlocRadius], shi[kPlocBlock + 2 * kPlocRadius];
@@ -250,15 +261,9 @@ __global__ void __launch_bounds__(kPlocBlock) pl_nearest(const float4* __restric
     {
         const int j = i + d;
         if (d == 0 || j < 0 || j >= n) continue;
-        const float a = union_area(lo, hi, slo[threadIdx.x + kPlocRadius + d], shi[threadIdx.x + kPlocRadius + d]);
-        // (area, min(i, j), max(i, j)) lexicographic; candidates come in increasing j
-        bool better = a < best;
-        if (!better && a == best && bj >= 0)
-        {
-            const int m0 = min(i, j), m1 = max(i, j), b0 = min(i, bj), b1 = max(i, bj);
-            better = m0 < b0 || (m0 == b0 && m1 < b1);
-        }
-        if (better || bj < 0) { best = a; bj = j; }
+        float a = union_area(lo, hi, slo[threadIdx.x + kPlocRadius + d], shi[threadIdx.x + kPlocRadius + d]);
+        if (!(a == a)) a = FLT_MAX;                                   // NaN boxes (non-finite input) sort last
+        if (bj < 0 || pl_pair_less(a, i, j, best, bj)) { best = a; bj = j; }
     }
     nn[i] = bj;
 }
@@ -569,8 +574,8 @@ struct Pool       // frees everything it handed out
         if (e__ != cudaSuccess) { err = std::string(#expr) + ": " + cudaGetErrorString(e__); return 1; } \
     } while (0)
 
-// 0 = ok; 1 = CUDA error; 2 = the input is outside what this builder handles (caller falls back to the host builder)
-int build_flat_bvh_device(const float* tri9_host, int n_tri, int device, FlatBVH& out, std::string& err)
+// 0 = ok; 1 = CUDA error; 2 = the input is outside what this builder handles
+static int build_flat_bvh_device_impl(const float* tri9_host, int n_tri, int device, bool use_lbvh, FlatBVH& out, std::string& err)
 {
     const auto t0 = std::chrono::high_resolution_clock::now();
     if (n_tri <= kWideMaxLeaf) { err = "fewer than 4 triangles"; return 2; }
@@ -631,7 +636,6 @@ int build_flat_bvh_device(const float* tri9_host, int n_tri, int device, FlatBVH
     n_tri -= n_large;                         // the tree is built over the first n_tri sorted triangles
     A.n = n_tri;
     grid_n = (n_tri + tb - 1) / tb;
-    static const bool use_lbvh = []() { const char* e = getenv("B200RT_DEVICE_BUILDER"); return e && std::string(e) == "lbvh"; }();
     if (use_lbvh)
     {
         lb_tree<<<grid_n, tb>>>(A);
@@ -653,7 +657,7 @@ int build_flat_bvh_device(const float* tri9_host, int n_tri, int device, FlatBVH
         int nc = n_tri, cur = 0, rounds = 0;
         while (nc > 1)
         {
-            if (++rounds > 4096) { err = "clustering did not converge"; return 1; }
+            if (++rounds > 512) { err = "clustering needs more than 512 rounds (a size gradient along the Morton curve merges one pair per round)"; return 2; }
             const int g = (nc + kPlocBlock - 1) / kPlocBlock;
             pl_nearest<<<g, kPlocBlock>>>(P.clo[cur], P.chi[cur], nc, P.nn);
             pl_merge<<<g, kPlocBlock>>>(A, P, cur, nc);
@@ -786,6 +790,17 @@ int build_flat_bvh_device(const float* tri9_host, int n_tri, int device, FlatBVH
     }
     out.info.build_seconds = std::chrono::duration<double>(std::chrono::high_resolution_clock::now() - t0).count();
     return 0;
+}
+
+// 0 = ok; 1 = CUDA error; 2 = the input is outside what this builder handles (caller falls back to the host builder).
+// Clustering first; an input it gives up on (too many rounds, a tree deeper than the traversal stack) gets the Morton radix tree.
+int build_flat_bvh_device(const float* tri9_host, int n_tri, int device, FlatBVH& out, std::string& err)
+{
+    static const bool lbvh_only = []() { const char* e = getenv("B200RT_DEVICE_BUILDER"); return e && std::string(e) == "lbvh"; }();
+    int rc = 2;
+    if (!lbvh_only) rc = build_flat_bvh_device_impl(tri9_host, n_tri, device, false, out, err);
+    if (rc == 2) rc = build_flat_bvh_device_impl(tri9_host, n_tri, device, true, out, err);
+    return rc;
 }
 
 } // namespace b200rt
