@@ -305,9 +305,10 @@ __global__ void pl_init(DevArrays A, PlocArrays P)
     P.cid[0][i] = i | kLeafBit; P.clo[0][i] = A.plo[t]; P.chi[0][i] = A.phi[t];
 }
 
-// depth-first layout, one tree level per launch: a node's triangles occupy [first, first + size) of the final order; its left
-// subtree comes first. frontier: inner nodes of this level; leaves get their final position in newpos.
-__global__ void pl_layout(DevArrays A, PlocArrays P, const int* frontier, int n_front, int* next_frontier, int* n_next, int* newpos)
+// depth-first layout, one tree level per launch: a node's triangles occupy [first, first + size) of the final order, its left
+// subtree first; pre[] = the node's rank in a depth-first pre-order of the inner nodes (root 0, left child next, right child after
+// the left subtree). frontier: inner nodes of this level; leaves get their final position in newpos.
+__global__ void pl_layout(DevArrays A, PlocArrays P, const int* frontier, int n_front, int* next_frontier, int* n_next, int* newpos, int* pre)
 {
     const int k = blockIdx.x * blockDim.x + threadIdx.x;
     if (k >= n_front) return;
@@ -316,25 +317,30 @@ __global__ void pl_layout(DevArrays A, PlocArrays P, const int* frontier, int n_
     A.last[node] = first + P.size[node] - 1;
     const int L = A.left[node], R = A.right[node];
     const int ls = (L & kLeafBit) ? 1 : P.size[L];
-    if (L & kLeafBit) newpos[L & ~kLeafBit] = first; else { A.first[L] = first; next_frontier[atomicAdd(n_next, 1)] = L; }
-    if (R & kLeafBit) newpos[R & ~kLeafBit] = first + ls; else { A.first[R] = first + ls; next_frontier[atomicAdd(n_next, 1)] = R; }
+    if (L & kLeafBit) newpos[L & ~kLeafBit] = first; else { A.first[L] = first; pre[L] = pre[node] + 1; next_frontier[atomicAdd(n_next, 1)] = L; }
+    if (R & kLeafBit) newpos[R & ~kLeafBit] = first + ls; else { A.first[R] = first + ls; pre[R] = pre[node] + ls; next_frontier[atomicAdd(n_next, 1)] = R; }
 }
 
-// leaves move to their depth-first positions: the triangle order (vals) is permuted and the leaf references / parents follow
-__global__ void pl_permute_vals(const int* vals, const int* newpos, const int* parent_leaf, int n, int* vals_out, int* parent_leaf_out)
+// leaves move to their depth-first positions: the triangle order (vals) is permuted
+__global__ void pl_permute_vals(const int* vals, const int* newpos, int n, int* vals_out)
 {
     const int p = blockIdx.x * blockDim.x + threadIdx.x;
-    if (p >= n) return;
-    vals_out[newpos[p]] = vals[p];
-    parent_leaf_out[newpos[p]] = parent_leaf[p];
+    if (p < n) vals_out[newpos[p]] = vals[p];
 }
-__global__ void pl_relabel(DevArrays A, const int* newpos)
+
+// inner nodes move to their pre-order ranks (clustering numbered them in merge order, i.e. scattered in memory: every step of a
+// traversal would be a cache miss — the binary layout's records are emitted in node order) and their references follow
+__global__ void pl_relabel_nodes(DevArrays A, const int* pre, const int* newpos, int* o_left, int* o_right, int* o_first, int* o_last,
+                                 float4* o_lo, float4* o_hi)
 {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= A.n - 1) return;
-    const int L = A.left[i], R = A.right[i];
-    if (L & kLeafBit) A.left[i] = newpos[L & ~kLeafBit] | kLeafBit;
-    if (R & kLeafBit) A.right[i] = newpos[R & ~kLeafBit] | kLeafBit;
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= A.n - 1) return;
+    const int nv = pre[v];
+    const int L = A.left[v], R = A.right[v];
+    o_left[nv] = (L & kLeafBit) ? (newpos[L & ~kLeafBit] | kLeafBit) : pre[L];
+    o_right[nv] = (R & kLeafBit) ? (newpos[R & ~kLeafBit] | kLeafBit) : pre[R];
+    o_first[nv] = A.first[v]; o_last[nv] = A.last[v];
+    o_lo[nv] = A.nlo[v]; o_hi[nv] = A.nhi[v];
 }
 
 // ---- 8-ary collapse ------------------------------------------------------------------------------------------------------------
@@ -676,13 +682,15 @@ static int build_flat_bvh_device_impl(const float* tri9_host, int n_tri, int dev
             GCU(cudaMemcpy(A.parent_node, &none, sizeof(int), cudaMemcpyHostToDevice));
             GCU(cudaMemcpy(A.first, &zero, sizeof(int), cudaMemcpyHostToDevice));
         }
-        // depth-first layout level by level (P.cid / P.nn / P.pos are free again: frontiers and the leaf permutation)
+        // depth-first layout level by level (the clustering arrays are free again: frontiers, the leaf permutation, the relabelled nodes)
         int* front[2] = { P.cid[0], P.cid[1] };
         int* d_nnext = P.next_node;
         int* newpos = P.nn;
+        int* pre = reinterpret_cast<int*>(A.visits);
         {
             const int zero = 0;
             GCU(cudaMemcpy(front[0], &zero, sizeof(int), cudaMemcpyHostToDevice));
+            GCU(cudaMemcpy(pre, &zero, sizeof(int), cudaMemcpyHostToDevice));
         }
         int n_front = 1, f = 0, depth = 1;
         while (n_front > 0)
@@ -690,17 +698,17 @@ static int build_flat_bvh_device_impl(const float* tri9_host, int n_tri, int dev
             depth++;
             if (depth > 4096) { err = "layout did not terminate"; return 1; }
             GCU(cudaMemset(d_nnext, 0, sizeof(int)));
-            pl_layout<<<(n_front + 255) / 256, 256>>>(A, P, front[f], n_front, front[f ^ 1], d_nnext, newpos);
+            pl_layout<<<(n_front + 255) / 256, 256>>>(A, P, front[f], n_front, front[f ^ 1], d_nnext, newpos, pre);
             GCU(cudaMemcpy(&n_front, d_nnext, sizeof(int), cudaMemcpyDeviceToHost));
             f ^= 1;
         }
         GCU(cudaMemcpy(d_misc, &depth, sizeof(int), cudaMemcpyHostToDevice));
-        pl_permute_vals<<<grid_n, tb>>>(A.vals, newpos, A.parent_leaf, n_tri, A.vals_alt, P.pos);
-        pl_relabel<<<grid_n, tb>>>(A, newpos);
+        pl_permute_vals<<<grid_n, tb>>>(A.vals, newpos, n_tri, A.vals_alt);
         // the outsized triangles behind the tree keep their places in the order
         if (n_large) GCU(cudaMemcpy(A.vals_alt + n_tri, A.vals + n_tri, (size_t)n_large * sizeof(int), cudaMemcpyDeviceToDevice));
+        pl_relabel_nodes<<<grid_n, tb>>>(A, pre, newpos, A.parent_node, A.parent_leaf, P.pos, P.valid, P.clo[0], P.chi[0]);
         std::swap(A.vals, A.vals_alt);
-        GCU(cudaMemcpy(A.parent_leaf, P.pos, (size_t)n_tri * sizeof(int), cudaMemcpyDeviceToDevice));
+        A.left = A.parent_node; A.right = A.parent_leaf; A.first = P.pos; A.last = P.valid; A.nlo = P.clo[0]; A.nhi = P.chi[0];
     }
     int scene_h[8];
     int misc_h[4];

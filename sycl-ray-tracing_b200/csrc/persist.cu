@@ -102,8 +102,13 @@ pt_persist(SceneDev S, RenderParams P, WfBuffers B, unsigned int* next_pixel, in
         }
         if (qn == 0)
         {
-            if (pool_empty) break;
-            continue;                           // every claimed slot was tile padding: claim again
+            // nothing to trace. Done only when no pixel is left to claim AND no slot has shading work left: a terminated path whose
+            // side rays were all skipped produces no ray but still has to be shaded once more; claimed tile padding means claim again
+            bool live = false;
+#pragma unroll
+            for (int k = 0; k < K; k++) live = live || !(st[k] & WF_DONE);
+            if (pool_empty && !__any_sync(FULL, live)) break;
+            continue;
         }
         rays += qn;
         __syncwarp();

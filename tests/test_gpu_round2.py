@@ -523,7 +523,7 @@ def test_denoise_stage(rt, golden_cameras):
     assert np.allclose(rt.OIDN_denoise(const), const, atol=1e-6)
     step = np.zeros((64, 64, 4), np.float32); step[:, 32:, :3] = 0.9; step[..., 3] = 2.5
     out = rt.OIDN_denoise(step)
-    assert np.abs(out[..., :3] - step[..., :3]).max() < 2e-3 and np.allclose(out[..., 3], 1.0), "edges survive; alpha -> 1 (utils.cpp:186)"
+    assert np.abs(out[..., :3] - step[..., :3]).max() < 5e-3 and np.allclose(out[..., 3], 1.0), "edges survive; alpha -> 1 (utils.cpp:186)"
     c3 = scenes.c3_scene(nu=100, nv=50, sky_w=64, sky_h=32)
     sc = scene_of(rt, c3)
     noisy, _ = sc.render(c3["camera"], 320, 180, 4, 8)
