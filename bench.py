@@ -59,6 +59,7 @@ def parse_args():
     p.add_argument("--flags", type=int, default=0)
     p.add_argument("--no-cpu-baseline", action="store_true")
     p.add_argument("--cpu-sample", default="", help="WxHxSPP of the bounded CPU sample (default per workload)")
+    p.add_argument("--lean", action="store_true", help="skip the optional legs (kernel-alone timing, RGBA8 end-to-end, dead-ray frame): for minutes-long frames (c5)")
     p.add_argument("--verify", action="store_true", help="N>1: rank 0 also renders the frame alone and asserts the gathered frame is bit-identical")
     return p.parse_args()
 
@@ -305,19 +306,6 @@ def main():
         warm_step()
     barrier()
 
-    if not primary_only:
-        # rays of the whole frame (deterministic) and this rank's launch count: one untimed pass with stats
-        tiles_probe = torch.empty_like(g.tiles)
-        st = scene.render_tiles_device(cam, w, h, spp, bounces, tiles_probe.data_ptr(), stream_ptr=cur_stream(),
-                                       integrator=args.integrator, flags=args.flags, rank=rank, world=world, want_stats=True)
-        rays_t = torch.tensor([st["rays"]], dtype=torch.int64, device=device)
-        if world > 1:
-            dist.all_reduce(rays_t)
-        rays_per_frame = int(rays_t.item())
-        rank_rays = int(st["rays"])
-        del tiles_probe
-        launches_per_step = int(st["gpu_launches"]) + (2 if rank == 0 else 0)       # + framebuffer fill and the accumulating un-tile on rank 0
-
     verified = None
     if args.verify and not primary_only:
         img = step()
@@ -345,7 +333,6 @@ def main():
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(total_ms.item()) / args.steps
-    value = rays_per_frame / (ms_per_step * 1e-3) / 1e6
 
     # ---- roofline of the dominant kernel, measured live (CUDA events on the streams the kernels are launched on) ---------------------
     peak, peak_src = measured_peak()
@@ -356,6 +343,7 @@ def main():
     if primary_only or args.integrator != 1:
         # one launch per step: the kernel's duration is the frame's render time
         kms = []
+        kst = None
         k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         for i in range(args.steps):
             flush.fill_(i & 0xff)
@@ -363,8 +351,8 @@ def main():
             if primary_only:
                 scene.trace_primary_device(cam, w, h, prim.data_ptr(), tbuf.data_ptr(), stream_ptr=cur_stream(), rank=rank, world=world, flags=args.flags)
             else:
-                scene.render_tiles_device(cam, w, h, spp, bounces, probe.data_ptr(), stream_ptr=cur_stream(), integrator=args.integrator,
-                                          flags=args.flags, rank=rank, world=world)
+                kst = scene.render_tiles_device(cam, w, h, spp, bounces, probe.data_ptr(), stream_ptr=cur_stream(), integrator=args.integrator,
+                                                flags=args.flags, rank=rank, world=world, want_stats=(i == 0)) or kst
             k1.record()
             torch.cuda.synchronize()
             kms.append(k0.elapsed_time(k1))
@@ -372,7 +360,9 @@ def main():
         if world > 1:
             dist.all_reduce(kernel_ms, op=dist.ReduceOp.MAX)
         kernel_ms = float(kernel_ms.item())
-        rays_per_launch = rays_per_frame / world
+        if not primary_only:
+            rank_rays, rank_launches = int(kst["rays"]), int(kst["gpu_launches"])
+        rays_per_launch = w * h / world if primary_only else rank_rays
         achieved = rays_per_launch * bytes_per_ray / (kernel_ms * 1e-3) / 1e9
         roofline.update({"achieved": achieved, "frac": achieved / peak, "launches": 1, "avg_launch_ms": kernel_ms, "rays_per_launch": rays_per_launch})
     else:
@@ -388,6 +378,7 @@ def main():
         t1e.record()
         torch.cuda.synchronize()
         frame_ms = t0e.elapsed_time(t1e)
+        rank_rays, rank_launches = int(kst["rays"]), int(kst["gpu_launches"])
         union = max(kst["trace_union_ms"], 1e-9)
         achieved = kst["rays"] * bytes_per_ray / (union * 1e-3) / 1e9
         roofline.update({"achieved": achieved, "frac": achieved / peak, "launches": kst["trace_launches"],
@@ -399,12 +390,21 @@ def main():
                          "tail": {"kernel": "wf_tail", "launches": kst["tail_launches"], "sum_launch_ms": kst["tail_ms"]}})
         # the same kernel with the machine to itself (B200RT_FLAG_TIME_KERNELS: groups one after the other, full persistent grid): round 1's figure
         flush.fill_(9)
-        ast = scene.render_tiles_device(cam, w, h, spp, bounces, probe.data_ptr(), stream_ptr=cur_stream(), integrator=args.integrator,
-                                        flags=args.flags | rt.FLAG_TIME_KERNELS, rank=rank, world=world, want_stats=True)
+        ast = {"trace_launches": 0, "trace_ms": 0.0} if args.lean else scene.render_tiles_device(
+            cam, w, h, spp, bounces, probe.data_ptr(), stream_ptr=cur_stream(), integrator=args.integrator,
+            flags=args.flags | rt.FLAG_TIME_KERNELS, rank=rank, world=world, want_stats=True)
         if ast["trace_launches"] > 0 and ast["trace_ms"] > 0:
             a_ach = ast["rays"] * bytes_per_ray / (ast["trace_ms"] * 1e-3) / 1e9
             roofline["alone"] = {"launches": ast["trace_launches"], "avg_launch_ms": ast["trace_ms"] / ast["trace_launches"], "achieved": a_ach,
                                  "frac": a_ach / peak, "share_of_kernel_time": ast["trace_ms"] / (ast["trace_ms"] + ast["shade_ms"])}
+    # rays of the whole frame (deterministic: counted by the device during the frame timed above) and this rank's launch count
+    if not primary_only:
+        rays_t = torch.tensor([rank_rays], dtype=torch.int64, device=device)
+        if world > 1:
+            dist.all_reduce(rays_t)
+        rays_per_frame = int(rays_t.item())
+        launches_per_step = rank_launches + (2 if rank == 0 else 0)       # + framebuffer fill and the accumulating un-tile on rank 0
+    value = rays_per_frame / (ms_per_step * 1e-3) / 1e6
     tpr = profile_traffic(args.workload + "_trace_bytes_per_ray")
     roofline["traffic"] = (tpr * roofline["rays_per_launch"]) if (tpr and not primary_only and args.integrator == 1) else None
     roofline["ncu"] = ncu_counters(args.workload)
@@ -418,6 +418,8 @@ def main():
         t_h = rt.pinned_array((h, w), np.float32) if primary_only else None
         times = []
         stats = None
+        if not primary_only:
+            scene.render(cam, w, h, min(spp, 2), bounces, framebuffer=fb, integrator=args.integrator, flags=args.flags)       # allocations of this entry point
         for i in range(max(1, min(args.steps, 3))):
             fb[...] = (0.0, 0.0, 0.0, 1.0)
             torch.cuda.synchronize()
@@ -431,9 +433,10 @@ def main():
         e2e = {"value": rays_per_frame / e_sec / 1e6, "unit": "Mrays/s", "h2d_bytes_per_step": int(stats["h2d_bytes"]),
                "d2h_bytes_per_step": int(stats["d2h_bytes"]), "api": "b200rt_trace_primary" if primary_only else "b200rt_render",
                "host_buffers": "page-locked (b200rt_host_alloc)"}
-        if not primary_only:
+        if not primary_only and not args.lean:
             # the same frame leaving the GPU as the PNG's RGBA8 bytes (b200rt_render_rgba8: 4 B/pixel down instead of 16)
             out8 = rt.pinned_array((h, w, 4), np.uint8)
+            scene.render_rgba8(cam, w, h, min(spp, 2), bounces, framebuffer=fb, out=out8, integrator=args.integrator, flags=args.flags)   # allocations
             t0 = time.perf_counter()
             _, st8 = scene.render_rgba8(cam, w, h, spp, bounces, framebuffer=fb, out=out8, integrator=args.integrator, flags=args.flags)
             e8 = time.perf_counter() - t0
@@ -464,7 +467,7 @@ def main():
     # same frame with the rays that provably cannot change the image skipped (B200RT_FLAG_SKIP_DEAD_RAYS): reported next to
     # the headline, which keeps the reference's full ray set
     dead = None
-    if not primary_only and args.workload != "c5":
+    if not primary_only and not args.lean:
         g2 = D.make_cuda_gatherer(scene, cam, w, h, spp, bounces, rank, world, device, integrator=args.integrator,
                                   flags=args.flags | rt.binding.FLAG_SKIP_DEAD_RAYS)
         g2.frame()

@@ -538,6 +538,29 @@ void build_flat_bvh(const float* tri9, int n_tri, const b200rt_bvh_options& opts
     out.info.wide_max_depth = wide_depth;
 }
 
+// SAH cost of a flattened tree from its binary records (the same figure build_flat_bvh reports: sum over nodes of area / root area,
+// leaves weighted by their triangle count), for trees that were not built here (the device builder's)
+double sah_cost_of(const FlatBVH& bvh)
+{
+    if (bvh.axis.empty()) return 0.0;
+    auto half_area = [](const float* lo, const float* hi) {
+        const double dx = (double)hi[0] - lo[0], dy = (double)hi[1] - lo[1], dz = (double)hi[2] - lo[2];
+        return (dx < 0 || dy < 0 || dz < 0) ? 0.0 : dx * dy + dy * dz + dz * dx;
+    };
+    const AxisNode& r = bvh.axis[0];
+    float lo[3], hi[3];
+    for (int a = 0; a < 3; a++) { lo[a] = std::min(r.l_lo[a], r.r_lo[a]); hi[a] = std::max(r.l_hi[a], r.r_hi[a]); }
+    const double root_area = std::max(1e-30, half_area(lo, hi));
+    double sah = 1.0;
+    for (const AxisNode& n : bvh.axis)
+    {
+        const double al = half_area(n.l_lo, n.l_hi) / root_area, ar = half_area(n.r_lo, n.r_hi) / root_area;
+        sah += n.l_ref >= 0 ? al : al * n.l_count;
+        sah += n.r_ref >= 0 ? ar : ar * n.r_count;
+    }
+    return sah;
+}
+
 // Hangs triangles that were kept out of the tree (the device builder's outsized ones) in front of both layouts' roots: the old
 // root record moves to the end of its array, record 0 becomes a top-level node whose one inner child is the old root (or the
 // next top-level node) and whose other children are leaves holding the extra triangles (8-ary: 7 leaves x 3 triangles per

@@ -77,6 +77,7 @@ inline float diag_dist(int k, float x, float y, float z)
 
 void build_flat_bvh(const float* tri9, int n_tri, const b200rt_bvh_options& opts, FlatBVH& out);
 int check_flat_bvh(const FlatBVH& bvh, const float* tri9, int n_tri);
+double sah_cost_of(const FlatBVH& bvh);
 // triangles kept out of the tree become leaf children of extra top-level nodes in front of both layouts' roots (bvh_build.cpp)
 void append_top_level(FlatBVH& bvh, const float* tri9, const std::vector<int>& ids, float abs_pad);
 // device builder (bvh_build_gpu.cu): 0 = ok, 1 = CUDA error, 2 = input outside what it handles (err says why)

@@ -552,6 +552,7 @@ int b200rt_bvh_get_info(const b200rt_bvh* bvh, b200rt_bvh_info* out)
 {
     if (!bvh || !out) return fail(B200RT_ERR_ARG, "NULL argument");
     *out = bvh->flat.info;
+    if (out->sah_cost == 0.0) out->sah_cost = sah_cost_of(bvh->flat);       // device-built trees: computed on request from the binary records
     return B200RT_OK;
 }
 

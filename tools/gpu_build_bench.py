@@ -19,7 +19,7 @@ for name, sc, w, h, spp in (("c3", scenes.c3_scene(), 1920, 1080, 8),) + ((("c5"
         scene.render(sc["camera"], w, h, 1, 8)
         img, st = scene.render(sc["camera"], w, h, spp, 8)
         res[kind] = dict(build_wall_s=wall, build_s=info["build_seconds"], inner=info["n_inner_nodes"], wide=info["n_wide_nodes"], depth=info["max_depth"],
-                         wide_depth=info["wide_max_depth"], primary_mrays_s=w * h / stp["kernel_ms"] / 1e3, mrays_s=st["rays"] / st["kernel_ms"] / 1e3,
+                         wide_depth=info["wide_max_depth"], sah=info["sah_cost"], primary_mrays_s=w * h / stp["kernel_ms"] / 1e3, mrays_s=st["rays"] / st["kernel_ms"] / 1e3,
                          rays=int(st["rays"]), image_crc=int(np.bitwise_xor.reduce(img.view(np.uint32).ravel())))
         print(name, kind, res[kind], flush=True)
         del scene, bvh
