@@ -51,6 +51,7 @@ struct DevArrays
     int* scene;                              // ordered ints: [0..5] centre-bounds min xyz / max xyz, [6] max |coord|, [8..13] scene box min / max; [14] = outsized count
     int segregate;                           // 1: outsized triangles get the largest sort key and stay out of the tree
     int n;
+    int leaf_max;                            // subtrees of at most this many triangles (<= kWideMaxLeaf) become leaves
 };
 
 __device__ __forceinline__ int f2ord(float f) { int i = __float_as_int(f); return i >= 0 ? i : i ^ 0x7fffffff; }
@@ -210,7 +211,7 @@ __global__ void lb_fit(DevArrays A, int* max_depth)
 }
 
 // ---- parallel locally-ordered clustering -----------------------------------------------------------------------------------------
-constexpr int kPlocRadius = 16;
+constexpr int kPlocRadius = 32;          // largest search radius (shared-memory halo); the radius in use is a launch argument
 constexpr int kPlocBlock = 256;
 
 struct PlocArrays
@@ -243,7 +244,7 @@ __device__ __forceinline__ bool pl_pair_less(float a, int i, int j, float b, int
     return mj < mk;
 }
 
-__global__ void __launch_bounds__(kPlocBlock) pl_nearest(const float4* __restrict__ clo, const float4* __restrict__ chi, int n, int* __restrict__ nn)
+__global__ void __launch_bounds__(kPlocBlock) pl_nearest(const float4* __restrict__ clo, const float4* __restrict__ chi, int n, int radius, int* __restrict__ nn)
 {
     __shared__ float4 slo[kPlocBlock + 2 * kPlocRadius], shi[kPlocBlock + 2 * kPlocRadius];
     const int base = blockIdx.x * kPlocBlock - kPlocRadius;
@@ -257,7 +258,7 @@ __global__ void __launch_bounds__(kPlocBlock) pl_nearest(const float4* __restric
     if (i >= n) return;
     const float4 lo = slo[threadIdx.x + kPlocRadius], hi = shi[threadIdx.x + kPlocRadius];
     float best = FLT_MAX; int bj = -1;
-    for (int d = -kPlocRadius; d <= kPlocRadius; d++)
+    for (int d = -radius; d <= radius; d++)
     {
         const int j = i + d;
         if (d == 0 || j < 0 || j >= n) continue;
@@ -358,7 +359,7 @@ struct WideArrays
 constexpr int kEmpty = -1;
 
 __device__ __forceinline__ int ref_size(const DevArrays& A, int ref) { return (ref & kLeafBit) ? 1 : A.last[ref] - A.first[ref] + 1; }
-__device__ __forceinline__ bool ref_inner(const DevArrays& A, int ref) { return ref_size(A, ref) > kWideMaxLeaf; }
+__device__ __forceinline__ bool ref_inner(const DevArrays& A, int ref) { return ref_size(A, ref) > A.leaf_max; }
 __device__ __forceinline__ void ref_box(const DevArrays& A, int ref, float4& lo, float4& hi)
 {
     if (ref & kLeafBit) { const int t = A.vals[ref & ~kLeafBit]; lo = A.plo[t]; hi = A.phi[t]; }
@@ -527,7 +528,7 @@ __global__ void lw_emit(DevArrays A, WideArrays W, int n_wide, float abs_pad, Wi
 __global__ void lb_mark_live(DevArrays A, int* live)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < A.n - 1) live[i] = (A.last[i] - A.first[i] + 1) > kWideMaxLeaf ? 1 : 0;
+    if (i < A.n - 1) live[i] = (A.last[i] - A.first[i] + 1) > A.leaf_max ? 1 : 0;
 }
 
 __global__ void lb_emit(DevArrays A, WideArrays W, const int* live, const int* axis_idx, float abs_pad, AxisNode* axis)
@@ -590,6 +591,9 @@ static int build_flat_bvh_device_impl(const float* tri9_host, int n_tri, int dev
     DevArrays A;
     memset(&A, 0, sizeof(A));
     A.n = n_tri;
+    static const int leaf_env = []() { const char* e = getenv("B200RT_DEVICE_LEAF"); const int v = e ? atoi(e) : kWideMaxLeaf; return v < 1 ? 1 : (v > kWideMaxLeaf ? kWideMaxLeaf : v); }();
+    static const int ploc_radius = []() { const char* e = getenv("B200RT_PLOC_RADIUS"); const int v = e ? atoi(e) : 16; return v < 1 ? 1 : (v > kPlocRadius ? kPlocRadius : v); }();
+    A.leaf_max = leaf_env;
     const size_t n = (size_t)n_tri;
     float* d_tri9 = nullptr;
     GCU(pool.get(&d_tri9, 9 * n));
@@ -665,7 +669,7 @@ static int build_flat_bvh_device_impl(const float* tri9_host, int n_tri, int dev
         {
             if (++rounds > 512) { err = "clustering needs more than 512 rounds (a size gradient along the Morton curve merges one pair per round)"; return 2; }
             const int g = (nc + kPlocBlock - 1) / kPlocBlock;
-            pl_nearest<<<g, kPlocBlock>>>(P.clo[cur], P.chi[cur], nc, P.nn);
+            pl_nearest<<<g, kPlocBlock>>>(P.clo[cur], P.chi[cur], nc, ploc_radius, P.nn);
             pl_merge<<<g, kPlocBlock>>>(A, P, cur, nc);
             GCU(cub::DeviceScan::ExclusiveSum(pscan_tmp, pscan_bytes, P.valid, P.pos, nc));
             pl_compact<<<g, kPlocBlock>>>(P, cur, nc);
