@@ -21,6 +21,7 @@
 // diagonal slabs (has_diag_slabs = 0: the 7-plane ablation needs the host builder).
 #include <algorithm>
 #include <cfloat>
+#include <cfloat>
 #include <chrono>
 #include <cstdint>
 #include <cstdlib>
@@ -298,6 +299,13 @@ __global__ void pl_compact(PlocArrays P, int cur, int n)
     P.cid[cur ^ 1][o] = P.cid[cur][i]; P.clo[cur ^ 1][o] = P.clo[cur][i]; P.chi[cur ^ 1][o] = P.chi[cur][i];
 }
 
+// triangles below every remaining cluster (for the host's top-level sweep)
+__global__ void pl_cluster_sizes(const int* cid, const int* size, int nc, int* out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < nc) out[i] = (cid[i] & kLeafBit) ? 1 : size[cid[i]];
+}
+
 __global__ void pl_init(DevArrays A, PlocArrays P)
 {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -560,6 +568,76 @@ __global__ void lb_emit(DevArrays A, WideArrays W, const int* live, const int* a
     axis[axis_idx[i]] = an;
 }
 
+// ---- top of the clustered tree: surface-area-heuristic sweep on the host -----------------------------------------------------------
+// Agglomerative clustering builds excellent lower levels and mediocre upper ones (few, large clusters seen through a fixed window
+// along the Morton curve), and every ray walks the upper levels. When at most kTopClusters clusters are left the clustering stops and
+// the tree above them is built top-down by a full SAH sweep (sort by centroid on every axis, cost = area x triangles below): a few
+// thousand boxes, well under a millisecond on the host.
+struct TopCluster { float lo[3], hi[3]; int ref, size; };
+
+struct TopBuilder
+{
+    std::vector<TopCluster> c;
+    std::vector<int> left, right, size;
+    std::vector<float4> nlo, nhi;
+    int next = 0;
+
+    static double area(const float* lo, const float* hi)
+    {
+        const double dx = (double)hi[0] - lo[0], dy = (double)hi[1] - lo[1], dz = (double)hi[2] - lo[2];
+        return dx * dy + dy * dz + dz * dx;
+    }
+
+    // builds the subtree over c[begin, end) (reordered in place); returns its reference
+    int build(int begin, int end)
+    {
+        if (end - begin == 1) return c[(size_t)begin].ref;
+        const int id = next++;
+        float lo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, hi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+        int total = 0;
+        for (int i = begin; i < end; i++)
+        {
+            for (int a = 0; a < 3; a++) { lo[a] = std::min(lo[a], c[(size_t)i].lo[a]); hi[a] = std::max(hi[a], c[(size_t)i].hi[a]); }
+            total += c[(size_t)i].size;
+        }
+        nlo[(size_t)id] = make_float4(lo[0], lo[1], lo[2], 0.0f); nhi[(size_t)id] = make_float4(hi[0], hi[1], hi[2], 0.0f);
+        size[(size_t)id] = total;
+        const int n = end - begin;
+        int best_axis = -1, best_split = -1;
+        double best_cost = DBL_MAX;
+        std::vector<double> right_area((size_t)n);
+        std::vector<int> right_cnt((size_t)n);
+        for (int axis = 0; axis < 3; axis++)
+        {
+            std::sort(c.begin() + begin, c.begin() + end, [axis](const TopCluster& p, const TopCluster& q) { return p.lo[axis] + p.hi[axis] < q.lo[axis] + q.hi[axis]; });
+            float rlo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, rhi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+            int rc = 0;
+            for (int i = n - 1; i >= 1; i--)
+            {
+                const TopCluster& t = c[(size_t)(begin + i)];
+                for (int a = 0; a < 3; a++) { rlo[a] = std::min(rlo[a], t.lo[a]); rhi[a] = std::max(rhi[a], t.hi[a]); }
+                rc += t.size;
+                right_area[(size_t)i] = area(rlo, rhi); right_cnt[(size_t)i] = rc;
+            }
+            float llo[3] = { FLT_MAX, FLT_MAX, FLT_MAX }, lhi[3] = { -FLT_MAX, -FLT_MAX, -FLT_MAX };
+            int lc = 0;
+            for (int i = 1; i < n; i++)
+            {
+                const TopCluster& t = c[(size_t)(begin + i - 1)];
+                for (int a = 0; a < 3; a++) { llo[a] = std::min(llo[a], t.lo[a]); lhi[a] = std::max(lhi[a], t.hi[a]); }
+                lc += t.size;
+                const double cost = area(llo, lhi) * lc + right_area[(size_t)i] * right_cnt[(size_t)i];
+                if (cost < best_cost) { best_cost = cost; best_axis = axis; best_split = i; }
+            }
+        }
+        if (best_axis != 2)
+            std::sort(c.begin() + begin, c.begin() + end, [best_axis](const TopCluster& p, const TopCluster& q) { return p.lo[best_axis] + p.hi[best_axis] < q.lo[best_axis] + q.hi[best_axis]; });
+        const int l = build(begin, begin + best_split), r = build(begin + best_split, end);
+        left[(size_t)id] = l; right[(size_t)id] = r;
+        return id;
+    }
+};
+
 struct Pool       // frees everything it handed out
 {
     std::vector<void*> p;
@@ -664,8 +742,9 @@ static int build_flat_bvh_device_impl(const float* tri9_host, int n_tri, int dev
         const int first_node = n_tri - 2;
         GCU(cudaMemcpy(P.next_node, &first_node, sizeof(int), cudaMemcpyHostToDevice));
         pl_init<<<grid_n, tb>>>(A, P);
+        static const int top_clusters = []() { const char* e = getenv("B200RT_PLOC_TOP"); const int v = e ? atoi(e) : 4096; return v < 1 ? 1 : v; }();
         int nc = n_tri, cur = 0, rounds = 0;
-        while (nc > 1)
+        while (nc > top_clusters)
         {
             if (++rounds > 512) { err = "clustering needs more than 512 rounds (a size gradient along the Morton curve merges one pair per round)"; return 2; }
             const int g = (nc + kPlocBlock - 1) / kPlocBlock;
@@ -679,6 +758,37 @@ static int build_flat_bvh_device_impl(const float* tri9_host, int n_tri, int dev
             const int next = last_pos + last_valid;
             if (next >= nc) { err = "clustering round merged nothing"; return 1; }
             nc = next; cur ^= 1;
+        }
+        if (nc > 1)
+        {
+            // the tree above the remaining clusters: SAH sweep on the host, into the node indices clustering has not used (0 .. nc - 2)
+            std::vector<int> h_cid((size_t)nc);
+            std::vector<float4> h_lo((size_t)nc), h_hi((size_t)nc);
+            std::vector<int> h_size((size_t)nc);
+            pl_cluster_sizes<<<(nc + 255) / 256, 256>>>(P.cid[cur], P.size, nc, P.nn);
+            GCU(cudaMemcpy(h_size.data(), P.nn, (size_t)nc * sizeof(int), cudaMemcpyDeviceToHost));
+            GCU(cudaMemcpy(h_cid.data(), P.cid[cur], (size_t)nc * sizeof(int), cudaMemcpyDeviceToHost));
+            GCU(cudaMemcpy(h_lo.data(), P.clo[cur], (size_t)nc * sizeof(float4), cudaMemcpyDeviceToHost));
+            GCU(cudaMemcpy(h_hi.data(), P.chi[cur], (size_t)nc * sizeof(float4), cudaMemcpyDeviceToHost));
+            TopBuilder T;
+            T.c.resize((size_t)nc);
+            for (int i = 0; i < nc; i++)
+            {
+                TopCluster& t = T.c[(size_t)i];
+                t.lo[0] = h_lo[(size_t)i].x; t.lo[1] = h_lo[(size_t)i].y; t.lo[2] = h_lo[(size_t)i].z;
+                t.hi[0] = h_hi[(size_t)i].x; t.hi[1] = h_hi[(size_t)i].y; t.hi[2] = h_hi[(size_t)i].z;
+                t.ref = h_cid[(size_t)i];
+                t.size = h_size[(size_t)i];
+            }
+            const size_t nt = (size_t)nc - 1;
+            T.left.resize(nt); T.right.resize(nt); T.size.resize(nt); T.nlo.resize(nt); T.nhi.resize(nt);
+            const int root = T.build(0, nc);
+            if (root != 0 || T.next != nc - 1) { err = "top-level build produced an inconsistent tree"; return 1; }
+            GCU(cudaMemcpy(A.left, T.left.data(), nt * sizeof(int), cudaMemcpyHostToDevice));
+            GCU(cudaMemcpy(A.right, T.right.data(), nt * sizeof(int), cudaMemcpyHostToDevice));
+            GCU(cudaMemcpy(P.size, T.size.data(), nt * sizeof(int), cudaMemcpyHostToDevice));
+            GCU(cudaMemcpy(A.nlo, T.nlo.data(), nt * sizeof(float4), cudaMemcpyHostToDevice));
+            GCU(cudaMemcpy(A.nhi, T.nhi.data(), nt * sizeof(float4), cudaMemcpyHostToDevice));
         }
         // the root is the node created last: index 0
         {
