@@ -570,7 +570,7 @@ __global__ void lb_emit(DevArrays A, WideArrays W, const int* live, const int* a
 
 // ---- top of the clustered tree: surface-area-heuristic sweep on the host -----------------------------------------------------------
 // Agglomerative clustering builds excellent lower levels and mediocre upper ones (few, large clusters seen through a fixed window
-// along the Morton curve), and every ray walks the upper levels. When at most kTopClusters clusters are left the clustering stops and
+// along the Morton curve), and every ray walks the upper levels. When at most 1024 clusters (B200RT_PLOC_TOP) are left the clustering stops and
 // the tree above them is built top-down by a full SAH sweep (sort by centroid on every axis, cost = area x triangles below): a few
 // thousand boxes, well under a millisecond on the host.
 struct TopCluster { float lo[3], hi[3]; int ref, size; };
@@ -742,7 +742,7 @@ static int build_flat_bvh_device_impl(const float* tri9_host, int n_tri, int dev
         const int first_node = n_tri - 2;
         GCU(cudaMemcpy(P.next_node, &first_node, sizeof(int), cudaMemcpyHostToDevice));
         pl_init<<<grid_n, tb>>>(A, P);
-        static const int top_clusters = []() { const char* e = getenv("B200RT_PLOC_TOP"); const int v = e ? atoi(e) : 4096; return v < 1 ? 1 : v; }();
+        static const int top_clusters = []() { const char* e = getenv("B200RT_PLOC_TOP"); const int v = e ? atoi(e) : 1024; return v < 1 ? 1 : v; }();
         int nc = n_tri, cur = 0, rounds = 0;
         while (nc > top_clusters)
         {
