@@ -201,7 +201,7 @@ def port_ray_count(s, cam17, name, sw, sh, sspp, bounces):
     return rays
 
 
-def reference_arm(args):
+def reference_arm(args, stdout_fd=1):
     """--impl reference: the reference's own CPU implementation (oracle/_ref when it was compiled, else the port) on all
     host cores, same workload config / metric / unit; each step is a bounded sample of the frame. Rank 0 only."""
     rank = int(os.environ.get("RANK", "0"))
@@ -227,7 +227,7 @@ def reference_arm(args):
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit_line(stdout_fd, line)
 
 
 def ncu_counters(workload):
@@ -242,10 +242,20 @@ def ncu_counters(workload):
     return None
 
 
+def emit_line(stdout_fd, line):
+    """The one JSON line goes to the process's ORIGINAL stdout; everything else any library prints (NCCL's version banner, warnings)
+    was sent to stderr by main()."""
+    os.write(stdout_fd, (json.dumps(line) + "\n").encode())
+
+
 def main():
     args = parse_args()
+    # stdout carries exactly one JSON line: keep the real stdout aside and point fd 1 at stderr for the rest of the run
+    sys.stdout.flush()
+    stdout_fd = os.dup(1)
+    os.dup2(2, 1)
     if args.impl == "reference":
-        reference_arm(args)
+        reference_arm(args, stdout_fd)
         return
 
     import torch
@@ -525,7 +535,7 @@ def main():
             "roofline": roofline,
             "cpu_baseline": cpu_baseline,
         }
-        print(json.dumps(line), flush=True)
+        emit_line(stdout_fd, line)
     if world > 1:
         dist.destroy_process_group()
 
