@@ -343,6 +343,7 @@ def main():
     if world > 1:
         dist.all_reduce(total_ms, op=dist.ReduceOp.MAX)
     ms_per_step = float(total_ms.item()) / args.steps
+    print(f"bench.py rank {rank}: timed steps {['%.2f' % v for v in step_ms]} ms", file=sys.stderr, flush=True)
 
     # ---- roofline of the dominant kernel, measured live (CUDA events on the streams the kernels are launched on) ---------------------
     peak, peak_src = measured_peak()
@@ -514,7 +515,7 @@ def main():
         info = scene.bvh_info()
         line = {
             "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
+            "ms_per_step": ms_per_step, "step_ms_rank0": step_ms, "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32",
             "data": ("the reference's own assets, ingested by the library" if "real assets" in desc else
                      "synthetic (procedural stand-ins: the reference ships neither the Dragon OBJ nor the HDR skysphere)")
                     if args.workload != "c1" else "bundled cornell_pbr.obj (parsed by the reference, committed fixture)",
