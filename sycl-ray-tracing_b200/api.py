@@ -326,8 +326,9 @@ class FlattenedBVH:
         a, d, t = FP(), FP(), FP()
         B.check(L.b200rt_bvh_get_arrays(bvh._h, C.byref(a), C.byref(d), C.byref(t)))
         n = info["n_inner_nodes"]
-        self.axis = np.ctypeslib.as_array(a, shape=(n, 16))
-        self.diag = np.ctypeslib.as_array(d, shape=(n, 16))
+        self.axis = np.ctypeslib.as_array(a, shape=(n, 16)) if (n and a) else np.zeros((0, 16), np.float32)
+        # device-built trees carry no diagonal slabs (has_diag_slabs = 0): no diag records
+        self.diag = np.ctypeslib.as_array(d, shape=(n, 16)) if (n and d and info["has_diag_slabs"]) else np.zeros((0, 16), np.float32)
         self.tris = np.ctypeslib.as_array(t, shape=(max(info["n_triangles"], 0), 12)) if info["n_triangles"] else np.zeros((0, 12), np.float32)
         # the 8-ary layout as a structured array (80-byte records, csrc/bvh_build.h WideNode)
         wp, wn = C.c_void_p(), C.c_int()
