@@ -151,7 +151,7 @@ int make_params(const b200rt_scene* s, const float* camera17, int w, int h, int 
     P.n_rank_tiles = b200rt_tiles_for_rank(w, h, d.rank, d.world);
     P.flags = d.flags;
     P.rx0 = P.ry0 = P.rw = P.rh = 0;
-    P.sample_begin = 0; P.sample_end = spp; P.acc_rng = nullptr; P.acc_sum = nullptr;
+    P.sample_begin = 0; P.sample_end = spp; P.stamp0 = 0; P.acc_rng = nullptr; P.acc_sum = nullptr;
     return B200RT_OK;
 }
 
@@ -293,7 +293,8 @@ cudaError_t wf_alloc(b200rt_scene* s, T** p, size_t n)
 // (multi-GPU) is latency-bound per pass and gains a little from a fourth chain (one rank of 8 emulated: 115.9 -> 112.2 ms)
 int wavefront_group_count(const RenderParams& P)
 {
-    static const int env_n = []() { const char* e = getenv("B200RT_WF_GROUPS"); int v = e ? atoi(e) : 0; return v > kMaxWfGroups ? kMaxWfGroups : v; }();
+    const char* e = getenv("B200RT_WF_GROUPS");          // read per frame (tools sweep it inside one process)
+    const int env_n = e ? std::min(atoi(e), kMaxWfGroups) : 0;
     if (env_n >= 1) return env_n;
     return (long long)P.n_rank_tiles * kTilePixels < 700000 ? 4 : 3;
 }
@@ -337,8 +338,17 @@ int ensure_wavefront(b200rt_scene* s, const RenderParams& P)
             CU(wf_alloc(s, &w.rng, n)); CU(wf_alloc(s, &w.sample, n)); CU(wf_alloc(s, &w.bounce, n)); CU(wf_alloc(s, &w.flags, n));
             CU(wf_alloc(s, &w.final_c, n)); CU(wf_alloc(s, &w.sample_c, n)); CU(wf_alloc(s, &w.thr, n)); CU(wf_alloc(s, &w.thr_next, n));
             CU(wf_alloc(s, &w.ray_o, 5 * n)); CU(wf_alloc(s, &w.ray_d, 5 * n)); CU(wf_alloc(s, &w.side_w, 4 * n));
-            CU(wf_alloc(s, &w.res_t, 5 * n)); CU(wf_alloc(s, &w.res_prim, 5 * n)); CU(wf_alloc(s, &w.res_tslot, 5 * n));
+            CU(wf_alloc(s, &w.res, 5 * n));
             CU(wf_alloc(s, &w.queue, 5 * n)); CU(wf_alloc(s, &w.counters, 8)); CU(wf_alloc(s, &w.rays_total, 1));
+            // rings of the barrier-free continuation (async.cu); without them the group finishes with wf_tail
+            WfAsyncMem& a = s->wf[g].amem;
+            a = WfAsyncMem{};
+            if (s->dev.has_wide && wavefront_async_fits(most))
+            {
+                a.ray_log2 = wavefront_async_ray_log2(most); a.chunk_words = wavefront_async_chunk_words(most);
+                CU(wf_alloc(s, &a.ray_ring, (size_t)1 << a.ray_log2)); CU(wf_alloc(s, &a.ctrl, 64));
+                CU(wf_alloc(s, &a.chunk_cnt, (size_t)a.chunk_words)); CU(wf_alloc(s, &a.chunk_live, (size_t)a.chunk_words));
+            }
         }
         s->wf_groups = G;
     }
@@ -373,7 +383,7 @@ int ensure_persistent(b200rt_scene* s)
     CU(pw_alloc(s, &w.rng, m)); CU(pw_alloc(s, &w.sample, m)); CU(pw_alloc(s, &w.bounce, m)); CU(pw_alloc(s, &w.flags, m));
     CU(pw_alloc(s, &w.final_c, m)); CU(pw_alloc(s, &w.sample_c, m)); CU(pw_alloc(s, &w.thr, m)); CU(pw_alloc(s, &w.thr_next, m));
     CU(pw_alloc(s, &w.ray_o, 5 * m)); CU(pw_alloc(s, &w.ray_d, 5 * m)); CU(pw_alloc(s, &w.side_w, 4 * m));
-    CU(pw_alloc(s, &w.res_t, 5 * m)); CU(pw_alloc(s, &w.res_prim, 5 * m)); CU(pw_alloc(s, &w.res_tslot, 5 * m));
+    CU(pw_alloc(s, &w.res, 5 * m));
     CU(pw_alloc(s, &w.queue, 5 * m)); CU(pw_alloc(s, &w.counters, (size_t)8)); CU(pw_alloc(s, &w.rays_total, (size_t)1));
     w.n_slots = n; w.tile_stride = 1; w.tile_offset = 0;
     s->pw_cap = n;

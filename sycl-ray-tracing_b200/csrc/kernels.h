@@ -81,6 +81,14 @@ cudaError_t launch_wavefront_tail(const SceneDev& S, const RenderParams& P, cons
                                   float4* out_tiles, cudaStream_t stream);
 int wavefront_tail_max_ctas();
 
+// barrier-free continuation that pools rays and shading work across warps through device-wide ticket rings (async.cu)
+int wavefront_async_ray_log2(int n_slots);
+int wavefront_async_chunk_words(int n_slots);
+bool wavefront_async_fits(int n_slots);
+int wavefront_async_max_ctas();
+cudaError_t launch_wavefront_async(const SceneDev& S, const RenderParams& P, const WfBuffers& B, const WfAsyncMem& M, int ctas,
+                                   const float4* fb_in_rowmajor, float4* out_tiles, cudaStream_t stream);
+
 // persistent integrator (persist.cu): one launch per frame, every warp its own wavefront machine
 int persistent_grid();
 int persistent_slots(int grid);

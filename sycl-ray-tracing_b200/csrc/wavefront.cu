@@ -297,16 +297,42 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
     if ((e = cudaEventRecord(fork_event, stream)) != cudaSuccess) return e;
     cudaError_t err = cudaSuccess;
 #define WF_TRY(expr) do { if (err == cudaSuccess) { const cudaError_t e__ = (expr); if (e__ != cudaSuccess) err = e__; } } while (0)
-    struct GroupRun { RenderParams P; int parity; bool finished, forked; int slot_grid; long long it, poll_it; bool poll_pending; unsigned int tail_below; };
+    struct GroupRun { RenderParams P; int parity; bool finished, forked, barrier_free; int slot_grid; long long it, poll_it; bool poll_pending; unsigned int tail_below; };
     // barrier-free tail (persist.cu): when a group has at most B200RT_WF_TAIL_PCT % of its pixels (and at most B200RT_WF_TAIL_CAP) left,
     // or is smaller than B200RT_WF_TAIL_MIN pixels to begin with. 8-ary layout, default trace kernel only; not in the per-kernel timing modes.
     // Measured on C3 at 64 spp (profiles/r2_tail.jsonl): whole frame 433.3 ms without, 428.9 with a 30 k cap (445 with 100 k: the tail
     // kernel's throughput is below the pass kernels', it only pays once passes are latency-bound); one rank of 8: 108.1 -> 101.7 ms at 20 %.
-    static const int tail_pct = []() { const char* e = getenv("B200RT_WF_TAIL_PCT"); int v = e ? atoi(e) : 20; return v < 0 ? 0 : (v > 100 ? 100 : v); }();
-    static const long long tail_cap = []() { const char* e = getenv("B200RT_WF_TAIL_CAP"); return e ? atoll(e) : 30000ll; }();
-    static const int tail_min = []() { const char* e = getenv("B200RT_WF_TAIL_MIN"); return e ? atoi(e) : 16384; }();
-    const bool tail_ok = coop && tail_pct > 0 && !timing;
+    // (the knobs are read per frame: tools/async_bench.py sweeps them inside one process)
+    auto env_ll = [](const char* name, long long dflt) { const char* e = getenv(name); return e ? atoll(e) : dflt; };
+    const int tail_pct = (int)std::min(100ll, std::max(0ll, env_ll("B200RT_WF_TAIL_PCT", 20)));
+    const long long tail_cap = env_ll("B200RT_WF_TAIL_CAP", 30000);
+    const int tail_min = (int)env_ll("B200RT_WF_TAIL_MIN", 16384);
+    // Which barrier-free kernel finishes a group: wf_tail (persist.cu), or — B200RT_FLAG_WF_ASYNC / B200RT_WF_ASYNC=1 — wf_async
+    // (async.cu: shading by chunk-owning warps, tracing pooled across the whole grid through a device-wide ticket ring), which takes
+    // over below B200RT_WF_ASYNC_PCT % of the group's pixels (and B200RT_WF_ASYNC_CAP), or from the first pass on for groups of at
+    // most B200RT_WF_ASYNC_MIN pixels. Bit-identical; measured slower than passes + wf_tail everywhere: a study path.
+    const bool async_env = env_ll("B200RT_WF_ASYNC", 0) != 0 || (P.flags & B200RT_FLAG_WF_ASYNC) != 0;
+    const int async_pct = (int)std::min(100ll, std::max(0ll, env_ll("B200RT_WF_ASYNC_PCT", 20)));
+    const long long async_cap = env_ll("B200RT_WF_ASYNC_CAP", 60000);
+    const int async_min = (int)env_ll("B200RT_WF_ASYNC_MIN", 70000);
+    const bool passes_only = (P.flags & B200RT_FLAG_WF_PASSES_ONLY) != 0;
+    const bool tail_ok = coop && tail_pct > 0 && !timing && !passes_only;
     const int tail_ctas = tail_ok ? std::max(1, wavefront_tail_max_ctas() / n_groups) : 0;
+    const bool async_ok = coop && async_env && !timing && !passes_only;
+    const int async_ctas = async_ok ? std::max(1, wavefront_async_max_ctas() / n_groups) : 0;
+    // one of the two for group g: launches the barrier-free kernel that finishes the group behind whatever is queued on its stream
+    auto group_async = [&](int g) { return async_ok && groups[g].amem.ray_ring != nullptr && wavefront_async_fits(groups[g].buf.n_slots); };
+    auto finish_group = [&](int g, const RenderParams& GP) -> cudaError_t
+    {
+        const WfGroup& G = groups[g];
+        WfTimeline::Launch tlt = { g, 0, 0, 0 };
+        if (tln) { tlt.e0 = tln->used; cudaEventRecord(tln->take(), G.stream); }
+        const cudaError_t fe = group_async(g) ? launch_wavefront_async(S, GP, G.buf, G.amem, async_ctas, fb_in_rowmajor, out_tiles, G.stream)
+                                              : launch_wavefront_tail(S, GP, G.buf, tail_ctas, fb_in_rowmajor, out_tiles, G.stream);
+        if (tln) { tlt.e1 = tln->used; cudaEventRecord(tln->take(), G.stream); tln->tails.push_back(tlt); }
+        launches += 2;
+        return fe;
+    };
     GroupRun run[kMaxWfGroups];
     for (int g = 0; g < n_groups; g++)
     {
@@ -316,7 +342,11 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
         R.P.rank = P.rank + g * P.world;
         R.P.world = P.world * n_groups;
         R.P.n_rank_tiles = G.buf.n_slots / kTilePixels;
-        R.parity = 0; R.it = 0; R.poll_it = 0; R.poll_pending = false; R.forked = false;
+        // results carry the slot's shading-step count as a stamp (async.cu): every frame starts the count somewhere else, so that
+        // what an earlier frame left in the result records cannot pass for this frame's
+        static unsigned int frame_nonce = 0u;
+        R.P.stamp0 = (int)((frame_nonce += 1000003u) & 0x7ffffffu);
+        R.parity = 0; R.it = 0; R.poll_it = 0; R.poll_pending = false; R.forked = false; R.barrier_free = false;
         R.slot_grid = (G.buf.n_slots + 255) / 256;
         R.finished = R.slot_grid <= 0;
         if (err != cudaSuccess) { R.finished = true; continue; }
@@ -329,15 +359,14 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
         if (R.finished) continue;
         wf_init<<<R.slot_grid, 256, 0, G.stream>>>(S, R.P, G.buf, fb_in_rowmajor, out_tiles);
         launches++;
-        R.tail_below = (unsigned int)std::min<long long>(tail_cap, (long long)G.buf.n_slots * tail_pct / 100);
-        if (tail_ok && G.buf.n_slots <= tail_min)
+        const bool as = group_async(g);
+        R.barrier_free = as || tail_ok;
+        R.tail_below = as ? (unsigned int)std::min<long long>(async_cap, (long long)G.buf.n_slots * async_pct / 100)
+                          : (unsigned int)std::min<long long>(tail_cap, (long long)G.buf.n_slots * tail_pct / 100);
+        if (R.barrier_free && G.buf.n_slots <= (as ? async_min : tail_min))
         {
             // a group this small is latency-bound from its first pass on: barrier-free from the start
-            WfTimeline::Launch tlt = { g, 0, 0, 0 };
-            if (tln) { tlt.e0 = tln->used; cudaEventRecord(tln->take(), G.stream); }
-            WF_TRY(launch_wavefront_tail(S, R.P, G.buf, tail_ctas, fb_in_rowmajor, out_tiles, G.stream));
-            if (tln) { tlt.e1 = tln->used; cudaEventRecord(tln->take(), G.stream); tln->tails.push_back(tlt); }
-            launches += 2;
+            WF_TRY(finish_group(g, R.P));
             R.finished = true;
         }
     }
@@ -360,14 +389,10 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
             {
                 R.poll_pending = false;
                 if (*G.host_active == 0) { R.finished = true; remaining--; continue; }
-                if (tail_ok && *G.host_active <= R.tail_below)
+                if (R.barrier_free && *G.host_active <= R.tail_below)
                 {
-                    // few pixels left: no more passes; one barrier-free launch finishes them (persist.cu), behind the passes already queued
-                    WfTimeline::Launch tlt = { g, 0, 0, 0 };
-                    if (tln) { tlt.e0 = tln->used; cudaEventRecord(tln->take(), G.stream); }
-                    WF_TRY(launch_wavefront_tail(S, R.P, G.buf, tail_ctas, fb_in_rowmajor, out_tiles, G.stream));
-                    if (tln) { tlt.e1 = tln->used; cudaEventRecord(tln->take(), G.stream); tln->tails.push_back(tlt); }
-                    launches += 2;
+                    // few pixels left: no more passes; one barrier-free launch finishes them, behind the passes already queued
+                    WF_TRY(finish_group(g, R.P));
                     R.finished = true; remaining--;
                     continue;
                 }

@@ -537,3 +537,64 @@ def test_denoise_stage(rt, golden_cameras):
     print("rmse noisy", rmse(noisy), "denoised", rmse(den4), "blend 0.5", rmse(half))
     assert rmse(den4) < 0.8 * rmse(noisy) and rmse(half) < rmse(noisy)
     assert np.allclose(half[..., :3], 0.5 * den4[..., :3] + 0.5 * noisy[..., :3], atol=1e-6)
+
+
+# ---- barrier-free continuation that pools work across warps (csrc/async.cu) -----------------------------------------------------------
+def test_async_continuation_equals_passes_bit_for_bit(rt, golden_scenes, golden_cameras):
+    """wf_async (B200RT_FLAG_WF_ASYNC) finishes a tile group with chunk-owning shader warps and tracer warps fed by a device-wide ticket
+    ring: same device functions, same per-pixel RNG streams -> the frame and the ray count equal the pure pass-synchronous frame's
+    (B200RT_FLAG_WF_PASSES_ONLY), the default frame's (passes + per-warp tail) and the megakernel's, bit for bit: groups that are barrier-free from the first pass
+    (small frames), groups that switch once few pixels are left (a 1280x720 frame), interleaved ranks with a non-black incoming
+    framebuffer, spheres, emissive triangles (MIS.obj), and the dead-ray elimination (slots that are alive without a ray)."""
+    from sycl_ray_tracing_b200 import scenes
+    for key, fixture in [("cornell", "render_cornell_env.npz"), ("mis", "render_mis_env.npz")]:
+        g = load_golden(fixture)
+        w, h, spp, b = int(g["w"]), int(g["h"]), int(g["spp"]), int(g["bounces"])
+        a = scene_arrays(golden_scenes, key)
+        sc = rt.Scene(a["tri9"], a["mat_idx"], a["mats10"], a["emissive"], skysphere=g["env"])
+        c = rt.Camera.from_array17(golden_cameras[key])
+        mega, st_m = sc.render(c, w, h, spp, b, integrator=rt.INTEGRATOR_MEGAKERNEL)
+        asy, st_a = sc.render(c, w, h, spp, b, flags=rt.FLAG_WF_ASYNC)
+        pas, st_p = sc.render(c, w, h, spp, b, flags=rt.FLAG_WF_PASSES_ONLY)
+        tail, st_t = sc.render(c, w, h, spp, b)
+        for name, img, st in (("async", asy, st_a), ("passes", pas, st_p), ("warp tail", tail, st_t)):
+            assert np.array_equal(bits(mega), bits(img)), f"{fixture} {name}: {(bits(mega) != bits(img)).any(axis=-1).sum()} pixels differ"
+            assert st["rays"] == st_m["rays"], (fixture, name, st["rays"], st_m["rays"])
+        assert st_a["gpu_launches"] < st_p["gpu_launches"], "the small frame is barrier-free from its first pass"
+        assert_radiance_parity(asy, g["image"], f"async {fixture}")
+        rng = np.random.default_rng(11)
+        w2, h2 = 100, 70
+        fb0 = (rng.random((h2, w2, 4)) * 0.2).astype(np.float32)
+        want = fb0.copy(); sc.render(c, w2, h2, 3, 4, framebuffer=want, flags=rt.FLAG_WF_PASSES_ONLY)
+        got = fb0.copy()
+        for rank in range(3):
+            sc.render(c, w2, h2, 3, 4, framebuffer=got, rank=rank, world=3, flags=rt.FLAG_WF_ASYNC)
+        assert np.array_equal(bits(want), bits(got)), "ranks + non-black framebuffer"
+    g = load_golden("render_c3small.npz")
+    c3 = scenes.c3_scene(roughness=float(g["roughness"]), nu=int(g["nu"]), nv=int(g["nv"]), sky_w=int(g["sky_w"]), sky_h=int(g["sky_h"]))
+    sc = scene_of(rt, c3)
+    for (w, h, spp) in ((640, 360, 6), (1280, 720, 4), (1920, 1080, 2)):
+        pas, st_p = sc.render(c3["camera"], w, h, spp, 8, flags=rt.FLAG_WF_PASSES_ONLY)
+        asy, st_a = sc.render(c3["camera"], w, h, spp, 8, flags=rt.FLAG_WF_ASYNC)
+        assert np.array_equal(bits(pas), bits(asy)), f"c3 {w}x{h}: {(bits(pas) != bits(asy)).any(axis=-1).sum()} pixels differ"
+        assert st_p["rays"] == st_a["rays"] and st_a["gpu_launches"] < st_p["gpu_launches"]
+        skip_p, st_sp = sc.render(c3["camera"], w, h, spp, 8, flags=rt.FLAG_WF_PASSES_ONLY | rt.FLAG_SKIP_DEAD_RAYS)
+        skip_a, st_sa = sc.render(c3["camera"], w, h, spp, 8, flags=rt.FLAG_WF_ASYNC | rt.FLAG_SKIP_DEAD_RAYS)
+        assert np.array_equal(bits(pas), bits(skip_a)) and st_sp["rays"] == st_sa["rays"] < st_p["rays"]
+    # one rank of 8 of the 1080p frame (the shape the continuation exists for), twice: the rings are re-armed per launch
+    want, st_w = sc.render(c3["camera"], 1920, 1080, 3, 8, rank=5, world=8, flags=rt.FLAG_WF_PASSES_ONLY)
+    for _ in range(2):
+        got, st_g = sc.render(c3["camera"], 1920, 1080, 3, 8, rank=5, world=8, flags=rt.FLAG_WF_ASYNC)
+        assert np.array_equal(bits(want), bits(got)) and st_w["rays"] == st_g["rays"]
+    # analytic spheres finish inside the tracer lanes
+    gs = load_golden("sphere_cornell.npz")
+    a = scene_arrays(golden_scenes, "cornell")
+    n = len(a["tri9"])
+    mat_idx = np.concatenate([a["mat_idx"], np.array([len(gs["mats10"]) - 1], np.int32)])
+    sph = [((float(gs["spheres4"][0, 0]), float(gs["spheres4"][0, 1]), float(gs["spheres4"][0, 2])), float(gs["spheres4"][0, 3]), n)]
+    scs = rt.Scene(a["tri9"], mat_idx, gs["mats10"], a["emissive"], spheres=sph, skysphere=gs["env"])
+    cs = rt.Camera.from_array17(golden_cameras["cornell"])
+    ws, hs, spps, bs = int(gs["w"]), int(gs["h"]), int(gs["spp"]), int(gs["bounces"])
+    m, st_m = scs.render(cs, ws, hs, spps, bs, integrator=rt.INTEGRATOR_MEGAKERNEL)
+    s_a, st_a = scs.render(cs, ws, hs, spps, bs, flags=rt.FLAG_WF_ASYNC)
+    assert np.array_equal(bits(m), bits(s_a)) and st_m["rays"] == st_a["rays"]
