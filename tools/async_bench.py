@@ -39,6 +39,8 @@ for world in (1, 8):
             add(f"async from the start, shaders {sh}", world, WF_ASYNC_SHADERS=sh, WF_ASYNC_MIN=10000000)
     if "prof" in sets and world == int(os.environ.get("PROF_WORLD", "1")):
         add("async from the start, 1 group (profiling shape)", world, WF_ASYNC_MIN=10000000, WF_GROUPS=1, WF_ASYNC_SHADERS=os.environ.get("PROF_SHADERS", "1/4"))
+    if "default" in sets:
+        add("default (passes + per-warp tail)", world, 0)
     if "quick" in sets:
         add("warp tail (round-2 default)", world, 0)
         for sh in ("1/4", "1/3"):
