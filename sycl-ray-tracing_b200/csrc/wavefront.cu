@@ -24,8 +24,11 @@
 
 namespace b200rt {
 
+#ifndef WF_SHADE_BLOCK
+#define WF_SHADE_BLOCK 256              // threads per wf_shade CTA
+#endif
 #ifndef WF_SHADE_MIN_BLOCKS
-#define WF_SHADE_MIN_BLOCKS 4
+#define WF_SHADE_MIN_BLOCKS (1024 / WF_SHADE_BLOCK)      // 64 registers
 #endif
 
 __global__ void __launch_bounds__(256) wf_init(SceneDev S, RenderParams P, WfBuffers B, const float4* __restrict__ fb_in_rowmajor,
@@ -55,7 +58,7 @@ __global__ void __launch_bounds__(256) wf_init(SceneDev S, RenderParams P, WfBuf
     wf_enqueue(B.queue, &B.counters[3], q_path, ((unsigned int)slot << 3) | 4u);
 }
 
-__global__ void __launch_bounds__(256, WF_SHADE_MIN_BLOCKS) wf_shade(SceneDev S, RenderParams P, WfBuffers B, const float4* __restrict__ fb_in_rowmajor,
+__global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) wf_shade(SceneDev S, RenderParams P, WfBuffers B, const float4* __restrict__ fb_in_rowmajor,
                                                 float4* __restrict__ out_tiles, int parity)
 {
     const int slot = blockIdx.x * blockDim.x + threadIdx.x;
@@ -78,11 +81,9 @@ __global__ void __launch_bounds__(256, WF_SHADE_MIN_BLOCKS) wf_shade(SceneDev S,
     const unsigned int done_mask = __ballot_sync(0xffffffffu, R.pixel_done);
     if ((threadIdx.x & 31) == 0 && done_mask) atomicSub(&B.counters[2], (unsigned int)__popc(done_mask));
     const unsigned int s3 = (unsigned int)slot << 3;
-    wf_enqueue(B.queue, q_count, R.q_path, s3 | 4u);
-    wf_enqueue(B.queue, q_count, R.q0, s3 | 0u);
-    wf_enqueue(B.queue, q_count, R.q1, s3 | 1u);
-    wf_enqueue(B.queue, q_count, R.q2, s3 | 2u);
-    wf_enqueue(B.queue, q_count, R.q3, s3 | 3u);
+    const bool q[5] = { R.q_path, R.q0, R.q1, R.q2, R.q3 };
+    const unsigned int entry[5] = { s3 | 4u, s3 | 0u, s3 | 1u, s3 | 2u, s3 | 3u };
+    wf_enqueue5(B.queue, q_count, q, entry);
 }
 
 // ablation variant (B200RT_FLAG_SIMPLE_TRACE): one ray per lane, grid-stride over the queue (the warp waits for its slowest ray)
@@ -418,7 +419,7 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
             if (timing) cudaEventRecord(tev[1], G.stream);
             if (tln) { tll.e1 = tln->used; cudaEventRecord(tln->take(), G.stream); }
             R.parity ^= 1;
-            wf_shade<<<R.slot_grid, 256, 0, G.stream>>>(S, R.P, G.buf, fb_in_rowmajor, out_tiles, R.parity);
+            wf_shade<<<(G.buf.n_slots + WF_SHADE_BLOCK - 1) / WF_SHADE_BLOCK, WF_SHADE_BLOCK, 0, G.stream>>>(S, R.P, G.buf, fb_in_rowmajor, out_tiles, R.parity);
             if (tln) { tll.e2 = tln->used; cudaEventRecord(tln->take(), G.stream); tln->launches.push_back(tll); }
             launches += 2;
             WF_TRY(cudaGetLastError());

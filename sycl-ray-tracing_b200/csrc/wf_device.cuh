@@ -28,6 +28,28 @@ __device__ __forceinline__ void wf_enqueue(unsigned int* queue, unsigned int* co
     if (pred) queue[base + __popc(mask & ((1u << lane) - 1u))] = entry;
 }
 
+// As wf_enqueue for up to five entries per lane with ONE reservation per warp (the shade kernels: path ray + four side rays):
+// the warp's entries are laid out kind-major — all lanes' entry 0, then all lanes' entry 1, ... — so 32 neighbouring pixels' rays
+// of one kind still sit side by side, and the warp waits for one returned atomic instead of five.
+__device__ __forceinline__ void wf_enqueue5(unsigned int* queue, unsigned int* counter, const bool q[5], const unsigned int entry[5])
+{
+    const int lane = threadIdx.x & 31;
+    const unsigned int below = (1u << lane) - 1u;
+    unsigned int m[5], total = 0u;
+#pragma unroll
+    for (int k = 0; k < 5; k++) { m[k] = __ballot_sync(0xffffffffu, q[k]); total += __popc(m[k]); }
+    if (!total) return;
+    unsigned int base = 0;
+    if (lane == 0) base = atomicAdd(counter, total);
+    base = __shfl_sync(0xffffffffu, base, 0);
+#pragma unroll
+    for (int k = 0; k < 5; k++)
+    {
+        if (q[k]) queue[base + __popc(m[k] & below)] = entry[k];
+        base += __popc(m[k]);
+    }
+}
+
 __device__ __forceinline__ void wf_store_ray(const WfBuffers& B, int k, int slot, v3 o, v3 d, float tmax, int kind)
 {
     const size_t i = (size_t)k * B.n_slots + slot;
@@ -425,32 +447,10 @@ __device__ __forceinline__ void st_relaxed(unsigned int* p, unsigned int v) { as
 __device__ __forceinline__ void st_release(unsigned int* p, unsigned int v) { asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 __device__ __forceinline__ void red_add_relaxed(unsigned int* p, unsigned int v) { asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory"); }
 
-// every lane of the warp calls this; lanes with `pred` append `payload`. release: the lane's earlier stores become visible
-// before the entry (then cleared: a lane's later entries follow the same MEMBAR in program order).
-__device__ __forceinline__ unsigned int ring_push(const WfRing& R, bool pred, unsigned int payload, bool& release)
-{
-    const unsigned int m = __ballot_sync(0xffffffffu, pred);
-    if (!m) return 0u;
-    const int lane = threadIdx.x & 31;
-    const int leader = __ffs(m) - 1;
-    unsigned int base = 0;
-    if (lane == leader) base = atomicAdd(R.ctrl + 1, (unsigned int)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if (pred)
-    {
-        const unsigned int i = base + __popc(m & ((1u << lane) - 1u));
-        unsigned int* p = R.buf + R.pos(i);
-        while (ld_relaxed(p) != kRingEmpty) { }           // the consumer of this word one lap ago has long put the sentinel back
-        const unsigned int e = (R.tag(i) << kRingPayloadBits) | payload;
-        if (release) { st_release(p, e); release = false; }
-        else st_relaxed(p, e);
-    }
-    return (unsigned int)__popc(m);
-}
-
-// As ring_push for up to five entries per lane (q[k] -> payload[k]) with ONE reservation for the whole warp: the entries are laid
-// out kind-major (all lanes' entry 0, then all lanes' entry 1, ...), the sentinel checks of a lane's entries are in flight
-// together. The lane's first store is a release store when `release` is set.
+// Every lane of the warp calls this; lane appends payload[k] for every k with q[k] — ONE reservation for the whole warp. The
+// entries are laid out kind-major (all lanes' entry 0, then all lanes' entry 1, ...), the sentinel checks of a lane's entries
+// are in flight together. release: the lane's earlier stores become visible before its first entry (its later entries follow
+// the same MEMBAR in program order).
 __device__ __forceinline__ unsigned int ring_push5(const WfRing& R, const bool q[5], const unsigned int payload[5], bool release)
 {
     const int lane = threadIdx.x & 31;
@@ -511,6 +511,7 @@ __device__ __forceinline__ bool ring_poll(const WfRing& R, unsigned int ticket, 
 struct CoopQueueRing
 {
     static constexpr bool kRing = true;
+    static constexpr bool kCacheEntries = false;
     WfRing rays;                      // rays to trace
     unsigned int* cnt;                // per chunk of 32 slots: rays pushed and not traced yet (owner-major, see chunk_index)
     unsigned int* chunk_live;         // per chunk: slots not finished yet (written by the chunk's shader warp only)
@@ -522,6 +523,7 @@ struct CoopQueueRing
 struct CoopQueueShared
 {
     static constexpr bool kRing = false;
+    static constexpr bool kCacheEntries = true;       // blocks of at most kWarpBlock entries: a claimed block's entries live in registers
     unsigned int* head; unsigned int n_rays, warp_block;
     __device__ __forceinline__ bool claim(int lane, unsigned int& blk_next, unsigned int& blk_end)
     {
@@ -536,6 +538,7 @@ struct CoopQueueShared
 struct CoopQueuePrivate
 {
     static constexpr bool kRing = false;
+    static constexpr bool kCacheEntries = false;
     unsigned int next, end;
     __device__ __forceinline__ bool claim(int, unsigned int& blk_next, unsigned int& blk_end)
     {
@@ -562,7 +565,8 @@ __device__ __forceinline__ void coop_trace_queue(const SceneDev& S, const WfBuff
     bool active = false;
     size_t r = 0;
     int mode = TRACE_CLOSEST;
-    unsigned int blk_next = 0, blk_end = 0;                    // warp-uniform: the warp's current block of queue entries
+    unsigned int blk_next = 0, blk_end = 0, blk_base = 0;      // warp-uniform: the warp's current block of queue entries
+    unsigned int qe[kWarpBlock / 32 > 0 ? kWarpBlock / 32 : 1] = {};   // kCacheEntries: this lane's share of the block's entries
     unsigned int head = 0, dcount = 0, qtris = 0;              // warp-uniform: descriptor ring
     bool exhausted = false;                                    // warp-uniform
     unsigned int ent = 0u, ticket = 0u;                        // ring source: the lane's queue entry; its ticket while it waits for one
@@ -630,16 +634,55 @@ __device__ __forceinline__ void coop_trace_queue(const SceneDev& S, const WfBuff
         unsigned int idle = __ballot_sync(FULL, !active);
         if (idle && !exhausted && (idle == FULL || __popc(idle) >= kRefillThreshold))
         {
-            if (blk_next >= blk_end && !src.claim(lane, blk_next, blk_end)) exhausted = true;
+            if (blk_next >= blk_end)
+            {
+                if (!src.claim(lane, blk_next, blk_end)) exhausted = true;
+                else if constexpr (Source::kCacheEntries)
+                {
+                    // the whole block's entries at once (lane l holds entries l, 32 + l, ...): the refills below then cost one
+                    // dependent round trip (the ray record) instead of two
+                    blk_base = blk_next;
+#pragma unroll
+                    for (int j = 0; j < kWarpBlock / 32; j++)
+                    {
+                        const unsigned int qi = blk_base + 32u * j + (unsigned int)lane;
+                        qe[j] = qi < blk_end ? queue[qi] : 0u;
+                    }
+#ifndef B200RT_NO_RAY_PREFETCH
+                    // ... and the ray records those entries name start moving towards L1 now (a pass kernel reads each of them
+                    // exactly once, through L1: see the load below)
+#pragma unroll
+                    for (int j = 0; j < kWarpBlock / 32; j++)
+                        if (blk_base + 32u * j + (unsigned int)lane < blk_end)
+                        {
+                            const size_t pr = (size_t)(qe[j] & 7u) * n + (qe[j] >> 3);
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(B.ray_o + pr));
+                            asm volatile("prefetch.global.L1 [%0];" ::"l"(B.ray_d + pr));
+                        }
+#endif
+                }
+            }
             if (blk_next < blk_end)
             {
                 const unsigned int idx = blk_next + __popc(idle & lanes_below);
+                unsigned int e = 0u;
+                if constexpr (Source::kCacheEntries)
+                {
+                    const unsigned int rel = idx - blk_base;
+#pragma unroll
+                    for (int j = 0; j < kWarpBlock / 32; j++)
+                    {
+                        const unsigned int v = __shfl_sync(FULL, qe[j], (int)(rel & 31u));
+                        if ((rel >> 5) == (unsigned int)j) e = v;
+                    }
+                }
                 if (!active && idx < blk_end)
                 {
-                    const unsigned int e = queue[idx];
+                    if constexpr (!Source::kCacheEntries) e = queue[idx];
                     const int slot = (int)(e >> 3), k = (int)(e & 7u);
                     r = (size_t)k * n + slot;
-                    const float4 ro4 = wf_ld(B.ray_o + r), rd4 = wf_ld(B.ray_d + r);
+                    // (kCacheEntries = a pass kernel: the records were written by the previous launch, plain loads find the prefetched lines)
+                    const float4 ro4 = Source::kCacheEntries ? B.ray_o[r] : wf_ld(B.ray_o + r), rd4 = Source::kCacheEntries ? B.ray_d[r] : wf_ld(B.ray_d + r);
                     const int kind = __float_as_int(rd4.w);
                     mode = kind == SIDE_SHADOW ? TRACE_SHADOW : (kind == SIDE_CLOSEST_LIGHT ? TRACE_CLOSEST : TRACE_ANY);
                     const int tmode = spheres ? TRACE_CLOSEST : mode;
