@@ -431,6 +431,8 @@ def main():
         stats = None
         if not primary_only:
             scene.render(cam, w, h, min(spp, 2), bounces, framebuffer=fb, integrator=args.integrator, flags=args.flags)       # allocations of this entry point
+        else:
+            scene.trace_primary_into(cam, w, h, prim_h, t_h, flags=args.flags)                                              # allocations of this entry point
         for i in range(max(1, min(args.steps, 3))):
             fb[...] = (0.0, 0.0, 0.0, 1.0)
             torch.cuda.synchronize()

@@ -189,6 +189,10 @@ void b200rt_hdr_destroy(b200rt_hdr* hdr);
                                             the group is traced by whichever tracer lane is free, through a device-wide ticket ring) instead of the
                                             default wf_tail (csrc/persist.cu: every warp finishes a few slots of its own). Also: B200RT_WF_ASYNC=1.
                                             Bit-identical frames; measured slower on every configuration, hence not the default */
+#define B200RT_FLAG_WF_DETACH 4096        /* wavefront study: after B200RT_WF_DETACH_AT passes (default 36) the B200RT_WF_DETACH_SLOTS pixels of a device that lag
+                                            furthest behind leave the passes for a barrier-free kernel on a stream of its own (csrc/persist.cu
+                                            launch_wavefront_detach). Bit-identical; the detached pixels run 1.5-2.3x faster per step, the passes that share
+                                            the machine with them slower: no net gain, hence not the default. Also: B200RT_WF_DETACH=1 */
 #define B200RT_FLAG_LINEAR_TILES 256     /* b200rt_render_tiles_device: the tile buffer receives each pixel's mean radiance (`final_color / spp`,
                                             render_kernel.cpp:167) instead of the tone-mapped value; b200rt_untile_accumulate_device then does
                                             `framebuffer += final; tone map` (:169-180) on the gathering device, so the incoming framebuffer is

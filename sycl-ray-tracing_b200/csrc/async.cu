@@ -58,7 +58,7 @@ __device__ __forceinline__ bool async_slot_ready(const WfBuffers& B, int slot, i
 #pragma unroll
     for (int k = 0; k < 5; k++) stamp_k[k] = __float_as_uint(wf_ld(&B.res[(size_t)k * n + slot].w));
     if (st & WF_DONE) return false;
-    const unsigned int stamp = (unsigned int)st >> 4;
+    const unsigned int stamp = (unsigned int)st >> kWfSeqShift;
     bool ok = !(st & WF_ALIVE) || stamp_k[4] == stamp;
 #pragma unroll
     for (int k = 0; k < 4; k++)

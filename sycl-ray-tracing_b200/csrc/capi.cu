@@ -147,6 +147,7 @@ int make_params(const b200rt_scene* s, const float* camera17, int w, int h, int 
     P.spp = spp; P.max_bounces = bounces;
     P.rank = d.rank; P.world = d.world;
     P.tiles_x = (w + kTileDim - 1) / kTileDim;
+    P.tile_skew = tile_skew();
     P.tiles_y = (h + kTileDim - 1) / kTileDim;
     P.n_rank_tiles = b200rt_tiles_for_rank(w, h, d.rank, d.world);
     P.flags = d.flags;
@@ -309,8 +310,11 @@ int ensure_wavefront(b200rt_scene* s, const RenderParams& P)
         for (int g = 0; g < kMaxWfGroups; g++)
         {
             CU(cudaStreamCreateWithFlags(&s->wf[g].stream, cudaStreamNonBlocking));
+            CU(cudaStreamCreateWithFlags(&s->wf[g].detach_stream, cudaStreamNonBlocking));
             CU(cudaEventCreateWithFlags(&s->wf[g].poll_event, cudaEventDisableTiming));
             CU(cudaEventCreateWithFlags(&s->wf[g].join_event, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s->wf[g].detach_ready, cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&s->wf[g].detach_join, cudaEventDisableTiming));
             s->wf[g].host_active = s->h_active + g;
         }
     }
@@ -340,6 +344,15 @@ int ensure_wavefront(b200rt_scene* s, const RenderParams& P)
             CU(wf_alloc(s, &w.ray_o, 5 * n)); CU(wf_alloc(s, &w.ray_d, 5 * n)); CU(wf_alloc(s, &w.side_w, 4 * n));
             CU(wf_alloc(s, &w.res, 5 * n));
             CU(wf_alloc(s, &w.queue, 5 * n)); CU(wf_alloc(s, &w.counters, 8)); CU(wf_alloc(s, &w.rays_total, 1));
+            // memory of the early hand-over of the group's lagging pixels (persist.cu): control words, the list, the tail kernel's private queues
+            WfDetachMem& dm = s->wf[g].dmem;
+            dm = WfDetachMem{};
+            if (s->dev.has_wide)
+            {
+                dm.list_words = 65536; dm.ctas = wavefront_tail_max_ctas();
+                CU(wf_alloc(s, &dm.ctl, (size_t)wavefront_detach_ctl_words())); CU(wf_alloc(s, &dm.list, (size_t)dm.list_words));
+                CU(wf_alloc(s, &dm.queue, (size_t)wavefront_detach_queue_words(dm.ctas)));
+            }
             // rings of the barrier-free continuation (async.cu); without them the group finishes with wf_tail
             WfAsyncMem& a = s->wf[g].amem;
             a = WfAsyncMem{};
@@ -971,8 +984,11 @@ void b200rt_scene_destroy(b200rt_scene* s)
         for (int g = 0; g < kMaxWfGroups; g++)
         {
             if (s->wf[g].stream) cudaStreamDestroy(s->wf[g].stream);
+            if (s->wf[g].detach_stream) cudaStreamDestroy(s->wf[g].detach_stream);
             if (s->wf[g].poll_event) cudaEventDestroy(s->wf[g].poll_event);
             if (s->wf[g].join_event) cudaEventDestroy(s->wf[g].join_event);
+            if (s->wf[g].detach_ready) cudaEventDestroy(s->wf[g].detach_ready);
+            if (s->wf[g].detach_join) cudaEventDestroy(s->wf[g].detach_join);
         }
         cudaEventDestroy(s->fork_event);
         cudaFreeHost(s->h_active);
@@ -1035,7 +1051,8 @@ int b200rt_render_tiles_device(b200rt_scene* s, const float* camera17, int w, in
         unsigned long long px = 0;
         for (int k = 0; k < P.n_rank_tiles; k++)
         {
-            int tile = P.rank + k * P.world, tx = tile % P.tiles_x, ty = tile / P.tiles_x;
+            int tx, ty;
+            tile_xy(P.rank + k * P.world, P.tiles_x, P.tile_skew, tx, ty);
             px += (unsigned long long)std::min(kTileDim, w - tx * kTileDim) * std::min(kTileDim, h - ty * kTileDim);
         }
         stats->samples = px * (unsigned long long)spp;
@@ -1062,7 +1079,8 @@ unsigned long long pixels_of_rank(const RenderParams& P, int w, int h)
     unsigned long long px = 0;
     for (int k = 0; k < P.n_rank_tiles; k++)
     {
-        const int tile = P.rank + k * P.world, tx = tile % P.tiles_x, ty = tile / P.tiles_x;
+        int tx, ty;
+        tile_xy(P.rank + k * P.world, P.tiles_x, P.tile_skew, tx, ty);
         px += (unsigned long long)std::min(kTileDim, w - tx * kTileDim) * std::min(kTileDim, h - ty * kTileDim);
     }
     return px;
@@ -1575,7 +1593,8 @@ int b200rt_trace_primary_device(b200rt_scene* s, const float* camera17, int w, i
         unsigned long long px = 0;
         for (int k = 0; k < P.n_rank_tiles; k++)
         {
-            int tile = P.rank + k * P.world, tx = tile % P.tiles_x, ty = tile / P.tiles_x;
+            int tx, ty;
+            tile_xy(P.rank + k * P.world, P.tiles_x, P.tile_skew, tx, ty);
             px += (unsigned long long)std::min(kTileDim, w - tx * kTileDim) * std::min(kTileDim, h - ty * kTileDim);
         }
         stats->rays = px; stats->samples = px;

@@ -10,6 +10,28 @@ constexpr int kTilePixels = kTileDim * kTileDim;
 constexpr int kPatchW = 8, kPatchH = 4;      // one warp = one 8x4 pixel patch
 constexpr int kStackSize = 64;
 
+// Which tile a rank's k-th tile is. Tiles are numbered L = 0 .. tiles_x * tiles_y - 1 and rank r owns the tiles with
+// L % world == r; L = ty * tiles_x + (tx + skew * ty) % tiles_x walks every tile row from a start column that moves `skew`
+// tiles per row (B200RT_TILE_SKEW, read once per process; RenderParams::tile_skew; the same map in distributed.py).
+// 0, the default, is plain row-major numbering: a world that divides tiles_x (1920 / 16 = 120 tiles, 8 ranks) then owns
+// whole tile COLUMNS. Measured on C3 / 8 GPUs (tools/rank_timing.py, every rank emulated on one GPU): columns give the ranks
+// 125.6 ... 127.6 M rays and 94 ... 113 ms (mean 103); a skew of 5 (every 8 x 8 block of tiles holds every rank 8 times)
+// evens the rays out to 126.0 ... 126.9 M and makes the ranks SLOWER, 104 ... 115 ms (mean 109): a rank's time is its chain
+// of dependent passes, not its ray count, and a rank that sees vertical slabs of the scene keeps a smaller
+// part of the BVH hot.
+#ifdef __CUDACC__
+#define B200RT_HD __host__ __device__
+#else
+#define B200RT_HD
+#endif
+B200RT_HD inline void tile_xy(int L, int tiles_x, int skew, int& tx, int& ty)
+{
+    ty = L / tiles_x;
+    const int c = L - ty * tiles_x;
+    tx = (c + tiles_x - (int)(((long long)skew * ty) % tiles_x)) % tiles_x;
+}
+B200RT_HD inline int tile_number(int tx, int ty, int tiles_x, int skew) { return ty * tiles_x + (int)((tx + (long long)skew * ty) % tiles_x); }
+
 struct MaterialDev   // SimpleMaterial (simple_material.h:6-13) without the junk alphas, two float4
 {
     float er, eg, eb, metalness;
@@ -62,8 +84,9 @@ struct RenderParams
 {
     CameraDev cam;
     int spp, max_bounces;
-    int rank, world;           // interleaved 16x16 tiles: tile_id % world == rank
+    int rank, world;           // interleaved 16x16 tiles: tile number % world == rank (tile_xy / tile_number above)
     int tiles_x, tiles_y;
+    int tile_skew;             // see tile_xy above
     int n_rank_tiles;          // tiles owned by this rank
     int flags;
     // region mode (b200rt_render_region, megakernel only): slots are the pixels of the rectangle [rx0, rx0 + rw) x [ry0, ry0 + rh)
@@ -104,13 +127,21 @@ struct WfAsyncMem
     int ray_log2, chunk_words;
 };
 
+// device memory of the early hand-over of a group's lagging pixels to a barrier-free kernel (persist.cu: launch_wavefront_detach)
+struct WfDetachMem
+{
+    unsigned int* ctl; unsigned int* list; unsigned int* queue;
+    int list_words, ctas;
+};
+
 // one interleaved tile group of the wavefront integrator: its state, stream and polling resources
 struct WfGroup
 {
     WfBuffers buf;
     WfAsyncMem amem;
-    cudaStream_t stream;
-    cudaEvent_t poll_event, join_event;
+    WfDetachMem dmem;
+    cudaStream_t stream, detach_stream;
+    cudaEvent_t poll_event, join_event, detach_ready, detach_join;
     unsigned int* host_active;      // pinned
 };
 

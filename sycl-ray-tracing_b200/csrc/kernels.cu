@@ -14,8 +14,8 @@ struct PixelSlot { int x, y; size_t out; bool inside; };
 __device__ __forceinline__ PixelSlot unit_pixel(const RenderParams& P, int unit, int lane)
 {
     const int k = unit >> 3, sub = unit & 7;
-    const int tile_id = P.rank + k * P.world;
-    const int tx = tile_id % P.tiles_x, ty = tile_id / P.tiles_x;
+    int tx, ty;
+    tile_xy(P.rank + k * P.world, P.tiles_x, P.tile_skew, tx, ty);
     PixelSlot s;
     s.x = tx * kTileDim + (sub & 1) * kPatchW + (lane & 7);
     s.y = ty * kTileDim + (sub >> 1) * kPatchH + (lane >> 3);
@@ -245,12 +245,12 @@ __global__ void __launch_bounds__(256) k_trace_rays(SceneDev S, const float* __r
 
 // ---- K4: tile-major (per-rank compact buffers, rank-major) -> row-major bottom-up RGBA --------------------------------------
 __global__ void __launch_bounds__(256) k_untile(const float4* __restrict__ tiles, int tiles_per_rank_padded, int world, int only_rank,
-                                                int w, int h, int tiles_x, float4* __restrict__ image)
+                                                int w, int h, int tiles_x, int skew, float4* __restrict__ image)
 {
     const int x = blockIdx.x * 16 + (threadIdx.x & 15);
     const int y = blockIdx.y * 16 + (threadIdx.x >> 4);
     if (x >= w || y >= h) return;
-    const int tile_id = (y / kTileDim) * tiles_x + (x / kTileDim);
+    const int tile_id = tile_number(x / kTileDim, y / kTileDim, tiles_x, skew);
     const int rank = tile_id % world, k = tile_id / world;
     if (only_rank >= 0 && rank != only_rank) return;
     const int lx = x % kTileDim, ly = y % kTileDim;
@@ -262,12 +262,12 @@ __global__ void __launch_bounds__(256) k_untile(const float4* __restrict__ tiles
 
 // K4 for B200RT_FLAG_LINEAR_TILES buffers: image (the incoming framebuffer) += mean radiance, tone map in place (:169-180)
 __global__ void __launch_bounds__(256) k_untile_accumulate(const float4* __restrict__ tiles, int tiles_per_rank_padded, int world, int w, int h,
-                                                           int tiles_x, float4* __restrict__ image)
+                                                           int tiles_x, int skew, float4* __restrict__ image)
 {
     const int x = blockIdx.x * 16 + (threadIdx.x & 15);
     const int y = blockIdx.y * 16 + (threadIdx.x >> 4);
     if (x >= w || y >= h) return;
-    const int tile_id = (y / kTileDim) * tiles_x + (x / kTileDim);
+    const int tile_id = tile_number(x / kTileDim, y / kTileDim, tiles_x, skew);
     const int rank = tile_id % world, k = tile_id / world;
     const int lx = x % kTileDim, ly = y % kTileDim;
     const int sub = (ly / kPatchH) * 2 + (lx / kPatchW);
@@ -281,7 +281,7 @@ cudaError_t launch_untile_accumulate(const float4* tiles, int tiles_per_rank_pad
 {
     const int tiles_x = (w + kTileDim - 1) / kTileDim, tiles_y = (h + kTileDim - 1) / kTileDim;
     dim3 grid(tiles_x, tiles_y);
-    k_untile_accumulate<<<grid, 256, 0, stream>>>(tiles, tiles_per_rank_padded, world, w, h, tiles_x, image);
+    k_untile_accumulate<<<grid, 256, 0, stream>>>(tiles, tiles_per_rank_padded, world, w, h, tiles_x, tile_skew(), image);
     return cudaGetLastError();
 }
 
@@ -361,6 +361,12 @@ cudaError_t launch_env_cdf_search(const SceneDev& S, const float* values, int n,
 
 // ---- launchers ----------------------------------------------------------------------------------------------------------------
 // SM count of the calling thread's current device (cached per device: one process may drive several GPU models)
+int tile_skew()
+{
+    static const int v = []() { const char* e = getenv("B200RT_TILE_SKEW"); const int k = e ? atoi(e) : 0; return k < 0 ? 0 : k; }();
+    return v;
+}
+
 int current_sm_count()
 {
     static int cache[64] = {};
@@ -434,7 +440,7 @@ cudaError_t launch_untile(const float4* tiles, int tiles_per_rank_padded, int wo
 {
     const int tiles_x = (w + kTileDim - 1) / kTileDim, tiles_y = (h + kTileDim - 1) / kTileDim;
     dim3 grid(tiles_x, tiles_y);
-    k_untile<<<grid, 256, 0, stream>>>(tiles, tiles_per_rank_padded, world, only_rank, w, h, tiles_x, image);
+    k_untile<<<grid, 256, 0, stream>>>(tiles, tiles_per_rank_padded, world, only_rank, w, h, tiles_x, tile_skew(), image);
     return cudaGetLastError();
 }
 

@@ -22,6 +22,8 @@ inline int traversal_layout(const SceneDev& S, int flags, bool coherent = false)
 
 // SM count of the current device (cached per device id)
 int current_sm_count();
+// B200RT_TILE_SKEW (device_types.h tile_xy), read once per process
+int tile_skew();
 
 cudaError_t launch_megakernel(const SceneDev& S, const RenderParams& P, const float4* fb_in_rowmajor, float4* out_tiles,
                               unsigned int* work_counter, unsigned long long* ray_counter, cudaStream_t stream);
@@ -80,6 +82,11 @@ cudaError_t wavefront_sum_rays(const WfGroup* groups, int n_groups, unsigned lon
 cudaError_t launch_wavefront_tail(const SceneDev& S, const RenderParams& P, const WfBuffers& B, int max_ctas, const float4* fb_in_rowmajor,
                                   float4* out_tiles, cudaStream_t stream);
 int wavefront_tail_max_ctas();
+// the lagging pixels of a group leave the passes early (persist.cu)
+int wavefront_detach_ctl_words();
+int wavefront_detach_queue_words(int ctas);
+cudaError_t launch_wavefront_detach(const SceneDev& S, const RenderParams& P, const WfBuffers& B, const WfDetachMem& D, unsigned int budget, int ctas,
+                                    const float4* fb_in_rowmajor, float4* out_tiles, cudaStream_t stream, cudaStream_t detach_stream, cudaEvent_t ready);
 
 // barrier-free continuation that pools rays and shading work across warps through device-wide ticket rings (async.cu)
 int wavefront_async_ray_log2(int n_slots);

@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(WF_SHADE_BLOCK, WF_SHADE_MIN_BLOCKS) wf_shade(
     ShadeOut R;
     R.q_path = R.q0 = R.q1 = R.q2 = R.q3 = R.pixel_done = false; R.flags = 0;
     const int flags_in = slot < n ? B.flags[slot] : WF_DONE;
-    if (!(flags_in & WF_DONE))
+    if (!(flags_in & (WF_DONE | WF_DETACHED)))
     {
         int x, y;
         wf_slot_pixel(P, slot, x, y);
@@ -298,7 +298,7 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
     if ((e = cudaEventRecord(fork_event, stream)) != cudaSuccess) return e;
     cudaError_t err = cudaSuccess;
 #define WF_TRY(expr) do { if (err == cudaSuccess) { const cudaError_t e__ = (expr); if (e__ != cudaSuccess) err = e__; } } while (0)
-    struct GroupRun { RenderParams P; int parity; bool finished, forked, barrier_free; int slot_grid; long long it, poll_it; bool poll_pending; unsigned int tail_below; };
+    struct GroupRun { RenderParams P; int parity; bool finished, forked, barrier_free, detach, detached; int slot_grid; long long it, poll_it; bool poll_pending; unsigned int tail_below; };
     // barrier-free tail (persist.cu): when a group has at most B200RT_WF_TAIL_PCT % of its pixels (and at most B200RT_WF_TAIL_CAP) left,
     // or is smaller than B200RT_WF_TAIL_MIN pixels to begin with. 8-ary layout, default trace kernel only; not in the per-kernel timing modes.
     // Measured on C3 at 64 spp (profiles/r2_tail.jsonl): whole frame 433.3 ms without, 428.9 with a 30 k cap (445 with 100 k: the tail
@@ -320,6 +320,14 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
     const bool tail_ok = coop && tail_pct > 0 && !timing && !passes_only;
     const int tail_ctas = tail_ok ? std::max(1, wavefront_tail_max_ctas() / n_groups) : 0;
     const bool async_ok = coop && async_env && !timing && !passes_only;
+    // Early hand-over of the pixels that lag furthest behind (persist.cu: launch_wavefront_detach; B200RT_FLAG_WF_DETACH or
+    // B200RT_WF_DETACH=1 — a study path, off by default): after B200RT_WF_DETACH_AT passes (default 36) the B200RT_WF_DETACH_SLOTS
+    // (default 12 288 per device, shared by the groups) slowest pixels of a group go to a barrier-free kernel of
+    // B200RT_WF_DETACH_CTAS CTAs per SM (default 2, shared by the groups) on a stream of its own.
+    const long long detach_at = env_ll("B200RT_WF_DETACH_AT", 36);
+    const unsigned int detach_budget = (unsigned int)std::max(0ll, env_ll("B200RT_WF_DETACH_SLOTS", 12288) / n_groups);
+    const int detach_ctas = (int)std::max(1ll, env_ll("B200RT_WF_DETACH_CTAS", 2) * n_sm / n_groups);
+    const bool detach_ok = tail_ok && !async_ok && detach_at > 0 && detach_budget > 0u && ((P.flags & B200RT_FLAG_WF_DETACH) || env_ll("B200RT_WF_DETACH", 0) != 0);
     const int async_ctas = async_ok ? std::max(1, wavefront_async_max_ctas() / n_groups) : 0;
     // one of the two for group g: launches the barrier-free kernel that finishes the group behind whatever is queued on its stream
     auto group_async = [&](int g) { return async_ok && groups[g].amem.ray_ring != nullptr && wavefront_async_fits(groups[g].buf.n_slots); };
@@ -346,8 +354,8 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
         // results carry the slot's shading-step count as a stamp (async.cu): every frame starts the count somewhere else, so that
         // what an earlier frame left in the result records cannot pass for this frame's
         static unsigned int frame_nonce = 0u;
-        R.P.stamp0 = (int)((frame_nonce += 1000003u) & 0x7ffffffu);
-        R.parity = 0; R.it = 0; R.poll_it = 0; R.poll_pending = false; R.forked = false; R.barrier_free = false;
+        R.P.stamp0 = (int)((frame_nonce += 1000003u) & kWfSeqMask);
+        R.parity = 0; R.it = 0; R.poll_it = 0; R.poll_pending = false; R.forked = false; R.barrier_free = false; R.detach = false; R.detached = false;
         R.slot_grid = (G.buf.n_slots + 255) / 256;
         R.finished = R.slot_grid <= 0;
         if (err != cudaSuccess) { R.finished = true; continue; }
@@ -362,6 +370,9 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
         launches++;
         const bool as = group_async(g);
         R.barrier_free = as || tail_ok;
+        // worth it when the chain is long and the group much larger than what is taken out of it
+        R.detach = detach_ok && !as && G.dmem.list != nullptr && (long long)G.buf.n_slots > 4ll * detach_budget && detach_budget <= (unsigned int)G.dmem.list_words &&
+                   (long long)(P.sample_end - P.sample_begin) * (P.max_bounces + 1) >= 4 * detach_at;
         R.tail_below = as ? (unsigned int)std::min<long long>(async_cap, (long long)G.buf.n_slots * async_pct / 100)
                           : (unsigned int)std::min<long long>(tail_cap, (long long)G.buf.n_slots * tail_pct / 100);
         if (R.barrier_free && G.buf.n_slots <= (as ? async_min : tail_min))
@@ -419,6 +430,17 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
             if (timing) cudaEventRecord(tev[1], G.stream);
             if (tln) { tll.e1 = tln->used; cudaEventRecord(tln->take(), G.stream); }
             R.parity ^= 1;
+            if (R.detach && !R.detached && R.it + 1 == detach_at)
+            {
+                // between this trace pass and its shade pass: the lagging pixels' results wait for the barrier-free kernel
+                WfTimeline::Launch tlt = { g, 0, 0, 0 };
+                if (tln) { tlt.e0 = tln->used; cudaEventRecord(tln->take(), G.stream); }
+                WF_TRY(launch_wavefront_detach(S, R.P, G.buf, G.dmem, detach_budget, std::min(detach_ctas, G.dmem.ctas), fb_in_rowmajor, out_tiles, G.stream,
+                                               G.detach_stream, G.detach_ready));
+                if (tln) { tlt.e1 = tln->used; cudaEventRecord(tln->take(), G.detach_stream); tln->tails.push_back(tlt); }
+                R.detached = true;
+                launches += 4;
+            }
             wf_shade<<<(G.buf.n_slots + WF_SHADE_BLOCK - 1) / WF_SHADE_BLOCK, WF_SHADE_BLOCK, 0, G.stream>>>(S, R.P, G.buf, fb_in_rowmajor, out_tiles, R.parity);
             if (tln) { tll.e2 = tln->used; cudaEventRecord(tln->take(), G.stream); tln->launches.push_back(tll); }
             launches += 2;
@@ -451,6 +473,12 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
         const cudaError_t e1 = cudaEventRecord(G.join_event, G.stream);
         const cudaError_t e2 = e1 == cudaSuccess ? cudaStreamWaitEvent(stream, G.join_event, 0) : e1;
         if (err == cudaSuccess && e2 != cudaSuccess) err = e2;
+        if (run[g].detached)
+        {
+            const cudaError_t e3 = cudaEventRecord(G.detach_join, G.detach_stream);
+            const cudaError_t e4 = e3 == cudaSuccess ? cudaStreamWaitEvent(stream, G.detach_join, 0) : e3;
+            if (err == cudaSuccess && e4 != cudaSuccess) err = e4;
+        }
     }
 #undef WF_TRY
     if (timing)

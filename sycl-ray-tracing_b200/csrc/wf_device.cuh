@@ -7,7 +7,10 @@
 
 namespace b200rt {
 
-enum { WF_ALIVE = 1, WF_PENDING = 2, WF_TERMINATED = 4, WF_DONE = 8 };
+enum { WF_ALIVE = 1, WF_PENDING = 2, WF_TERMINATED = 4, WF_DONE = 8,
+       WF_DETACHED = 16 };        // the slot left the passes: a barrier-free kernel runs it to the end (wavefront.cu, persist.cu)
+constexpr int kWfSeqShift = 8;    // bits 8..31 of a slot's flag word: its shading-step count (the stamp of its rays' results)
+constexpr unsigned int kWfSeqMask = 0xffffffu;
 
 // Loads of per-slot integrator state (WfBuffers) go to L2 (ld.global.cg), never through L1: in the barrier-free kernels
 // (async.cu) a slot is shaded and its rays are traced by whichever warps of the machine take them, and L1 is not coherent
@@ -81,8 +84,8 @@ __device__ __forceinline__ bool wf_slot_pixel(const RenderParams& P, int slot, i
 #endif
     const int unit = slot >> 5, lane = slot & 31;
     const int k = unit >> 3, sub = unit & 7;
-    const int tile_id = P.rank + k * P.world;
-    const int tx = tile_id % P.tiles_x, ty = tile_id / P.tiles_x;
+    int tx, ty;
+    tile_xy(P.rank + k * P.world, P.tiles_x, P.tile_skew, tx, ty);
     x = tx * kTileDim + (sub & 1) * kPatchW + (lane & 7);
     y = ty * kTileDim + (sub >> 1) * kPatchH + (lane >> 3);
     return x < P.cam.w && y < P.cam.h;
@@ -113,7 +116,7 @@ __device__ __forceinline__ void wf_begin_pixel(const RenderParams& P, const WfBu
     B.final_c[slot] = resume ? P.acc_sum[out_index] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     B.sample_c[slot] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
     B.thr[slot] = make_float4(1.0f, 1.0f, 1.0f, 0.0f);
-    B.flags[slot] = WF_ALIVE | (int)(((unsigned int)P.stamp0 & 0x7ffffffu) << 4);
+    B.flags[slot] = WF_ALIVE | (int)(((unsigned int)P.stamp0 & kWfSeqMask) << kWfSeqShift);
 }
 
 // what one shading step of a slot produced: which of its ray slots (0..3 side rays, 4 path ray) hold a ray to trace now
@@ -138,7 +141,7 @@ __device__ __forceinline__ ShadeOut wf_shade_slot(const SceneDev& S, const Rende
     float4 t4 = wf_ld(B.thr + slot), s4 = wf_ld(B.sample_c + slot);
     col throughput = CO(t4.x, t4.y, t4.z), sample_color = CO(s4.x, s4.y, s4.z);
     // the upper bits of the slot's flag word count its shading steps: the stamp its rays' results must carry (async.cu)
-    const unsigned int seq = (unsigned int)flags_in >> 4;
+    const unsigned int seq = (unsigned int)flags_in >> kWfSeqShift;
     int flags = flags_in & 15;
     bool finish = false;
     const bool trace_light_brdf = S.any_emissive_material || !(P.flags & B200RT_FLAG_SKIP_DEAD_RAYS);
@@ -279,7 +282,7 @@ __device__ __forceinline__ ShadeOut wf_shade_slot(const SceneDev& S, const Rende
     B.bounce[slot] = bounce;
     B.thr[slot] = make_float4(throughput.r, throughput.g, throughput.b, 0.0f);
     B.sample_c[slot] = make_float4(sample_color.r, sample_color.g, sample_color.b, 0.0f);
-    flags |= (int)(((seq + 1u) & 0x7ffffffu) << 4);
+    flags |= (flags_in & WF_DETACHED) | (int)(((seq + 1u) & kWfSeqMask) << kWfSeqShift);
     B.flags[slot] = flags;
     R.flags = flags;
     return R;
@@ -604,7 +607,7 @@ __device__ __forceinline__ void coop_trace_queue(const SceneDev& S, const WfBuff
                 const int slot = (int)(ent >> 3), k = (int)(ent & 7u);
                 r = (size_t)k * n + slot;
                 const float4 ro4 = wf_ld(B.ray_o + r), rd4 = wf_ld(B.ray_d + r);
-                stamp = (unsigned int)wf_ld(B.flags + slot) >> 4;
+                stamp = (unsigned int)wf_ld(B.flags + slot) >> kWfSeqShift;
                 const int kind = __float_as_int(rd4.w);
                 mode = kind == SIDE_SHADOW ? TRACE_SHADOW : (kind == SIDE_CLOSEST_LIGHT ? TRACE_CLOSEST : TRACE_ANY);
                 const int tmode = spheres ? TRACE_CLOSEST : mode;

@@ -1,5 +1,5 @@
 """Multi-GPU frame rendering: one process per GPU (torchrun), scene replicated, image cut into interleaved 16x16 tiles
-(tile_id % world == rank), one gather of the per-rank tile buffers to rank 0 per frame (NCCL over NVLink when the
+(tile number % world == rank), one gather of the per-rank tile buffers to rank 0 per frame (NCCL over NVLink when the
 tensors are CUDA tensors), then the un-tile kernel. The reference has no counterpart (it is one OpenMP process,
 render_kernel.cpp:198); pixels are independent (per-pixel seed 31 + x*y*spp, :77), so there is no exchange step during
 rendering and the N-rank image equals the 1-rank image bit for bit.
@@ -13,6 +13,21 @@ import numpy as np
 
 TILE = 16
 TILE_PX = 256
+
+
+import os
+
+TILE_SKEW = max(0, int(os.environ.get("B200RT_TILE_SKEW", "0")))      # csrc/device_types.h tile_xy (0 = row-major, the default: a skew measured slower): tile number L = ty * tiles_x + (tx + TILE_SKEW * ty) % tiles_x
+
+
+def tile_xy(L, tiles_x):
+    """Tile number -> (tx, ty) (device_types.h tile_xy); works on ints and numpy arrays."""
+    ty = L // tiles_x
+    return (L % tiles_x - TILE_SKEW * ty) % tiles_x, ty
+
+
+def tile_number(tx, ty, tiles_x):
+    return ty * tiles_x + (tx + TILE_SKEW * ty) % tiles_x
 
 
 def tiles_for_rank(w: int, h: int, rank: int, world: int) -> int:
@@ -31,8 +46,7 @@ def tile_slot_coords(w: int, h: int, rank: int, world: int, tiles_padded: int) -
     lx = (sub & 1) * 8 + (lane & 7)
     ly = (sub >> 1) * 4 + (lane >> 3)
     for k in range(n):
-        tile = rank + k * world
-        tx, ty = tile % tiles_x, tile // tiles_x
+        tx, ty = tile_xy(rank + k * world, tiles_x)
         x, y = tx * TILE + lx, ty * TILE + ly
         ok = (x < w) & (y < h)
         out[k * TILE_PX:(k + 1) * TILE_PX, 0] = np.where(ok, x, -1)

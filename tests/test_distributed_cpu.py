@@ -69,7 +69,8 @@ def test_gloo_tile_gather_reassembles_frame(tmp_path, world, w, h):
     assert np.array_equal(img[..., 0], xs) and np.array_equal(img[..., 1], ys)
     assert np.array_equal(img[..., 3], ys * w + xs)
     tiles_x = (w + 15) // 16
-    owner = ((ys // 16) * tiles_x + xs // 16) % world
+    from sycl_ray_tracing_b200 import distributed as D
+    owner = D.tile_number(xs // 16, ys // 16, tiles_x) % world
     assert np.array_equal(img[..., 2], owner), "pixel written by the rank that owns its tile"
     acc = np.load(out.replace(".npy", "_acc.npy"))
     assert np.array_equal(acc, img + 1000.0), "framebuffer += gathered tiles, once per frame"

@@ -581,6 +581,18 @@ def test_async_continuation_equals_passes_bit_for_bit(rt, golden_scenes, golden_
         skip_p, st_sp = sc.render(c3["camera"], w, h, spp, 8, flags=rt.FLAG_WF_PASSES_ONLY | rt.FLAG_SKIP_DEAD_RAYS)
         skip_a, st_sa = sc.render(c3["camera"], w, h, spp, 8, flags=rt.FLAG_WF_ASYNC | rt.FLAG_SKIP_DEAD_RAYS)
         assert np.array_equal(bits(pas), bits(skip_a)) and st_sp["rays"] == st_sa["rays"] < st_p["rays"]
+    # study path B200RT_FLAG_WF_DETACH: the pixels that lag furthest behind leave the passes after 36 of them for a barrier-free kernel on
+    # a stream of its own: same frame and ray count as the default, as passes only, as the megakernel; also as one rank of 2
+    for kw in (dict(), dict(rank=1, world=2)):
+        det, st_d = sc.render(c3["camera"], 960, 540, 24, 8, flags=rt.FLAG_WF_DETACH, **kw)
+        nod, st_n = sc.render(c3["camera"], 960, 540, 24, 8, **kw)
+        pas, st_p = sc.render(c3["camera"], 960, 540, 24, 8, flags=rt.FLAG_WF_PASSES_ONLY, **kw)
+        assert np.array_equal(bits(det), bits(nod)) and np.array_equal(bits(det), bits(pas)), kw
+        assert st_d["rays"] == st_n["rays"] == st_p["rays"], (kw, st_d["rays"], st_n["rays"], st_p["rays"])
+        assert st_d["gpu_launches"] != st_n["gpu_launches"], "the detach path ran"
+    mega, st_m = sc.render(c3["camera"], 960, 540, 24, 8, integrator=rt.INTEGRATOR_MEGAKERNEL)
+    det, st_d = sc.render(c3["camera"], 960, 540, 24, 8, flags=rt.FLAG_WF_DETACH)
+    assert np.array_equal(bits(det), bits(mega)) and st_d["rays"] == st_m["rays"]
     # one rank of 8 of the 1080p frame (the shape the continuation exists for), twice: the rings are re-armed per launch
     want, st_w = sc.render(c3["camera"], 1920, 1080, 3, 8, rank=5, world=8, flags=rt.FLAG_WF_PASSES_ONLY)
     for _ in range(2):

@@ -18,8 +18,8 @@ w, h = (3840, 2160) if workload == "c5" else (1920, 1080)
 s = {"c5": scenes.c5_scene, "c3k": scenes.c3_knot_scene if hasattr(scenes, "c3_knot_scene") else scenes.c3_scene}.get(workload, scenes.c3_scene)()
 sc = rt.Scene(s["tri9"], s["mat_idx"], s["mats10"], s["emissive"], skysphere=s["env"])
 fb = rt.Image(w, h, pinned=True).pixels
-KNOBS = ("B200RT_WF_ASYNC", "B200RT_WF_ASYNC_PCT", "B200RT_WF_ASYNC_CAP", "B200RT_WF_ASYNC_MIN", "B200RT_WF_ASYNC_SHADERS", "B200RT_WF_GROUPS",
-         "B200RT_WF_TAIL_PCT", "B200RT_WF_TAIL_CAP")
+KNOBS = ("B200RT_WF_DETACH_AT", "B200RT_WF_DETACH_SLOTS", "B200RT_WF_DETACH_CTAS", "B200RT_WF_ASYNC", "B200RT_WF_ASYNC_PCT", "B200RT_WF_ASYNC_CAP", "B200RT_WF_ASYNC_MIN", "B200RT_WF_ASYNC_SHADERS", "B200RT_WF_GROUPS",
+         "B200RT_WF_TAIL_PCT", "B200RT_WF_TAIL_CAP", "B200RT_WF_TAIL_MIN")
 
 configs = []
 def add(name, world, flags=None, **env):
@@ -41,6 +41,19 @@ for world in (1, 8):
         add("async from the start, 1 group (profiling shape)", world, WF_ASYNC_MIN=10000000, WF_GROUPS=1, WF_ASYNC_SHADERS=os.environ.get("PROF_SHADERS", "1/4"))
     if "default" in sets:
         add("default (passes + per-warp tail)", world, 0)
+    if "detach_quick" in sets:
+        add("no detach", world, 0)
+        for slots in (6144, 12288):
+            for ctas in (1, 2):
+                add(f"detach at 36 slots {slots} ctas/SM {ctas}", world, rt.FLAG_WF_DETACH, WF_DETACH_AT=36, WF_DETACH_SLOTS=slots, WF_DETACH_CTAS=ctas)
+        add("all tail from the start (groups <= 10M)", world, 0, WF_TAIL_MIN=10000000)
+    if "detach" in sets:
+        add("no detach", world, 0)
+        add("detach default", world, rt.FLAG_WF_DETACH)
+        for at in (18, 36, 72):
+            for slots in (6144, 12288, 24576, 49152):
+                for ctas in (1, 2, 3):
+                    add(f"detach at {at} slots {slots} ctas/SM {ctas}", world, rt.FLAG_WF_DETACH, WF_DETACH_AT=at, WF_DETACH_SLOTS=slots, WF_DETACH_CTAS=ctas)
     if "quick" in sets:
         add("warp tail (round-2 default)", world, 0)
         for sh in ("1/4", "1/3"):
