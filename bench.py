@@ -325,6 +325,8 @@ def main():
             if not verified:
                 raise SystemExit(f"bench.py --verify: the {world}-rank frame differs from the 1-rank frame")
         barrier()
+        warm_step()            # rank 0's 1-rank frame re-sized the integrator's buffers: size them for this world again, outside the timed steps
+        barrier()
 
     sampler = ClockSampler(local_rank)
     sampler.start()
