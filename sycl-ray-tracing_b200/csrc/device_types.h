@@ -28,9 +28,9 @@ B200RT_HD inline void tile_xy(int L, int tiles_x, int skew, int& tx, int& ty)
 {
     ty = L / tiles_x;
     const int c = L - ty * tiles_x;
-    tx = (c + tiles_x - (int)(((long long)skew * ty) % tiles_x)) % tiles_x;
+    tx = skew ? (c + tiles_x - (skew % tiles_x) * (ty % tiles_x) % tiles_x) % tiles_x : c;      // (tiles_x <= 2^15: the product fits)
 }
-B200RT_HD inline int tile_number(int tx, int ty, int tiles_x, int skew) { return ty * tiles_x + (int)((tx + (long long)skew * ty) % tiles_x); }
+B200RT_HD inline int tile_number(int tx, int ty, int tiles_x, int skew) { return ty * tiles_x + (skew ? (tx + (skew % tiles_x) * (ty % tiles_x) % tiles_x) % tiles_x : tx); }
 
 struct MaterialDev   // SimpleMaterial (simple_material.h:6-13) without the junk alphas, two float4
 {

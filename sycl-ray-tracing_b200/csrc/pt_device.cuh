@@ -643,16 +643,6 @@ __device__ __forceinline__ float ggx_d(float alpha, float NoH)
 __device__ __forceinline__ float g1_schlick(float k, float dp) { return dp / (dp * (1.0f - k) + k); }
 __device__ __forceinline__ float power_heuristic(float a, float b) { float a2 = a * a; return a2 / (a2 + b * b); }
 
-__device__ __forceinline__ float ct_pdf(const MaterialDev& m, v3 view, v3 to_light, v3 n)      // :247-258
-{
-    v3 h = normalize(view + to_light);
-    float alpha = m.roughness * m.roughness;
-    float VoH = smax(0.0f, dot(view, h));
-    float NoH = smax(0.0f, dot(n, h));
-    float D = ggx_d(alpha, NoH);
-    return D * NoH / (4.0f * VoH);
-}
-
 // B200RT_CT_NOINLINE: the BRDF evaluation / sampling bodies become real functions (5 + 3 call sites per surface interaction):
 // the shade kernel shrinks and stalls less on instruction fetch
 #ifdef B200RT_CT_NOINLINE
@@ -665,15 +655,21 @@ __device__ __forceinline__ float ct_pdf(const MaterialDev& m, v3 view, v3 to_lig
 #else
 #define B200RT_CT_INLINE2 __forceinline__
 #endif
-__device__ B200RT_CT_INLINE2 col ct_terms(const MaterialDev& m, float NoV, float NoL, float NoH, float VoH, float* pdf_out)   // :272-298 / :424-448
+// D = ggx_d(roughness^2, NoH), computed by the caller (the light- and env-sample paths need it for the pdf whether or not the BRDF
+// itself is evaluated: one double-precision division per pair instead of two)
+__device__ B200RT_CT_INLINE2 col ct_terms(const MaterialDev& m, float NoV, float NoL, float NoH, float VoH, float D, float* pdf_out)   // :272-298 / :424-448
 {
     const float metalness = m.metalness;
     const float alpha = m.roughness * m.roughness;
     const float f04 = 0.04f * (1.0f - metalness);
     const col F0 = CO(f04 + m.dr * metalness, f04 + m.dg * metalness, f04 + m.db * metalness);
-    const float p5 = powf((1.0f - VoH), 5.0f);
+    // pow(1 - VoH, 5.0f) (:219): three double multiplications and one rounding — the correctly rounded value in all but ~1e-9 of the
+    // cases, which is what glibc's powf returns to the reference; CUDA's powf is a 70-instruction routine (9.4 % of the shading step's
+    // instructions, five evaluations per surface interaction) that is off by one ulp in 3 % of the cases
+    const double omv = (double)(1.0f - VoH);
+    const double omv2 = omv * omv;
+    const float p5 = (float)((omv2 * omv2) * omv);
     const col F = CO(F0.r + (1.0f + -F0.r) * p5, F0.g + (1.0f + -F0.g) * p5, F0.b + (1.0f + -F0.b) * p5);   // fresnel_schlick :218-221
-    const float D = ggx_d(alpha, NoH);
     const float k = alpha / 2.0f;
     const float G = g1_schlick(k, NoL) * g1_schlick(k, NoV);                                               // :240-245
     const float kd0 = 1.0f - metalness;
@@ -684,14 +680,18 @@ __device__ B200RT_CT_INLINE2 col ct_terms(const MaterialDev& m, float NoV, float
     return diffuse_part + specular_part;
 }
 
-__device__ __forceinline__ col ct_brdf(const MaterialDev& m, v3 to_light, v3 view, v3 n)      // :260-301
+// cook_torrance_brdf (:260-301) and cook_torrance_brdf_pdf (:247-258) of the same pair of directions, as sample_light_sources and
+// sample_environment_map call them one after the other: the half vector, its two cosines and D are the same values in both
+__device__ __forceinline__ col ct_brdf_and_pdf(const MaterialDev& m, v3 to_light, v3 view, v3 n, float& pdf)
 {
     v3 h = normalize(view + to_light);
     float NoV = smax(0.0f, dot(n, view));
     float NoL = smax(0.0f, dot(n, to_light));
     float NoH = smax(0.0f, dot(n, h));
     float VoH = smax(0.0f, dot(h, view));
-    if (NoV > 0.0f && NoL > 0.0f && NoH > 0.0f) return ct_terms(m, NoV, NoL, NoH, VoH, nullptr);
+    const float D = ggx_d(m.roughness * m.roughness, NoH);
+    pdf = D * NoH / (4.0f * VoH);
+    if (NoV > 0.0f && NoL > 0.0f && NoH > 0.0f) return ct_terms(m, NoV, NoL, NoH, VoH, D, nullptr);
     return CO(0.0f, 0.0f, 0.0f);
 }
 
@@ -704,8 +704,12 @@ __device__ B200RT_CT_INLINE col ct_sample(const MaterialDev& m, v3 view, v3 n, v
     const float rand2 = xs_float(rng);
     const float phi = 2.0f * B200RT_PI_F * rand1;
     const float theta = acosf((1.0f - rand2) / (rand2 * (alpha * alpha - 1.0f) + 1.0f));   // no sqrt: the reference's own variant (:404)
-    const float sin_theta = sinf(theta);
-    v3 local = V(cosf(phi) * sin_theta, sinf(phi) * sin_theta, cosf(theta));
+    // sincosf returns exactly sinf / cosf of the argument (checked on 1e8 arguments in [0, 2 pi]: no differing bit) for one range
+    // reduction instead of two
+    float sin_theta, cos_theta, sin_phi, cos_phi;
+    sincosf(theta, &sin_theta, &cos_theta);
+    sincosf(phi, &sin_phi, &cos_phi);
+    v3 local = V(cos_phi * sin_theta, sin_phi * sin_theta, cos_theta);
     v3 mn = rotate_around_normal(n, local);
     if (dot(mn, n) < 0.0f) return CO(0.0f, 0.0f, 0.0f);
     v3 to_light = normalize((2.0f * dot(mn, view)) * mn - view);
@@ -714,7 +718,7 @@ __device__ B200RT_CT_INLINE col ct_sample(const MaterialDev& m, v3 view, v3 n, v
     float NoL = smax(0.0f, dot(n, to_light));
     float NoH = smax(0.0f, dot(n, mn));
     float VoH = smax(0.0f, dot(mn, view));
-    if (NoV > 0.0f && NoL > 0.0f && NoH > 0.0f) return ct_terms(m, NoV, NoL, NoH, VoH, &pdf);
+    if (NoV > 0.0f && NoL > 0.0f && NoH > 0.0f) return ct_terms(m, NoV, NoL, NoH, VoH, ggx_d(alpha, NoH), &pdf);
     return CO(0.0f, 0.0f, 0.0f);
 }
 
@@ -820,8 +824,8 @@ __device__ __forceinline__ void side_light_sample(const SceneDev& S, const Surfa
     if (!(dot_light > 0.0f)) return;
     light_pdf *= dist * dist;
     light_pdf /= dot_light;
-    const col brdf = ct_brdf(sf.m, sdn, sf.view, sf.n);
-    const float bp = ct_pdf(sf.m, sf.view, sdn, sf.n);
+    float bp;
+    const col brdf = ct_brdf_and_pdf(sf.m, sdn, sf.view, sf.n, bp);
     if (!(bp != 0.0f)) return;
     const MaterialDev em = S.mats[__ldg(S.mat_idx + em_tri)];
     const float w = power_heuristic(light_pdf, bp);
@@ -883,17 +887,18 @@ __device__ __forceinline__ void side_env_sample(const SceneDev& S, const Surface
     const float v = (float)y / (float)S.env_h;
     const float phi = (float)((double)(u * 2.0f) * B200RT_PI_D);             // double in the reference (:578-579)
     const float theta = (float)((double)v * B200RT_PI_D);
-    const float sin_theta = sinf(theta);
-    const float cos_theta = cosf(theta);
-    const v3 dir = V(-sin_theta * cosf(phi), -cos_theta, -sin_theta * sinf(phi));
+    float sin_theta, cos_theta, sin_phi, cos_phi;
+    sincosf(theta, &sin_theta, &cos_theta);
+    sincosf(phi, &sin_phi, &cos_phi);
+    const v3 dir = V(-sin_theta * cos_phi, -cos_theta, -sin_theta * sin_phi);
     const float cosine_term = dot(sf.n, dir);
     if (!(cosine_term > 0.0f)) return;
     const int idx = env_offset(S, x, y);
     const col radiance = env_texel(S, idx);
     float env_pdf = (float)(0.3086 * (double)radiance.r + 0.6094 * (double)radiance.g + 0.0820 * (double)radiance.b) / total;   // image.h:80-85
     env_pdf = (float)((double)((env_pdf * (float)S.env_w) * (float)S.env_h) / ((double)2.0f * B200RT_PI_D * B200RT_PI_D * (double)sin_theta));   // :595
-    const col brdf = ct_brdf(sf.m, dir, sf.view, sf.n);
-    const float brdf_pdf = ct_pdf(sf.m, sf.view, dir, sf.n);
+    float brdf_pdf;
+    const col brdf = ct_brdf_and_pdf(sf.m, dir, sf.view, sf.n, brdf_pdf);
     const float w = power_heuristic(env_pdf, brdf_pdf);
     r.weight = (((brdf * cosine_term) * w) * radiance) / env_pdf;          // :602
     r.o = sf.p + 1.0e-4f * sf.n; r.d = dir; r.kind = SIDE_OCCLUSION;
