@@ -22,6 +22,10 @@
 // publishes nothing — its result record carries the slot's shading-step count as a stamp (one 16-byte store is single-copy
 // atomic), and a shader that finds a chunk's count at zero only shades the slots whose expected results all carry the right
 // stamp (a result still in flight just waits for the next look). Per-slot state is read with loads that bypass L1 (wf_ld).
+//
+// Status: a study path (B200RT_FLAG_WF_ASYNC), bit-identical and tested, NOT the default — a group run this way sustains 1.4 Grays/s
+// against the passes' 2.4, because the 6 000-instruction shading step and the traversal loop then share every SM's instruction
+// cache (5.3 "no instruction" stalls per issue; DESIGN.md 4.3, profiles/r2d_*).
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>

@@ -418,12 +418,12 @@ __device__ __forceinline__ void coop_drain(const SceneDev& S, CoopWarp& W, const
     qtris -= lim;
 }
 
-// ---- device-wide ticket rings (async.cu) ---------------------------------------------------------------------------------------------
+// ---- device-wide ticket ring (async.cu) ----------------------------------------------------------------------------------------------
 // A multi-producer / multi-consumer ring in global memory. Producers reserve indices with one atomicAdd per warp on ctrl[1]
 // and store (lap tag << 25) | payload; consumers draw TICKETS — indices, possibly of entries that do not exist yet — with one
 // atomicAdd per warp on ctrl[0] and poll their own word until the entry with their ticket's lap tag shows up, then put
 // kRingEmpty back. Nobody waits on anybody in particular: a producer only waits for the consumer of the same word one lap
-// (>= 2^17 entries) earlier, a consumer only polls (once per iteration of its own work loop), so the rings cannot deadlock a
+// (>= 2^20 entries) earlier, a consumer only polls (once per iteration of its own work loop), so the rings cannot deadlock a
 // persistent grid whatever part of it is resident. An entry is handed to the oldest waiting ticket: FIFO, no claim races.
 constexpr unsigned int kRingEmpty = 0xffffffffu;
 constexpr int kRingPayloadBits = 25;                      // (slot << 3) | ray index k: slots < 2^22 per tile group
