@@ -114,6 +114,22 @@ def test_tiles_for_rank_partition(rt):
     assert rt.tiles_for_rank(0, 10, 0, 1) == 0 and rt.tiles_for_rank(10, 10, 2, 2) == 0
 
 
+def test_tile_numbering_is_a_bijection_for_any_skew(monkeypatch):
+    """device_types.h tile_xy / tile_number (mirrored in distributed.py): tile number <-> (tx, ty) is one-to-one whatever the
+    skew (B200RT_TILE_SKEW), and skew 0 is plain row-major numbering."""
+    from sycl_ray_tracing_b200 import distributed as D
+    for skew in (0, 1, 5, 13, 120, 1000):
+        monkeypatch.setattr(D, "TILE_SKEW", skew)
+        for tiles_x, tiles_y in ((120, 68), (7, 5), (1, 9), (240, 135)):
+            L = np.arange(tiles_x * tiles_y)
+            tx, ty = D.tile_xy(L, tiles_x)
+            assert ((0 <= tx) & (tx < tiles_x) & (0 <= ty) & (ty < tiles_y)).all()
+            assert np.array_equal(D.tile_number(tx, ty, tiles_x), L)
+            assert len(set(zip(tx.tolist(), ty.tolist()))) == len(L)
+            if skew == 0:
+                assert np.array_equal(tx, L % tiles_x) and np.array_equal(ty, L // tiles_x)
+
+
 def test_camera_presets_and_image_mirror(rt, golden_cameras):
     for name, key in [("CORNELL_BOX_CAMERA", "cornell"), ("GANESHA_CAMERA", "ganesha"), ("ITE_ORB_CAMERA", "ite_orb"),
                       ("PBRT_DRAGON_CAMERA", "dragon"), ("MIS_CAMERA", "mis")]:
