@@ -344,26 +344,33 @@ int ensure_wavefront(b200rt_scene* s, const RenderParams& P)
             CU(wf_alloc(s, &w.ray_o, 5 * n)); CU(wf_alloc(s, &w.ray_d, 5 * n)); CU(wf_alloc(s, &w.side_w, 4 * n));
             CU(wf_alloc(s, &w.res, 5 * n));
             CU(wf_alloc(s, &w.queue, 5 * n)); CU(wf_alloc(s, &w.counters, 8)); CU(wf_alloc(s, &w.rays_total, 1));
-            // memory of the early hand-over of the group's lagging pixels (persist.cu): control words, the list, the tail kernel's private queues
-            WfDetachMem& dm = s->wf[g].dmem;
-            dm = WfDetachMem{};
-            if (s->dev.has_wide)
-            {
-                dm.list_words = 65536; dm.ctas = wavefront_tail_max_ctas();
-                CU(wf_alloc(s, &dm.ctl, (size_t)wavefront_detach_ctl_words())); CU(wf_alloc(s, &dm.list, (size_t)dm.list_words));
-                CU(wf_alloc(s, &dm.queue, (size_t)wavefront_detach_queue_words(dm.ctas)));
-            }
-            // rings of the barrier-free continuation (async.cu); without them the group finishes with wf_tail
-            WfAsyncMem& a = s->wf[g].amem;
-            a = WfAsyncMem{};
-            if (s->dev.has_wide && wavefront_async_fits(most))
-            {
-                a.ray_log2 = wavefront_async_ray_log2(most); a.chunk_words = wavefront_async_chunk_words(most);
-                CU(wf_alloc(s, &a.ray_ring, (size_t)1 << a.ray_log2)); CU(wf_alloc(s, &a.ctrl, 64));
-                CU(wf_alloc(s, &a.chunk_cnt, (size_t)a.chunk_words)); CU(wf_alloc(s, &a.chunk_live, (size_t)a.chunk_words));
-            }
+            s->wf[g].dmem = WfDetachMem{};          // the study paths' memory is allocated below, when a frame asks for them
+            s->wf[g].amem = WfAsyncMem{};
         }
         s->wf_groups = G;
+    }
+    // study paths, only when a frame asks for them: the early hand-over of a group's lagging pixels (persist.cu: control
+    // words, the list, the tail kernel's private queues) and the ray ring + per-chunk counts of the cross-warp continuation (async.cu);
+    // sized for the groups' capacity, freed with the rest
+    const auto env_on = [](const char* name) { const char* e = getenv(name); return e && atoi(e) != 0; };
+    const bool want_detach = s->dev.has_wide && ((P.flags & B200RT_FLAG_WF_DETACH) || env_on("B200RT_WF_DETACH"));
+    const bool want_async = s->dev.has_wide && ((P.flags & B200RT_FLAG_WF_ASYNC) || env_on("B200RT_WF_ASYNC"));
+    for (int g = 0; g < G; g++)
+    {
+        WfDetachMem& dm = s->wf[g].dmem;
+        if (want_detach && !dm.list)
+        {
+            dm.list_words = 65536; dm.ctas = wavefront_tail_max_ctas();
+            CU(wf_alloc(s, &dm.ctl, (size_t)wavefront_detach_ctl_words())); CU(wf_alloc(s, &dm.list, (size_t)dm.list_words));
+            CU(wf_alloc(s, &dm.queue, (size_t)wavefront_detach_queue_words(dm.ctas)));
+        }
+        WfAsyncMem& a = s->wf[g].amem;
+        if (want_async && !a.ray_ring && wavefront_async_fits(s->wf_cap[g]))
+        {
+            a.ray_log2 = wavefront_async_ray_log2(s->wf_cap[g]); a.chunk_words = wavefront_async_chunk_words(s->wf_cap[g]);
+            CU(wf_alloc(s, &a.ray_ring, (size_t)1 << a.ray_log2)); CU(wf_alloc(s, &a.ctrl, 64));
+            CU(wf_alloc(s, &a.chunk_cnt, (size_t)a.chunk_words)); CU(wf_alloc(s, &a.chunk_live, (size_t)a.chunk_words));
+        }
     }
     for (int g = 0; g < G; g++)
     {

@@ -15,6 +15,7 @@
 // No RNG draw depends on a trace result, which is what allows a whole surface interaction — all four side
 // rays and the continuation ray — to be generated in one shade pass and traced in one trace pass.
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <utility>
@@ -353,8 +354,8 @@ cudaError_t run_wavefront(const SceneDev& S, const RenderParams& P, const WfGrou
         R.P.n_rank_tiles = G.buf.n_slots / kTilePixels;
         // results carry the slot's shading-step count as a stamp (async.cu): every frame starts the count somewhere else, so that
         // what an earlier frame left in the result records cannot pass for this frame's
-        static unsigned int frame_nonce = 0u;
-        R.P.stamp0 = (int)((frame_nonce += 1000003u) & kWfSeqMask);
+        static std::atomic<unsigned int> frame_nonce{0u};        // (multi-device scenes render from one host thread per device)
+        R.P.stamp0 = (int)((frame_nonce.fetch_add(1000003u, std::memory_order_relaxed) + 1000003u) & kWfSeqMask);
         R.parity = 0; R.it = 0; R.poll_it = 0; R.poll_pending = false; R.forked = false; R.barrier_free = false; R.detach = false; R.detached = false;
         R.slot_grid = (G.buf.n_slots + 255) / 256;
         R.finished = R.slot_grid <= 0;
