@@ -254,6 +254,9 @@ cudaError_t launch_wavefront_tail(const SceneDev& S, const RenderParams& P, cons
 // shade pass, and one wf_tail launch on a stream of its own runs them to the end barrier-free (~1.6x faster per step when every ray
 // has a lane), while the passes go on for the others and end when THEIR slowest pixel ends. Same device functions, same per-pixel
 // RNG streams: the frame stays bit-identical.
+// Status: a study path (B200RT_FLAG_WF_DETACH), tested, NOT the default: the detached pixels do run faster (81 us per step for 256 of
+// them per group on one rank of 8), but the passes are bound by the bulk of the object's pixels, not by the few deepest, and slow down
+// when the detached kernels take a share of every SM — no net gain (profiles/r2g_detach_lagging_pixels_64spp.txt).
 constexpr int kLagBins = 1024;
 
 __global__ void __launch_bounds__(256) wf_lag_histogram(WfBuffers B, int sample_begin, unsigned int* hist)
